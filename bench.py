@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py -- reads SW-scored/sec of the per-locus read-scoring path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores
+
+A *step* is one pass of the whole hot path (CB lookup -> 2x Smith-Waterman per pair -> call -> count
+matrix -> triplets) over one synthetic shard of the BASELINE.json config-3 shape (100k SNV loci x 50k
+barcodes, 150 bp reads, 50x, consensus mode); the unit is the (read, locus) pair that reaches the
+aligner (main.rs:896-930).  With N GPUs every rank scores its own shard of that shape (loci shard across
+ranks with no data-path collective; weak scaling) and the finished triplets are assembled with one
+allgatherv over NCCL inside the timed region.
+
+`value`  : pairs/s with the staged shard already resident in HBM (vtx_submit_device + vtx_finish_device).
+`e2e`    : pairs/s through the host-facing C ABI from pinned HOST buffers (vtx_submit + vtx_finish), i.e.
+           with the host->device copy of the shard and the device->host copy of the triplets in the timed region.
+`roofline`: the dominant kernel (vtx_k_sw_pairs) against the measured HBM peak, from CUDA events recorded on
+           the engine's stream inside the library (vtx_last_timing), averaged over the timed steps.
+`cpu_baseline`: the oracle's C port of the reference algorithm timed on this box's host cores (bounded sample).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "reads_sw_scored_per_sec"
+UNIT = "pairs/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="vartrix_b200", choices=["vartrix_b200", "reference"])
+    ap.add_argument("--workload", default="config3", help="synth.CONFIGS key (config3 = the shape the metric is quoted on)")
+    ap.add_argument("--loci", type=int, default=0, help="override loci per GPU (0 = the config's)")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def workload_config(args, rank):
+    import vartrix_b200 as vb
+    cfg = dict(vb.synth.CONFIGS[args.workload])
+    if args.loci:
+        cfg["n_loci"] = args.loci
+    base_seed = cfg["seed"]
+    cfg["barcode_seed"] = 1000 + base_seed           # every rank sees the same barcode list
+    cfg["seed"] = base_seed + 7919 * rank           # ... and its own loci / reads
+    cfg["row_offset"] = rank * cfg["n_loci"]
+    return cfg
+
+
+def describe(args, cfg, world, info):
+    return {
+        "workload": f"{args.workload}: synthetic {cfg['n_loci']} {cfg['kind'].upper()} loci x {cfg['n_barcodes']} barcodes per GPU, "
+                    f"{info['read_len']} bp reads, {info['depth']}x depth, {cfg['scoring_method']} mode"
+                    + (", --umi" if cfg.get("umi") else ""),
+        "loci_per_gpu": cfg["n_loci"], "barcodes": cfg["n_barcodes"], "pairs_per_gpu": info["n_pairs"],
+        "candidates_per_gpu": info["n_cand"], "scoring_method": cfg["scoring_method"], "umi": bool(cfg.get("umi")),
+        "parallelism": f"loci sharded over {world} GPU(s), one allgatherv of triplets" if world > 1 else "1 GPU",
+        "l2_policy": "inputs larger than L2 (staged shard >> 126 MB), no explicit flush",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle's C port of the reference algorithm on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_sample_run(sb, bcs, cfg, n_loci_sample, threads):
+    """-> (pairs, seconds) of the oracle on the first n_loci_sample loci of the shard."""
+    from oracle import pipeline as P
+    sub = sb.shard(0, n_loci_sample)
+    ob = P.Batch(**{f: getattr(sub, f) for f in P.Batch.FIELDS}, n_rows=sub.n_rows).normalized()
+    obc = P.Barcodes(bcs.keys)
+    t0 = time.perf_counter()
+    res = P.run_batch(ob, obc, P.MODES[cfg["scoring_method"]], bool(cfg.get("umi")), n_threads=threads)
+    dt = time.perf_counter() - t0
+    return res.metrics["num_scored"], dt
+
+
+def cpu_baseline(sb, bcs, cfg, info, target_s):
+    threads = cpu_threads()
+    probe_loci = min(sb.n_loci, max(threads * 4, 64))
+    pairs, dt = cpu_sample_run(sb, bcs, cfg, probe_loci, threads)
+    rate = pairs / max(dt, 1e-9)
+    n_loci = int(min(sb.n_loci, max(probe_loci, target_s * rate / max(info["n_pairs"] / sb.n_loci, 1))))
+    pairs, dt = cpu_sample_run(sb, bcs, cfg, n_loci, threads)
+    return {"value": pairs / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"first {n_loci} loci of the shard ({pairs} pairs, {dt:.1f} s); full-matrix SW C port of the reference "
+                      f"algorithm (oracle/vtx_oracle.c), static locus chunks like main.rs:250-254, {threads} threads"}
+
+
+def run_reference(args):
+    rank, world, local = dist_env()
+    if rank != 0:
+        return 0
+    import vartrix_b200 as vb
+    cfg = workload_config(args, 0)
+    # a bounded sample of the same workload per step, sized so the whole run ends within a few minutes
+    threads = cpu_threads()
+    probe_cfg = dict(cfg); probe_cfg["n_loci"] = max(threads * 4, 64)
+    sb, bcs, info = vb.synth.make_shard(**probe_cfg)
+    pairs, dt = cpu_sample_run(sb, bcs, cfg, sb.n_loci, threads)
+    rate = pairs / dt
+    budget_s = 150.0 / max(1, args.steps + args.warmup)
+    n_loci = int(min(cfg["n_loci"], max(probe_cfg["n_loci"], min(budget_s, 20.0) * rate / (info["n_pairs"] / sb.n_loci))))
+    scfg = dict(cfg); scfg["n_loci"] = n_loci
+    sb, bcs, info = vb.synth.make_shard(**scfg)
+    for _ in range(args.warmup):
+        cpu_sample_run(sb, bcs, cfg, min(sb.n_loci, probe_cfg["n_loci"]), threads)
+    t_tot, p_tot = 0.0, 0
+    for _ in range(args.steps):
+        p, d = cpu_sample_run(sb, bcs, cfg, sb.n_loci, threads)
+        t_tot += d; p_tot += p
+    value = p_tot / t_tot
+    full_cfg = dict(cfg)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32", "data": "synthetic", "impl": "reference",
+        "config": describe(args, full_cfg, 1, dict(info, n_pairs=info["n_pairs"], n_cand=info["n_cand"])),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{n_loci} loci of the workload shape per step ({info['n_pairs']} pairs); C port of the reference "
+                                   f"algorithm (full-matrix SW), {threads} host threads; the Rust binary cannot be built here"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md recipe)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True); self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append([t.strip() for t in ln.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try: self.proc.wait(timeout=2)
+        except Exception: self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import vartrix_b200 as vb
+    from vartrix_b200 import _capi
+
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: vartrix_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    cfg = workload_config(args, rank)
+    sb, bcs, info = vb.synth.make_shard(**cfg)
+    n_pairs = info["n_pairs"]
+
+    stream = torch.cuda.Stream()
+    eng = vb.Engine(cfg["scoring_method"], umi=bool(cfg.get("umi")), device=local, stream=stream.cuda_stream)
+    eng.set_barcodes(bcs)
+    if world > 1:       # ship the NCCL unique id of the engine's own communicator over torch.distributed
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            uid = torch.frombuffer(bytearray(vb.Engine.comm_unique_id()), dtype=torch.uint8).clone()
+        uid = uid.cuda(); dist.broadcast(uid, 0)
+        eng.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
+
+    # device-resident copy of the shard (for `value`) and pinned host copy (for `e2e`)
+    dev, pinned = {}, {}
+    for f in vb.StagedBatch.FIELDS:
+        a = getattr(sb, f)
+        t = torch.from_numpy(a.view(np.uint8).reshape(-1) if a.dtype.itemsize > 1 else a.reshape(-1))
+        pinned[f] = t.pin_memory() if t.numel() else t
+        dev[f] = pinned[f].cuda(non_blocking=False) if t.numel() else t.cuda()
+    dbatch = sb.to_c()
+    hbatch = sb.to_c()
+    for f in vb.StagedBatch.FIELDS:
+        setattr(dbatch, f, dev[f].data_ptr() if dev[f].numel() else None)
+        setattr(hbatch, f, pinned[f].data_ptr() if pinned[f].numel() else None)
+    h2d_bytes = sb.nbytes()
+    max_read, max_hap = int(info["read_len"]), int(info["max_hap_len"])
+
+    def step_device():
+        eng.submit_device(dbatch, max_read, max_hap)
+        res = eng.finish_device()
+        if world > 1:
+            res = eng.gather()
+        return res
+
+    import ctypes as C
+    def step_e2e():
+        rc = eng._L.vtx_submit(eng._h, C.byref(hbatch)); eng._ck(rc, "vtx_submit")
+        res = eng.finish_device()
+        if world > 1:
+            res = eng.gather()
+            if rank == 0:
+                return eng.fetch(res)        # rank 0 writes the matrix: it alone needs the triplets on the host
+            return res
+        return eng.fetch(res)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, sampler=None):
+        sw_ms, launches = [], 0
+        barrier()
+        if sampler: sampler.start()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        last = None
+        for _ in range(steps):
+            last = fn()
+            t = eng.timing(); sw_ms.append(t["sw_ms"]); launches += t["total_launches"]
+        e1.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        clocks = sampler.stop() if sampler else None
+        dev_ms = e0.elapsed_time(e1)
+        ms = max(dev_ms, 0.0)
+        # steps end with a host-visible result, so wall clock bounds the device time from above; report the
+        # larger of the two as the step time and take the max over ranks
+        ms = max(ms, wall * 1e3) if fn is step_e2e else ms
+        if world > 1:
+            tt = torch.tensor([ms], device="cuda", dtype=torch.float64); dist.all_reduce(tt, op=dist.ReduceOp.MAX); ms = float(tt.item())
+        return ms, sw_ms, launches, last, clocks
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms, sw_ms, launches, last, clocks = timed(step_device, args.steps, sampler)
+    total_pairs = n_pairs * world
+    if world > 1:
+        tp = torch.tensor([n_pairs], device="cuda", dtype=torch.int64); dist.all_reduce(tp); total_pairs = int(tp.item())
+    value = total_pairs * args.steps / (ms / 1e3)
+
+    for _ in range(max(args.warmup, 3)):
+        step_e2e()
+    ms_e, _, _, last_e, _ = timed(step_e2e, args.steps)
+    e2e_value = total_pairs * args.steps / (ms_e / 1e3)
+    n_out = int(last_e.n) if hasattr(last_e, "n") else len(last_e.row)
+    d2h_bytes = n_out * 36 + 32
+
+    line = None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0)); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6.65 TB/s"
+        b_alg = vb.synth.algorithmic_bytes_per_pair(info)
+        sw_avg_ms = float(np.mean(sw_ms))
+        achieved = n_pairs * b_alg / (sw_avg_ms / 1e3) / 1e9
+        cells = info["read_len"] * 2 * (2 * 100 + 1)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int16x2", "data": "synthetic", "config": describe(args, cfg, world, info),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "ms_per_step": ms_e / args.steps},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "vtx_k_sw_pairs<0>",
+                         "kernel_ms": sw_avg_ms, "algorithmic_bytes_per_pair": b_alg, "pairs_per_launch": n_pairs,
+                         "gcups": n_pairs * cells / (sw_avg_ms / 1e3) / 1e9,
+                         "note": "integer DP: ~540 cell updates per algorithmic byte, so the kernel is DPX-issue bound, not HBM "
+                                 "bound (DESIGN.md); gcups = DP cell updates/s of the SW kernel alone"},
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(sb, bcs, cfg, info, args.cpu_seconds)
+    eng.close()
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+    if line:
+        print(json.dumps(line))
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

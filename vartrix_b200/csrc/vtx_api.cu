@@ -1,0 +1,857 @@
+// vtx_api.cu -- C ABI of the engine (include/vartrix_b200.h): context, device memory, stream
+// orchestration of the kernels in vtx_pipeline.cuh / vtx_sw.cuh.  CUDA only -- there is no CPU path.
+#include "../../include/vartrix_b200.h"
+#include "vtx_pipeline.cuh"
+#include "vtx_sw.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace vtx;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+enum { EV_START = 0, EV_H2D, EV_PREP, EV_SW, EV_POST, EV_COUNT };
+
+}  // namespace
+
+struct vtx_ctx {
+    vtx_config cfg{};
+    int device = 0;
+    int n_sm = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+
+    // barcode table
+    DBuf bc_slot, bc_bytes, bc_off;
+    uint32_t bc_cap = 0, n_barcodes = 0;
+    bool have_barcodes = false;
+
+    // staged inputs (device copies for vtx_submit)
+    DBuf in_locus_row, in_hap, in_ref_off, in_ref_len, in_alt_off, in_alt_len, in_cand_start, in_read_nib, in_read_off,
+        in_read_len, in_cb_bytes, in_read_cb_off, in_read_cb_len, in_read_umi, in_cand_read;
+    // work buffers
+    DBuf read_col, keep, pidx, scan_sums, pair_read, pair_col, pair_umi, pair_locus, pair_start, tcount, tstart,
+        pair_first, pair_cslot, pair_uslot, cslot_col, cslot_locus, uslot_cslot, ccnt, ucnt, keep2, oidx, tile_counters,
+        scratch, pair_scores, d_metrics, d_res_n;
+    // results (device) + host mirrors
+    DBuf r_row, r_col, r_ref, r_alt, r_unk, r_val, r_val2;
+    size_t res_cap = 0;        // entries
+    size_t res_ub = 0;         // upper bound of entries currently held
+    bool finished = true;      // true: next submit starts a fresh result set
+    void* h_res[7] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+    size_t h_res_cap = 0;
+    void* h_scalars = nullptr; // pinned: res_n (u64) + 3 metrics (u64)
+    uint64_t last_n = 0;
+    vtx_metrics last_metrics{};
+
+    cudaEvent_t ev[EV_COUNT] = {};
+    bool timing_valid = false;
+    uint64_t t_sw_launches = 0, t_total_launches = 0, t_pairs = 0;
+    bool t_had_h2d = false;
+
+    // multi-GPU (vtx_comm.cpp)
+    void* comm = nullptr;
+    int rank = 0, n_ranks = 1;
+    void* g_host[7] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+    size_t g_host_cap = 0;
+    DBuf g_dev[7];
+    DBuf g_counts;
+};
+
+namespace {
+
+int set_err(vtx_ctx* c, int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return set_err(ctx, VTX_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+int ensure(vtx_ctx* ctx, DBuf& b, size_t bytes)
+{
+    if (bytes <= b.cap) return VTX_OK;
+    if (b.p) { CK(cudaStreamSynchronize(ctx->stream)); CK(cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) { b.p = nullptr; return set_err(ctx, VTX_E_NOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e)); }
+    b.cap = want;
+    return VTX_OK;
+}
+
+#define ENS(buf, bytes) do { int rc_ = ensure(ctx, buf, (bytes)); if (rc_) return rc_; } while (0)
+
+template <typename T> T* P(DBuf& b) { return static_cast<T*>(b.p); }
+
+inline unsigned blocks_for(uint64_t n, unsigned threads) { return unsigned((n + threads - 1) / threads); }
+
+// exclusive scan wrapper: out has n + 1 entries
+int scan_u32(vtx_ctx* ctx, const uint32_t* in, uint64_t n, uint32_t* out, uint64_t* launches)
+{
+    const unsigned nb = std::max(1u, blocks_for(n, kScanTile));
+    ENS(ctx->scan_sums, size_t(nb) * 4);
+    vtx_k_scan_tiles<<<nb, kScanThreads, 0, ctx->stream>>>(in, n, out, P<uint32_t>(ctx->scan_sums));
+    vtx_k_scan_sums<<<1, kScanThreads, 0, ctx->stream>>>(P<uint32_t>(ctx->scan_sums), nb, out + n);
+    vtx_k_scan_add<<<nb, kScanThreads, 0, ctx->stream>>>(out, n, P<uint32_t>(ctx->scan_sums));
+    if (launches) *launches += 3;
+    CK(cudaGetLastError());
+    return VTX_OK;
+}
+
+struct DevBatch {   // device pointers
+    uint32_t n_loci = 0; uint32_t n_reads = 0; uint64_t n_cand = 0;
+    const uint32_t* locus_row; const uint8_t* hap; const uint32_t *ref_off, *ref_len, *alt_off, *alt_len;
+    const uint64_t* cand_start; const uint8_t* read_nib; const uint64_t* read_off; const uint32_t* read_len;
+    const uint8_t* cb_bytes; const uint32_t* read_cb_off; const uint16_t* read_cb_len; const uint64_t* read_umi;
+    const uint32_t* cand_read;
+    uint32_t max_read_len = 0, max_hap_len = 0;
+};
+
+template <int CLS>
+int launch_sw_class(vtx_ctx* ctx, SwArgs a, uint64_t* launches)
+{
+    using TC = TileClass<CLS>;
+    constexpr int PPW = 32 / TC::LPP, RS = TC::LPP * TC::CS;
+    const size_t warp_bytes = (size_t(5 * RS) * 4 + size_t(PPW) * (a.mcap + 2 * TC::LPP) * 2 + 15) & ~size_t(15);
+    const size_t smem = warp_bytes * 8;
+    auto kern = vtx_k_sw_pairs<CLS>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
+    if (per_sm < 1) return set_err(ctx, VTX_E_CUDA, "SW kernel class %d does not fit on an SM (smem %zu)", CLS, smem);
+    kern<<<ctx->n_sm * per_sm, 256, smem, ctx->stream>>>(a);
+    CK(cudaGetLastError());
+    ++*launches;
+    return VTX_OK;
+}
+
+// classes + tiles + SW kernels, shared by submit and score_pairs.  pair_start must be ready.
+int run_sw(vtx_ctx* ctx, const DevBatch& b, uint32_t n_pairs_ub, const uint32_t* pair_slot, uint32_t* counters,
+           uint32_t* pair_scores, uint64_t* launches, uint64_t* sw_launches, bool record_events)
+{
+    const uint32_t nl = b.n_loci;
+    ENS(ctx->tcount, size_t(kNumClasses) * (nl + 1) * 4);
+    ENS(ctx->tstart, size_t(kNumClasses) * (nl + 1) * 4);
+    ENS(ctx->tile_counters, 64);
+    const int force_slow = b.max_read_len > uint32_t(kFastMaxRead) ? 1 : 0;
+    vtx_k_locus_prep<<<blocks_for(uint64_t(nl) * 32, 256), 256, 0, ctx->stream>>>(
+        nl, b.hap, b.ref_off, b.ref_len, b.alt_off, b.alt_len, P<uint32_t>(ctx->pair_start), force_slow,
+        P<uint32_t>(ctx->tcount));
+    ++*launches;
+    for (int c = 0; c < kNumClasses; ++c) {
+        int rc = scan_u32(ctx, P<uint32_t>(ctx->tcount) + size_t(c) * (nl + 1), nl,
+                          P<uint32_t>(ctx->tstart) + size_t(c) * (nl + 1), launches);
+        if (rc) return rc;
+    }
+    CK(cudaMemsetAsync(ctx->tile_counters.p, 0, 64, ctx->stream));
+    if (record_events) CK(cudaEventRecord(ctx->ev[EV_PREP], ctx->stream));
+
+    SwArgs a{};
+    a.hap_bytes = b.hap; a.ref_off = b.ref_off; a.ref_len = b.ref_len; a.alt_off = b.alt_off; a.alt_len = b.alt_len;
+    a.read_nib = b.read_nib; a.read_off = b.read_off; a.read_len = b.read_len;
+    a.pair_read = P<uint32_t>(ctx->pair_read); a.pair_start = P<uint32_t>(ctx->pair_start);
+    a.n_loci = nl; a.pair_slot = pair_slot; a.counters = counters; a.pair_scores = pair_scores;
+    a.min_score = ctx->cfg.min_score;
+    int mcap = int(std::min<uint32_t>(b.max_read_len, kFastMaxRead));
+    mcap = std::max(2, (mcap + 1) & ~1);
+    a.mcap = mcap;
+    a.max_hap = b.max_hap_len;
+
+    uint64_t before = *launches;
+    for (int c = 0; c < kNumFastClasses; ++c) {
+        a.tile_start = P<uint32_t>(ctx->tstart) + size_t(c) * (nl + 1);
+        a.tile_counter = P<uint32_t>(ctx->tile_counters) + c;
+        int rc = VTX_OK;
+        switch (c) {
+        case 0: rc = launch_sw_class<0>(ctx, a, launches); break;
+        case 1: rc = launch_sw_class<1>(ctx, a, launches); break;
+        case 2: rc = launch_sw_class<2>(ctx, a, launches); break;
+        case 3: rc = launch_sw_class<3>(ctx, a, launches); break;
+        }
+        if (rc) return rc;
+    }
+    {   // generic class (rare)
+        const unsigned blocks = unsigned(ctx->n_sm) * 4, threads = 128;
+        const size_t warps = size_t(blocks) * threads / 32;
+        ENS(ctx->scratch, warps * (size_t(b.max_hap_len) + 1) * 32 * 4);
+        a.scratch = P<uint32_t>(ctx->scratch);
+        a.tile_start = P<uint32_t>(ctx->tstart) + size_t(kSlowClass) * (nl + 1);
+        a.tile_counter = P<uint32_t>(ctx->tile_counters) + kSlowClass;
+        vtx_k_sw_generic<<<blocks, threads, 0, ctx->stream>>>(a);
+        CK(cudaGetLastError());
+        ++*launches;
+    }
+    *sw_launches += *launches - before;
+    (void)n_pairs_ub;
+    return VTX_OK;
+}
+
+int grow_results(vtx_ctx* ctx, size_t need)
+{
+    if (need <= ctx->res_cap) return VTX_OK;
+    const size_t ncap = need + need / 4 + 1024;
+    DBuf* bufs[7] = { &ctx->r_row, &ctx->r_col, &ctx->r_ref, &ctx->r_alt, &ctx->r_unk, &ctx->r_val, &ctx->r_val2 };
+    const size_t esz[7] = { 4, 4, 4, 4, 4, 8, 8 };
+    for (int i = 0; i < 7; ++i) {
+        void* np = nullptr;
+        cudaError_t e = cudaMalloc(&np, ncap * esz[i]);
+        if (e != cudaSuccess) return set_err(ctx, VTX_E_NOMEM, "result cudaMalloc(%zu) failed: %s", ncap * esz[i], cudaGetErrorString(e));
+        if (bufs[i]->p && ctx->res_ub && !ctx->finished)
+            CK(cudaMemcpyAsync(np, bufs[i]->p, ctx->res_ub * esz[i], cudaMemcpyDeviceToDevice, ctx->stream));
+        if (bufs[i]->p) { CK(cudaStreamSynchronize(ctx->stream)); CK(cudaFree(bufs[i]->p)); }
+        bufs[i]->p = np; bufs[i]->cap = ncap * esz[i];
+    }
+    ctx->res_cap = ncap;
+    return VTX_OK;
+}
+
+int process_batch(vtx_ctx* ctx, const DevBatch& b)
+{
+    const uint64_t nc = b.n_cand;
+    const uint32_t nl = b.n_loci, nr = b.n_reads;
+    const int use_umi = ctx->cfg.use_umi ? 1 : 0;
+    uint64_t launches = 0, sw_launches = 0;
+    cudaStream_t st = ctx->stream;
+
+    if (ctx->finished) {      // fresh result set
+        CK(cudaMemsetAsync(ctx->d_res_n.p, 0, 8, st));
+        CK(cudaMemsetAsync(ctx->d_metrics.p, 0, 24, st));
+        ctx->res_ub = 0;
+        ctx->finished = false;
+    }
+    int rc = grow_results(ctx, ctx->res_ub + nc);
+    if (rc) return rc;
+
+    const size_t ncp = size_t(nc) + 1;
+    ENS(ctx->read_col, size_t(nr ? nr : 1) * 4);
+    ENS(ctx->keep, ncp * 4); ENS(ctx->pidx, ncp * 4);
+    ENS(ctx->pair_read, ncp * 4); ENS(ctx->pair_col, ncp * 4);
+    if (use_umi) ENS(ctx->pair_umi, ncp * 8);
+    ENS(ctx->pair_start, size_t(nl + 1) * 4);
+    ENS(ctx->pair_first, ncp);
+    ENS(ctx->pair_cslot, ncp * 4); ENS(ctx->cslot_col, ncp * 4); ENS(ctx->cslot_locus, ncp * 4);
+    ENS(ctx->ccnt, ncp * 16);
+    if (use_umi) { ENS(ctx->pair_uslot, ncp * 4); ENS(ctx->uslot_cslot, ncp * 4); ENS(ctx->ucnt, ncp * 16); }
+    ENS(ctx->keep2, ncp * 4); ENS(ctx->oidx, ncp * 4);
+    uint32_t* pair_scores = nullptr;
+    if (ctx->cfg.flags & VTX_F_KEEP_SCORES) { ENS(ctx->pair_scores, ncp * 4); pair_scores = P<uint32_t>(ctx->pair_scores); }
+
+    if (nl == 0 || nc == 0) {
+        CK(cudaEventRecord(ctx->ev[EV_PREP], st)); CK(cudaEventRecord(ctx->ev[EV_SW], st)); CK(cudaEventRecord(ctx->ev[EV_POST], st));
+        ctx->timing_valid = true; ctx->t_sw_launches = 0; ctx->t_total_launches = 0;
+        return VTX_OK;
+    }
+
+    // ---- K1: CB lookup, filter, compaction --------------------------------------------------------
+    BarcodeTable tab{ P<int32_t>(ctx->bc_slot), ctx->bc_cap - 1, P<uint8_t>(ctx->bc_bytes), P<uint32_t>(ctx->bc_off) };
+    vtx_k_cb_lookup<<<blocks_for(nr, 256), 256, 0, st>>>(tab, nr, b.cb_bytes, b.read_cb_off, b.read_cb_len, P<int32_t>(ctx->read_col));
+    vtx_k_cand_filter<<<blocks_for(nc, 256), 256, 0, st>>>(nc, b.cand_read, P<int32_t>(ctx->read_col), b.read_umi, use_umi,
+                                                           P<uint32_t>(ctx->keep), P<unsigned long long>(ctx->d_metrics));
+    launches += 2;
+    rc = scan_u32(ctx, P<uint32_t>(ctx->keep), nc, P<uint32_t>(ctx->pidx), &launches);
+    if (rc) return rc;
+    vtx_k_compact<<<blocks_for(nc, 256), 256, 0, st>>>(nc, b.cand_read, P<uint32_t>(ctx->keep), P<uint32_t>(ctx->pidx),
+                                                       P<int32_t>(ctx->read_col), b.read_umi, use_umi, P<uint32_t>(ctx->pair_read),
+                                                       P<uint32_t>(ctx->pair_col), P<uint64_t>(ctx->pair_umi));
+    vtx_k_pair_start<<<blocks_for(nl + 1, 256), 256, 0, st>>>(nl, b.cand_start, P<uint32_t>(ctx->pidx), P<uint32_t>(ctx->pair_start));
+    launches += 2;
+    const uint32_t* n_pairs_ptr = P<uint32_t>(ctx->pidx) + nc;
+
+    // ---- slots: the (row, col[, umi]) structure is independent of the alignment results ----------
+    CK(cudaMemsetAsync(ctx->cslot_col.p, 0xFF, size_t(nc) * 4, st));
+    CK(cudaMemsetAsync(ctx->ccnt.p, 0, size_t(nc) * 16, st));
+    if (use_umi) {
+        CK(cudaMemsetAsync(ctx->uslot_cslot.p, 0xFF, size_t(nc) * 4, st));
+        CK(cudaMemsetAsync(ctx->ucnt.p, 0, size_t(nc) * 16, st));
+    }
+    vtx_k_slots<<<std::min<uint32_t>(nl, 65535u * 8), kSlotThreads, 0, st>>>(
+        nl, P<uint32_t>(ctx->pair_start), P<uint32_t>(ctx->pair_col), P<uint64_t>(ctx->pair_umi), use_umi,
+        P<uint8_t>(ctx->pair_first), P<uint32_t>(ctx->pair_cslot), P<uint32_t>(ctx->pair_uslot),
+        P<uint32_t>(ctx->cslot_col), P<uint32_t>(ctx->cslot_locus), P<uint32_t>(ctx->uslot_cslot));
+    ++launches;
+    CK(cudaGetLastError());
+
+    // ---- K2 + K3: Smith-Waterman, call, atomic scatter ----------------------------------------------
+    rc = run_sw(ctx, b, uint32_t(nc), use_umi ? P<uint32_t>(ctx->pair_uslot) : P<uint32_t>(ctx->pair_cslot),
+                use_umi ? P<uint32_t>(ctx->ucnt) : P<uint32_t>(ctx->ccnt), pair_scores, &launches, &sw_launches, true);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev[EV_SW], st));
+
+    // ---- K4 + K5: UMI collapse, mode value, row-major emit ------------------------------------------
+    if (use_umi) {
+        vtx_k_umi_collapse<<<blocks_for(nc, 256), 256, 0, st>>>(uint32_t(nc), n_pairs_ptr, P<uint32_t>(ctx->uslot_cslot),
+                                                                P<uint32_t>(ctx->ucnt), P<uint32_t>(ctx->ccnt));
+        ++launches;
+    }
+    vtx_k_finalize<<<blocks_for(nc, 256), 256, 0, st>>>(uint32_t(nc), n_pairs_ptr, ctx->cfg.mode, P<uint32_t>(ctx->cslot_col),
+                                                        P<uint32_t>(ctx->ccnt), P<uint32_t>(ctx->keep2));
+    ++launches;
+    rc = scan_u32(ctx, P<uint32_t>(ctx->keep2), nc, P<uint32_t>(ctx->oidx), &launches);
+    if (rc) return rc;
+    ResultArrays out{ P<uint32_t>(ctx->r_row), P<uint32_t>(ctx->r_col), P<uint32_t>(ctx->r_ref), P<uint32_t>(ctx->r_alt),
+                      P<uint32_t>(ctx->r_unk), P<double>(ctx->r_val), P<double>(ctx->r_val2) };
+    vtx_k_emit<<<blocks_for(nc, 256), 256, 0, st>>>(uint32_t(nc), ctx->cfg.mode, P<uint32_t>(ctx->keep2), P<uint32_t>(ctx->oidx),
+                                                    P<unsigned long long>(ctx->d_res_n), P<uint32_t>(ctx->cslot_col),
+                                                    P<uint32_t>(ctx->cslot_locus), b.locus_row, P<uint32_t>(ctx->ccnt), out);
+    vtx_k_bump<<<1, 32, 0, st>>>(P<unsigned long long>(ctx->d_res_n), P<uint32_t>(ctx->oidx) + nc);
+    launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev[EV_POST], st));
+    ctx->res_ub += nc;
+    ctx->timing_valid = true;
+    ctx->t_sw_launches = sw_launches;
+    ctx->t_total_launches = launches;
+    return VTX_OK;
+}
+
+int validate_batch(vtx_ctx* ctx, const vtx_batch* b)
+{
+    if (!b) return set_err(ctx, VTX_E_INVALID, "batch is NULL");
+    if (b->n_cand >= 0xFFFFFFF0ull) return set_err(ctx, VTX_E_INVALID, "n_cand %llu exceeds 2^32 per shard; split the shard", (unsigned long long)b->n_cand);
+    if (b->n_loci && (!b->locus_row || !b->ref_off || !b->ref_len || !b->alt_off || !b->alt_len || !b->cand_start))
+        return set_err(ctx, VTX_E_INVALID, "locus arrays missing");
+    if (b->n_reads && (!b->read_off || !b->read_len || !b->read_cb_off || !b->read_cb_len || !b->read_umi_key))
+        return set_err(ctx, VTX_E_INVALID, "read arrays missing");
+    if (b->n_cand && !b->cand_read) return set_err(ctx, VTX_E_INVALID, "cand_read missing");
+    if (b->hap_bytes_len >= 0xFFFFFFFFull) return set_err(ctx, VTX_E_INVALID, "haplotype pool exceeds 4 GiB; split the shard");
+    return VTX_OK;
+}
+
+// host-side checks that need to touch the (host) arrays; also returns max lengths
+int scan_host_batch(vtx_ctx* ctx, const vtx_batch* b, uint32_t* max_read, uint32_t* max_hap, bool check_cands)
+{
+    uint32_t mr = 0, mh = 0;
+    for (uint32_t l = 0; l < b->n_loci; ++l) {
+        if ((b->ref_off[l] & 15) || (b->alt_off[l] & 15)) return set_err(ctx, VTX_E_INVALID, "locus %u: haplotype offsets must be multiples of 16", l);
+        if (uint64_t(b->ref_off[l]) + b->ref_len[l] > b->hap_bytes_len || uint64_t(b->alt_off[l]) + b->alt_len[l] > b->hap_bytes_len)
+            return set_err(ctx, VTX_E_INVALID, "locus %u: haplotype window outside hap_bytes", l);
+        if (l && b->locus_row[l] <= b->locus_row[l - 1]) return set_err(ctx, VTX_E_INVALID, "locus_row must be strictly ascending (locus %u)", l);
+        if (check_cands && b->cand_start[l] > b->cand_start[l + 1]) return set_err(ctx, VTX_E_INVALID, "cand_start must be ascending (locus %u)", l);
+        mh = std::max(mh, std::max(b->ref_len[l], b->alt_len[l]));
+    }
+    if (check_cands && b->n_loci && (b->cand_start[0] != 0 || b->cand_start[b->n_loci] != b->n_cand))
+        return set_err(ctx, VTX_E_INVALID, "cand_start must span [0, n_cand]");
+    if (check_cands && !b->n_loci && b->n_cand) return set_err(ctx, VTX_E_INVALID, "candidates without loci");
+    for (uint32_t r = 0; r < b->n_reads; ++r) {
+        if (b->read_off[r] & 15) return set_err(ctx, VTX_E_INVALID, "read %u: read_off must be a multiple of 16", r);
+        if (b->read_off[r] + (uint64_t(b->read_len[r]) + 1) / 2 > b->read_nib_len) return set_err(ctx, VTX_E_INVALID, "read %u outside read_nib", r);
+        if (b->read_cb_off[r] != VTX_NO_CB && uint64_t(b->read_cb_off[r]) + b->read_cb_len[r] > b->cb_bytes_len)
+            return set_err(ctx, VTX_E_INVALID, "read %u: CB outside cb_bytes", r);
+        if (b->read_umi_key[r] != VTX_NO_UMI && b->read_umi_key[r] > VTX_UMI_KEY_MAX) return set_err(ctx, VTX_E_INVALID, "read %u: UMI key exceeds VTX_UMI_KEY_MAX", r);
+        mr = std::max(mr, b->read_len[r]);
+    }
+    if (mr > 32000) return set_err(ctx, VTX_E_UNSUPPORTED, "reads longer than 32000 bases (int16 DP) are not supported (%u)", mr);
+    if (check_cands)
+        for (uint64_t c = 0; c < b->n_cand; ++c)
+            if (b->cand_read[c] >= b->n_reads) return set_err(ctx, VTX_E_INVALID, "cand_read[%llu] out of range", (unsigned long long)c);
+    *max_read = mr; *max_hap = mh;
+    return VTX_OK;
+}
+
+int upload(vtx_ctx* ctx, DBuf& d, const void* h, size_t bytes)
+{
+    ENS(d, bytes ? bytes : 16);
+    if (bytes) CK(cudaMemcpyAsync(d.p, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return VTX_OK;
+}
+
+#define UP(buf, ptr, bytes) do { int rc_ = upload(ctx, buf, ptr, (bytes)); if (rc_) return rc_; } while (0)
+
+int upload_common(vtx_ctx* ctx, const vtx_batch* hb, DevBatch& d)
+{
+    const uint32_t nl = hb->n_loci, nr = hb->n_reads;
+    UP(ctx->in_locus_row, hb->locus_row, size_t(nl) * 4);
+    UP(ctx->in_hap, hb->hap_bytes, hb->hap_bytes_len);
+    UP(ctx->in_ref_off, hb->ref_off, size_t(nl) * 4); UP(ctx->in_ref_len, hb->ref_len, size_t(nl) * 4);
+    UP(ctx->in_alt_off, hb->alt_off, size_t(nl) * 4); UP(ctx->in_alt_len, hb->alt_len, size_t(nl) * 4);
+    UP(ctx->in_read_nib, hb->read_nib, hb->read_nib_len);
+    UP(ctx->in_read_off, hb->read_off, size_t(nr) * 8); UP(ctx->in_read_len, hb->read_len, size_t(nr) * 4);
+    d.n_loci = nl; d.n_reads = nr;
+    d.locus_row = P<uint32_t>(ctx->in_locus_row); d.hap = P<uint8_t>(ctx->in_hap);
+    d.ref_off = P<uint32_t>(ctx->in_ref_off); d.ref_len = P<uint32_t>(ctx->in_ref_len);
+    d.alt_off = P<uint32_t>(ctx->in_alt_off); d.alt_len = P<uint32_t>(ctx->in_alt_len);
+    d.read_nib = P<uint8_t>(ctx->in_read_nib); d.read_off = P<uint64_t>(ctx->in_read_off); d.read_len = P<uint32_t>(ctx->in_read_len);
+    return VTX_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int vtx_abi_version(void) { return VTX_ABI_VERSION; }
+
+const char* vtx_last_error(const vtx_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int vtx_create(const vtx_config* cfg, vtx_ctx** out)
+{
+    vtx_ctx* ctx = nullptr;   // for CK/set_err before the ctx exists
+    if (!cfg || !out) return set_err(nullptr, VTX_E_INVALID, "vtx_create: NULL argument");
+    *out = nullptr;
+    if (cfg->match != kMatch || cfg->mismatch != kMismatch || cfg->gap_open != kGapOpen || cfg->gap_extend != kGapExtend)
+        return set_err(nullptr, VTX_E_UNSUPPORTED, "scoring constants are compiled in: match %d mismatch %d gap_open %d gap_extend %d (main.rs:35-38)",
+                       kMatch, kMismatch, kGapOpen, kGapExtend);
+    if (cfg->mode < 0 || cfg->mode > 2) return set_err(nullptr, VTX_E_INVALID, "unknown mode %d", cfg->mode);
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+        return set_err(nullptr, VTX_E_CUDA, "no CUDA device available (%s); vartrix_b200 has no CPU fallback", cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= n_dev) return set_err(nullptr, VTX_E_INVALID, "device %d out of range (%d devices)", cfg->device, n_dev);
+    CK(cudaSetDevice(cfg->device));
+    ctx = new vtx_ctx();
+    ctx->cfg = *cfg; ctx->device = cfg->device;
+    cudaDeviceProp prop{};
+    cudaError_t pe = cudaGetDeviceProperties(&prop, cfg->device);
+    if (pe != cudaSuccess) { g_create_error = cudaGetErrorString(pe); delete ctx; return VTX_E_CUDA; }
+    if (prop.major < 9) { g_create_error = "vartrix_b200 needs DPX (sm_90+); built for sm_100a"; delete ctx; return VTX_E_UNSUPPORTED; }
+    ctx->n_sm = prop.multiProcessorCount;
+    if (cfg->stream) { ctx->stream = static_cast<cudaStream_t>(cfg->stream); ctx->own_stream = false; }
+    else {
+        pe = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+        if (pe != cudaSuccess) { g_create_error = cudaGetErrorString(pe); delete ctx; return VTX_E_CUDA; }
+        ctx->own_stream = true;
+    }
+    for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+    bool ok = cudaMalloc(&ctx->d_metrics.p, 64) == cudaSuccess && cudaMalloc(&ctx->d_res_n.p, 64) == cudaSuccess &&
+              cudaHostAlloc(&ctx->h_scalars, 64, cudaHostAllocDefault) == cudaSuccess;
+    if (!ok) { g_create_error = "allocation of context scalars failed"; vtx_destroy(ctx); return VTX_E_NOMEM; }
+    ctx->d_metrics.cap = 64; ctx->d_res_n.cap = 64;
+    cudaMemsetAsync(ctx->d_metrics.p, 0, 64, ctx->stream);
+    cudaMemsetAsync(ctx->d_res_n.p, 0, 64, ctx->stream);
+    *out = ctx;
+    return VTX_OK;
+}
+
+void vtx_comm_destroy_internal(vtx_ctx* ctx);   // vtx_comm.cpp
+
+void vtx_destroy(vtx_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    vtx_comm_destroy_internal(ctx);
+    DBuf* all[] = { &ctx->bc_slot, &ctx->bc_bytes, &ctx->bc_off, &ctx->in_locus_row, &ctx->in_hap, &ctx->in_ref_off, &ctx->in_ref_len,
+                    &ctx->in_alt_off, &ctx->in_alt_len, &ctx->in_cand_start, &ctx->in_read_nib, &ctx->in_read_off, &ctx->in_read_len,
+                    &ctx->in_cb_bytes, &ctx->in_read_cb_off, &ctx->in_read_cb_len, &ctx->in_read_umi, &ctx->in_cand_read, &ctx->read_col,
+                    &ctx->keep, &ctx->pidx, &ctx->scan_sums, &ctx->pair_read, &ctx->pair_col, &ctx->pair_umi, &ctx->pair_locus,
+                    &ctx->pair_start, &ctx->tcount, &ctx->tstart, &ctx->pair_first, &ctx->pair_cslot, &ctx->pair_uslot, &ctx->cslot_col,
+                    &ctx->cslot_locus, &ctx->uslot_cslot, &ctx->ccnt, &ctx->ucnt, &ctx->keep2, &ctx->oidx, &ctx->tile_counters,
+                    &ctx->scratch, &ctx->pair_scores, &ctx->d_metrics, &ctx->d_res_n, &ctx->r_row, &ctx->r_col, &ctx->r_ref,
+                    &ctx->r_alt, &ctx->r_unk, &ctx->r_val, &ctx->r_val2, &ctx->g_counts };
+    for (DBuf* b : all) if (b->p) cudaFree(b->p);
+    for (auto& b : ctx->g_dev) if (b.p) cudaFree(b.p);
+    for (void* h : ctx->h_res) if (h) cudaFreeHost(h);
+    for (void* h : ctx->g_host) if (h) cudaFreeHost(h);
+    if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
+    for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int vtx_host_alloc(void** out, uint64_t bytes)
+{
+    if (!out) return VTX_E_INVALID;
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 16, cudaHostAllocDefault);
+    if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); *out = nullptr; return VTX_E_NOMEM; }
+    return VTX_OK;
+}
+
+int vtx_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? VTX_OK : VTX_E_CUDA; }
+
+int vtx_set_barcodes(vtx_ctx* ctx, const uint8_t* bytes, const uint32_t* off, uint32_t n)
+{
+    if (!ctx) return VTX_E_INVALID;
+    if (!off || (n && !bytes && off[n] > 0)) return set_err(ctx, VTX_E_INVALID, "vtx_set_barcodes: NULL argument");
+    if (n == 0) return set_err(ctx, VTX_E_INVALID, "Loaded 0 barcodes (main.rs:712-715)");
+    CK(cudaSetDevice(ctx->device));
+    uint32_t cap = 16;
+    while (cap < 2ull * n + 1) cap <<= 1;
+    std::vector<int32_t> slot(cap, -1);
+    for (uint32_t i = 0; i < n; ++i) {
+        if (off[i + 1] < off[i]) return set_err(ctx, VTX_E_INVALID, "barcode offsets must be ascending");
+        const uint32_t len = off[i + 1] - off[i];
+        if (len > 0xFFFF) return set_err(ctx, VTX_E_INVALID, "barcode %u longer than 65535 bytes", i);
+        uint32_t h = uint32_t(fnv1a64(bytes + off[i], len)) & (cap - 1);
+        for (;;) {
+            const int32_t s = slot[h];
+            if (s < 0) { slot[h] = int32_t(i); break; }
+            const uint32_t l2 = off[s + 1] - off[s];
+            if (l2 == len && memcmp(bytes + off[s], bytes + off[i], len) == 0)
+                return set_err(ctx, VTX_E_INVALID, "duplicate barcode at index %u (first seen at %d); dedup first (main.rs:706-709)", i, s);
+            h = (h + 1) & (cap - 1);
+        }
+    }
+    UP(ctx->bc_slot, slot.data(), size_t(cap) * 4);
+    UP(ctx->bc_bytes, bytes, off[n]);
+    UP(ctx->bc_off, off, size_t(n + 1) * 4);
+    CK(cudaStreamSynchronize(ctx->stream));   // `slot` is a local
+    ctx->bc_cap = cap; ctx->n_barcodes = n; ctx->have_barcodes = true;
+    return VTX_OK;
+}
+
+int vtx_submit(vtx_ctx* ctx, const vtx_batch* hb)
+{
+    if (!ctx) return VTX_E_INVALID;
+    if (!ctx->have_barcodes) return set_err(ctx, VTX_E_STATE, "vtx_set_barcodes must be called before vtx_submit");
+    int rc = validate_batch(ctx, hb);
+    if (rc) return rc;
+    DevBatch d{};
+    rc = scan_host_batch(ctx, hb, &d.max_read_len, &d.max_hap_len, true);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventRecord(ctx->ev[EV_START], ctx->stream));
+    rc = upload_common(ctx, hb, d);
+    if (rc) return rc;
+    const uint32_t nl = hb->n_loci, nr = hb->n_reads;
+    UP(ctx->in_cand_start, hb->cand_start, size_t(nl + 1) * 8);
+    UP(ctx->in_cb_bytes, hb->cb_bytes, hb->cb_bytes_len);
+    UP(ctx->in_read_cb_off, hb->read_cb_off, size_t(nr) * 4); UP(ctx->in_read_cb_len, hb->read_cb_len, size_t(nr) * 2);
+    UP(ctx->in_read_umi, hb->read_umi_key, size_t(nr) * 8);
+    UP(ctx->in_cand_read, hb->cand_read, size_t(hb->n_cand) * 4);
+    d.n_cand = hb->n_cand;
+    d.cand_start = P<uint64_t>(ctx->in_cand_start); d.cb_bytes = P<uint8_t>(ctx->in_cb_bytes);
+    d.read_cb_off = P<uint32_t>(ctx->in_read_cb_off); d.read_cb_len = P<uint16_t>(ctx->in_read_cb_len);
+    d.read_umi = P<uint64_t>(ctx->in_read_umi); d.cand_read = P<uint32_t>(ctx->in_cand_read);
+    CK(cudaEventRecord(ctx->ev[EV_H2D], ctx->stream));
+    ctx->t_had_h2d = true;
+    return process_batch(ctx, d);
+}
+
+// device batches carry their own bounds in the (otherwise unused) *_len fields of the pools:
+// the caller must pass max read / haplotype lengths through vtx_submit_device_ex.
+int vtx_submit_device_ex(vtx_ctx* ctx, const vtx_batch* db, uint32_t max_read_len, uint32_t max_hap_len)
+{
+    if (!ctx) return VTX_E_INVALID;
+    if (!ctx->have_barcodes) return set_err(ctx, VTX_E_STATE, "vtx_set_barcodes must be called before vtx_submit_device");
+    int rc = validate_batch(ctx, db);
+    if (rc) return rc;
+    if (max_read_len > 32000) return set_err(ctx, VTX_E_UNSUPPORTED, "reads longer than 32000 bases are not supported");
+    CK(cudaSetDevice(ctx->device));
+    DevBatch d{};
+    d.n_loci = db->n_loci; d.n_reads = db->n_reads; d.n_cand = db->n_cand;
+    d.locus_row = db->locus_row; d.hap = db->hap_bytes; d.ref_off = db->ref_off; d.ref_len = db->ref_len;
+    d.alt_off = db->alt_off; d.alt_len = db->alt_len; d.cand_start = db->cand_start; d.read_nib = db->read_nib;
+    d.read_off = db->read_off; d.read_len = db->read_len; d.cb_bytes = db->cb_bytes; d.read_cb_off = db->read_cb_off;
+    d.read_cb_len = db->read_cb_len; d.read_umi = db->read_umi_key; d.cand_read = db->cand_read;
+    d.max_read_len = max_read_len; d.max_hap_len = max_hap_len;
+    CK(cudaEventRecord(ctx->ev[EV_START], ctx->stream));
+    CK(cudaEventRecord(ctx->ev[EV_H2D], ctx->stream));
+    ctx->t_had_h2d = false;
+    return process_batch(ctx, d);
+}
+
+int vtx_submit_device(vtx_ctx* ctx, const vtx_batch* db)
+{
+    // conservative bounds when the caller does not state them: the largest fast-path read and the
+    // widest haplotype any tile class takes (wider inputs need vtx_submit_device_ex)
+    return vtx_submit_device_ex(ctx, db, kFastMaxRead, class_max_n(kNumFastClasses - 1));
+}
+
+int vtx_sync(vtx_ctx* ctx)
+{
+    if (!ctx) return VTX_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return VTX_OK;
+}
+
+static int finish_scalars(vtx_ctx* ctx)
+{
+    CK(cudaSetDevice(ctx->device));
+    uint64_t* hs = static_cast<uint64_t*>(ctx->h_scalars);
+    CK(cudaMemcpyAsync(hs, ctx->d_res_n.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(hs + 1, ctx->d_metrics.p, 24, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->last_n = ctx->finished ? 0 : hs[0];
+    ctx->last_metrics.num_not_cell_bc = ctx->finished ? 0 : hs[1];
+    ctx->last_metrics.num_non_umi = ctx->finished ? 0 : hs[2];
+    ctx->last_metrics.num_scored = ctx->finished ? 0 : hs[3];
+    ctx->t_pairs = ctx->last_metrics.num_scored;
+    ctx->finished = true;
+    return VTX_OK;
+}
+
+int vtx_finish_device(vtx_ctx* ctx, vtx_result* out)
+{
+    if (!ctx || !out) return VTX_E_INVALID;
+    int rc = finish_scalars(ctx);
+    if (rc) return rc;
+    out->n = ctx->last_n;
+    out->row = P<uint32_t>(ctx->r_row); out->col = P<uint32_t>(ctx->r_col); out->ref_cnt = P<uint32_t>(ctx->r_ref);
+    out->alt_cnt = P<uint32_t>(ctx->r_alt); out->unk_cnt = P<uint32_t>(ctx->r_unk);
+    out->val = P<double>(ctx->r_val); out->val2 = P<double>(ctx->r_val2);
+    out->metrics = ctx->last_metrics;
+    return VTX_OK;
+}
+
+static int fetch_to(vtx_ctx* ctx, const vtx_result* dev, vtx_result* out, void** hbuf, size_t* hcap)
+{
+    const size_t n = dev->n;
+    const size_t esz[7] = { 4, 4, 4, 4, 4, 8, 8 };
+    if (n > *hcap) {
+        const size_t ncap = n + n / 4 + 1024;
+        for (int i = 0; i < 7; ++i) {
+            if (hbuf[i]) { cudaFreeHost(hbuf[i]); hbuf[i] = nullptr; }
+            cudaError_t e = cudaHostAlloc(&hbuf[i], ncap * esz[i], cudaHostAllocDefault);
+            if (e != cudaSuccess) { *hcap = 0; return set_err(ctx, VTX_E_NOMEM, "pinned result alloc failed: %s", cudaGetErrorString(e)); }
+        }
+        *hcap = ncap;
+    }
+    const void* src[7] = { dev->row, dev->col, dev->ref_cnt, dev->alt_cnt, dev->unk_cnt, dev->val, dev->val2 };
+    if (n) {
+        for (int i = 0; i < 7; ++i) CK(cudaMemcpyAsync(hbuf[i], src[i], n * esz[i], cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    out->n = n;
+    out->row = static_cast<uint32_t*>(hbuf[0]); out->col = static_cast<uint32_t*>(hbuf[1]);
+    out->ref_cnt = static_cast<uint32_t*>(hbuf[2]); out->alt_cnt = static_cast<uint32_t*>(hbuf[3]);
+    out->unk_cnt = static_cast<uint32_t*>(hbuf[4]);
+    out->val = static_cast<double*>(hbuf[5]); out->val2 = static_cast<double*>(hbuf[6]);
+    out->metrics = dev->metrics;
+    return VTX_OK;
+}
+
+int vtx_fetch(vtx_ctx* ctx, const vtx_result* device_result, vtx_result* out)
+{
+    if (!ctx || !device_result || !out) return VTX_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    // gathered results get their own host buffers so that a local and a gathered copy can coexist
+    const bool gathered = device_result->row == ctx->g_dev[0].p && ctx->g_dev[0].p != nullptr;
+    return gathered ? fetch_to(ctx, device_result, out, ctx->g_host, &ctx->g_host_cap)
+                    : fetch_to(ctx, device_result, out, ctx->h_res, &ctx->h_res_cap);
+}
+
+int vtx_finish(vtx_ctx* ctx, vtx_result* out)
+{
+    if (!ctx || !out) return VTX_E_INVALID;
+    vtx_result dev{};
+    int rc = vtx_finish_device(ctx, &dev);
+    if (rc) return rc;
+    return fetch_to(ctx, &dev, out, ctx->h_res, &ctx->h_res_cap);
+}
+
+int vtx_last_timing(vtx_ctx* ctx, vtx_timing* t)
+{
+    if (!ctx || !t) return VTX_E_INVALID;
+    if (!ctx->timing_valid) return set_err(ctx, VTX_E_STATE, "no finished submit to time");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventSynchronize(ctx->ev[EV_POST]));
+    memset(t, 0, sizeof(*t));
+    if (ctx->t_had_h2d) CK(cudaEventElapsedTime(&t->h2d_ms, ctx->ev[EV_START], ctx->ev[EV_H2D]));
+    CK(cudaEventElapsedTime(&t->prep_ms, ctx->ev[EV_H2D], ctx->ev[EV_PREP]));
+    CK(cudaEventElapsedTime(&t->sw_ms, ctx->ev[EV_PREP], ctx->ev[EV_SW]));
+    CK(cudaEventElapsedTime(&t->post_ms, ctx->ev[EV_SW], ctx->ev[EV_POST]));
+    t->n_pairs = ctx->t_pairs; t->sw_launches = ctx->t_sw_launches; t->total_launches = ctx->t_total_launches;
+    return VTX_OK;
+}
+
+int vtx_score_pairs(vtx_ctx* ctx, const vtx_batch* hb, uint64_t n_pairs, const uint32_t* pair_read,
+                    const uint32_t* pair_locus, int16_t* ref_score, int16_t* alt_score)
+{
+    if (!ctx) return VTX_E_INVALID;
+    int rc = validate_batch(ctx, hb);
+    if (rc) return rc;
+    if (n_pairs >= 0xFFFFFFF0ull) return set_err(ctx, VTX_E_INVALID, "too many pairs");
+    if (n_pairs && (!pair_read || !pair_locus || !ref_score || !alt_score)) return set_err(ctx, VTX_E_INVALID, "NULL pair arrays");
+    DevBatch d{};
+    rc = scan_host_batch(ctx, hb, &d.max_read_len, &d.max_hap_len, false);
+    if (rc) return rc;
+    if (n_pairs == 0) return VTX_OK;
+    const uint32_t nl = hb->n_loci;
+    // counting sort by locus (tiles need the pairs of a locus to be contiguous)
+    std::vector<uint32_t> start(size_t(nl) + 2, 0), order(n_pairs), s_read(n_pairs), s_locus(n_pairs);
+    for (uint64_t i = 0; i < n_pairs; ++i) {
+        if (pair_locus[i] >= nl || pair_read[i] >= hb->n_reads) return set_err(ctx, VTX_E_INVALID, "pair %llu out of range", (unsigned long long)i);
+        ++start[pair_locus[i] + 1];
+    }
+    for (uint32_t l = 0; l < nl; ++l) start[l + 1] += start[l];
+    {
+        std::vector<uint32_t> cur(start.begin(), start.begin() + nl + 1);
+        for (uint64_t i = 0; i < n_pairs; ++i) { const uint32_t p = cur[pair_locus[i]]++; order[p] = uint32_t(i); s_read[p] = pair_read[i]; s_locus[p] = pair_locus[i]; }
+    }
+    CK(cudaSetDevice(ctx->device));
+    rc = upload_common(ctx, hb, d);
+    if (rc) return rc;
+    ENS(ctx->pair_read, n_pairs * 4 + 4); ENS(ctx->pair_locus, n_pairs * 4 + 4); ENS(ctx->pair_start, size_t(nl + 1) * 4);
+    ENS(ctx->pair_scores, n_pairs * 4 + 4);
+    CK(cudaMemcpyAsync(ctx->pair_read.p, s_read.data(), n_pairs * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->pair_locus.p, s_locus.data(), n_pairs * 4, cudaMemcpyHostToDevice, ctx->stream));
+    vtx_k_pair_start_explicit<<<blocks_for(nl + 1, 256), 256, 0, ctx->stream>>>(nl, uint32_t(n_pairs), P<uint32_t>(ctx->pair_locus),
+                                                                                P<uint32_t>(ctx->pair_start));
+    uint64_t launches = 1, sw_launches = 0;
+    rc = run_sw(ctx, d, uint32_t(n_pairs), nullptr, nullptr, P<uint32_t>(ctx->pair_scores), &launches, &sw_launches, false);
+    if (rc) return rc;
+    std::vector<uint32_t> packed(n_pairs);
+    CK(cudaMemcpyAsync(packed.data(), ctx->pair_scores.p, n_pairs * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (uint64_t p = 0; p < n_pairs; ++p) {
+        ref_score[order[p]] = int16_t(packed[p] & 0xFFFF);
+        alt_score[order[p]] = int16_t(packed[p] >> 16);
+    }
+    return VTX_OK;
+}
+
+uint64_t vtx_pack_umi(const uint8_t* s, uint32_t len)
+{
+    if (len > 18) return VTX_NO_UMI;
+    uint64_t k = 0;
+    for (uint32_t i = 0; i < len; ++i) {
+        uint64_t c;
+        switch (s[i]) { case 'A': c = 0; break; case 'C': c = 1; break; case 'G': c = 2; break; case 'T': c = 3; break; case 'N': c = 4; break; default: return VTX_NO_UMI; }
+        k = (k << 3) | c;
+    }
+    return (k << 5) | len;      // < 2^59: bits 59..61 stay clear for caller-interned ids
+}
+
+
+// -------------------------------------------------------------------------------------------------
+// multi-GPU: one allgatherv of the finished triplets over NCCL (NVLink 5 / NVSwitch).  NCCL has no
+// native "v" collective: ncclAllGather of the per-rank counts, then one grouped set of exact-size
+// ncclBroadcast calls (7 arrays x n_ranks roots).  NCCL is dlopen'ed so that single-GPU users (and
+// CPU-only build hosts) never need the library.
+// -------------------------------------------------------------------------------------------------
+}  // extern "C"
+
+#include <dlfcn.h>
+namespace {
+typedef struct { char internal[128]; } nccl_uid;
+typedef void* nccl_comm;
+struct NcclApi {
+    void* h = nullptr;
+    int (*GetUniqueId)(nccl_uid*) = nullptr;
+    int (*CommInitRank)(nccl_comm*, int, nccl_uid, int) = nullptr;
+    int (*CommDestroy)(nccl_comm) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, nccl_comm, cudaStream_t) = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, nccl_comm, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+NcclApi g_nccl;
+constexpr int kNcclUint8 = 1, kNcclUint64 = 5;
+
+bool load_nccl(std::string* why)
+{
+    if (g_nccl.ok) return true;
+    const char* names[] = { "libnccl.so.2", "libnccl.so" };
+    for (const char* n : names) { g_nccl.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (g_nccl.h) break; }
+    if (!g_nccl.h) { *why = std::string("dlopen(libnccl.so.2) failed: ") + dlerror(); return false; }
+#define SYM(field, name) *(void**)(&g_nccl.field) = dlsym(g_nccl.h, name); if (!g_nccl.field) { *why = std::string("missing symbol ") + name; return false; }
+    SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
+    SYM(AllGather, "ncclAllGather") SYM(Broadcast, "ncclBroadcast") SYM(GroupStart, "ncclGroupStart")
+    SYM(GroupEnd, "ncclGroupEnd") SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+    g_nccl.ok = true;
+    return true;
+}
+#define NK(call) do { int r_ = (call); if (r_ != 0) return set_err(ctx, VTX_E_NCCL, "%s failed: %s", #call, g_nccl.GetErrorString(r_)); } while (0)
+}  // namespace
+
+extern "C" {
+
+void vtx_comm_destroy_internal(vtx_ctx* ctx)
+{
+    if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(static_cast<nccl_comm>(ctx->comm));
+    ctx->comm = nullptr;
+}
+
+int vtx_comm_unique_id(uint8_t id_out[128])
+{
+    std::string why;
+    if (!id_out) return VTX_E_INVALID;
+    if (!load_nccl(&why)) { g_create_error = why; return VTX_E_NCCL; }
+    nccl_uid id;
+    int r = g_nccl.GetUniqueId(&id);
+    if (r != 0) { g_create_error = g_nccl.GetErrorString(r); return VTX_E_NCCL; }
+    memcpy(id_out, id.internal, 128);
+    return VTX_OK;
+}
+
+int vtx_comm_init(vtx_ctx* ctx, const uint8_t id[128], int32_t rank, int32_t n_ranks)
+{
+    if (!ctx || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return ctx ? set_err(ctx, VTX_E_INVALID, "vtx_comm_init: bad arguments") : VTX_E_INVALID;
+    std::string why;
+    if (!load_nccl(&why)) return set_err(ctx, VTX_E_NCCL, "%s", why.c_str());
+    CK(cudaSetDevice(ctx->device));
+    nccl_uid uid; memcpy(uid.internal, id, 128);
+    nccl_comm comm = nullptr;
+    NK(g_nccl.CommInitRank(&comm, n_ranks, uid, rank));
+    ctx->comm = comm; ctx->rank = rank; ctx->n_ranks = n_ranks;
+    return VTX_OK;
+}
+
+int vtx_gather(vtx_ctx* ctx, vtx_result* out)
+{
+    if (!ctx || !out) return VTX_E_INVALID;
+    if (!ctx->finished) return set_err(ctx, VTX_E_STATE, "vtx_gather must follow vtx_finish / vtx_finish_device");
+    CK(cudaSetDevice(ctx->device));
+    const size_t esz[7] = { 4, 4, 4, 4, 4, 8, 8 };
+    DBuf* loc[7] = { &ctx->r_row, &ctx->r_col, &ctx->r_ref, &ctx->r_alt, &ctx->r_unk, &ctx->r_val, &ctx->r_val2 };
+    const int nrk = ctx->n_ranks;
+    std::vector<uint64_t> counts(size_t(nrk) * 4, 0);     // {n, not_cell_bc, non_umi, scored} per rank
+    if (nrk == 1 || !ctx->comm) {
+        if (nrk != 1) return set_err(ctx, VTX_E_STATE, "vtx_comm_init has not been called");
+        counts[0] = ctx->last_n; counts[1] = ctx->last_metrics.num_not_cell_bc; counts[2] = ctx->last_metrics.num_non_umi; counts[3] = ctx->last_metrics.num_scored;
+    } else {
+        ENS(ctx->g_counts, size_t(nrk + 1) * 32);
+        uint64_t mine[4] = { ctx->last_n, ctx->last_metrics.num_not_cell_bc, ctx->last_metrics.num_non_umi, ctx->last_metrics.num_scored };
+        uint64_t* dmine = P<uint64_t>(ctx->g_counts) + size_t(nrk) * 4;
+        CK(cudaMemcpyAsync(dmine, mine, 32, cudaMemcpyHostToDevice, ctx->stream));
+        NK(g_nccl.AllGather(dmine, ctx->g_counts.p, 4, kNcclUint64, static_cast<nccl_comm>(ctx->comm), ctx->stream));
+        CK(cudaMemcpyAsync(counts.data(), ctx->g_counts.p, size_t(nrk) * 32, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    size_t total = 0;
+    std::vector<size_t> offs(nrk);
+    vtx_metrics met{};
+    for (int r = 0; r < nrk; ++r) {
+        offs[r] = total; total += counts[size_t(r) * 4];
+        met.num_not_cell_bc += counts[size_t(r) * 4 + 1]; met.num_non_umi += counts[size_t(r) * 4 + 2]; met.num_scored += counts[size_t(r) * 4 + 3];
+    }
+    const void* src[7];
+    if (nrk == 1) {
+        for (int i = 0; i < 7; ++i) src[i] = loc[i]->p;
+    } else {
+        for (int i = 0; i < 7; ++i) ENS(ctx->g_dev[i], (total ? total : 1) * esz[i]);
+        NK(g_nccl.GroupStart());
+        for (int i = 0; i < 7; ++i)
+            for (int r = 0; r < nrk; ++r) {
+                const size_t n = counts[size_t(r) * 4];
+                if (!n) continue;
+                NK(g_nccl.Broadcast(loc[i]->p, static_cast<uint8_t*>(ctx->g_dev[i].p) + offs[r] * esz[i], n * esz[i], kNcclUint8, r,
+                                    static_cast<nccl_comm>(ctx->comm), ctx->stream));
+            }
+        NK(g_nccl.GroupEnd());
+        for (int i = 0; i < 7; ++i) src[i] = ctx->g_dev[i].p;
+    }
+    out->n = total;
+    out->row = static_cast<const uint32_t*>(src[0]); out->col = static_cast<const uint32_t*>(src[1]);
+    out->ref_cnt = static_cast<const uint32_t*>(src[2]); out->alt_cnt = static_cast<const uint32_t*>(src[3]);
+    out->unk_cnt = static_cast<const uint32_t*>(src[4]);
+    out->val = static_cast<const double*>(src[5]); out->val2 = static_cast<const double*>(src[6]);
+    out->metrics = met;
+    return VTX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,383 @@
+// vtx_pipeline.cuh -- the integer/byte kernels either side of Smith-Waterman (sm_100a).
+// HBM-bound scatter/gather work: one thread per element, coalesced 4/8-byte accesses, no host
+// synchronisation between stages (every size that depends on data stays on the device).
+//
+//   vtx_k_cb_lookup     get_cell_barcode + HashMap<Vec<u8>,u32>     main.rs:737-750, 697-718
+//   vtx_k_cand_filter   CB miss / --umi gate + metric counters      main.rs:867-894
+//   vtx_k_compact       Scores{cell_index, umi, ..} push order      main.rs:923-930
+//   vtx_k_locus_prep    tile classes (haplotype width / alphabet)   (scheduler, replaces main.rs:250-254)
+//   vtx_k_slots         sort_by_key(cell_index) + group_by          main.rs:932, 1044, 1047-1057
+//   vtx_k_umi_collapse  per-UMI 0.75 consensus                      main.rs:1058-1082
+//   vtx_k_finalize      consensus_scoring / alt_frac / coverage     main.rs:1111-1164
+//   vtx_k_emit          TriMat::add_triplet in row-major order      main.rs:320-348
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "vtx_sw.cuh"
+
+namespace vtx {
+
+constexpr uint32_t kNoCb = 0xFFFFFFFFu;
+constexpr uint64_t kNoUmi = 0xFFFFFFFFFFFFFFFFull;
+constexpr uint32_t kInvalid = 0xFFFFFFFFu;
+
+__host__ __device__ inline uint64_t fnv1a64(const uint8_t* p, uint32_t n)
+{
+    uint64_t h = 1469598103934665603ull;
+    for (uint32_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+    return h;
+}
+
+struct BarcodeTable {
+    const int32_t* slot;      // [cap] barcode index or -1
+    uint32_t cap_mask;        // cap - 1 (cap is a power of two >= 2 n)
+    const uint8_t* bytes;
+    const uint32_t* off;      // [n + 1]
+};
+
+// one thread per read: exact byte-string lookup of the CB tag in the barcode list
+__global__ void vtx_k_cb_lookup(BarcodeTable t, uint32_t n_reads, const uint8_t* __restrict__ cb_bytes,
+                                const uint32_t* __restrict__ read_cb_off, const uint16_t* __restrict__ read_cb_len,
+                                int32_t* __restrict__ read_col)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    const uint32_t off = read_cb_off[r];
+    int32_t col = -1;
+    if (off != kNoCb) {
+        const uint32_t len = read_cb_len[r];
+        const uint8_t* key = cb_bytes + off;
+        uint32_t h = uint32_t(fnv1a64(key, len)) & t.cap_mask;
+        for (;;) {
+            const int32_t s = t.slot[h];
+            if (s < 0) break;
+            const uint32_t o = t.off[s], l2 = t.off[s + 1] - o;
+            if (l2 == len) {
+                bool eq = true;
+                for (uint32_t i = 0; i < len; ++i) eq &= (t.bytes[o + i] == key[i]);
+                if (eq) { col = s; break; }
+            }
+            h = (h + 1) & t.cap_mask;
+        }
+    }
+    read_col[r] = col;
+}
+
+// one thread per candidate: keep flag (for the compaction scan) + metric counters, warp-aggregated
+__global__ void vtx_k_cand_filter(uint64_t n_cand, const uint32_t* __restrict__ cand_read,
+                                  const int32_t* __restrict__ read_col, const uint64_t* __restrict__ read_umi_key,
+                                  int use_umi, uint32_t* __restrict__ keep, unsigned long long* __restrict__ metrics)
+{
+    const uint64_t c = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    bool miss_cb = false, miss_umi = false, ok = false;
+    if (c < n_cand) {
+        const uint32_t r = cand_read[c];
+        if (read_col[r] < 0) miss_cb = true;                                 // main.rs:868-876
+        else if (use_umi && read_umi_key[r] == kNoUmi) miss_umi = true;      // main.rs:880-888
+        else ok = true;
+        keep[c] = ok ? 1u : 0u;
+    }
+    const uint32_t b0 = __ballot_sync(0xffffffffu, miss_cb), b1 = __ballot_sync(0xffffffffu, miss_umi),
+                   b2 = __ballot_sync(0xffffffffu, ok);
+    if ((threadIdx.x & 31) == 0) {
+        if (b0) atomicAdd(metrics + 0, (unsigned long long)__popc(b0));
+        if (b1) atomicAdd(metrics + 1, (unsigned long long)__popc(b1));
+        if (b2) atomicAdd(metrics + 2, (unsigned long long)__popc(b2));
+    }
+}
+
+// largest l with cand_start[l] <= c
+__device__ __forceinline__ uint32_t locus_of_cand(const uint64_t* __restrict__ cand_start, uint32_t n_loci, uint64_t c)
+{
+    uint32_t lo = 0, hi = n_loci;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (cand_start[mid] <= c) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// kept candidates -> dense pair arrays (order preserved: locus-major, file order)
+__global__ void vtx_k_compact(uint64_t n_cand, const uint32_t* __restrict__ cand_read,
+                              const uint32_t* __restrict__ keep, const uint32_t* __restrict__ pidx,
+                              const int32_t* __restrict__ read_col, const uint64_t* __restrict__ read_umi_key,
+                              int use_umi, uint32_t* __restrict__ pair_read, uint32_t* __restrict__ pair_col,
+                              uint64_t* __restrict__ pair_umi)
+{
+    const uint64_t c = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (c >= n_cand || !keep[c]) return;
+    const uint32_t p = pidx[c], r = cand_read[c];
+    pair_read[p] = r;
+    pair_col[p] = uint32_t(read_col[r]);
+    if (use_umi) pair_umi[p] = read_umi_key[r];
+}
+
+__global__ void vtx_k_pair_start(uint32_t n_loci, const uint64_t* __restrict__ cand_start,
+                                 const uint32_t* __restrict__ pidx, uint32_t* __restrict__ pair_start)
+{
+    const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l <= n_loci) pair_start[l] = pidx[cand_start[l]];
+}
+
+// pairs given explicitly (vtx_score_pairs): pair_start from a locus-sorted pair_locus array
+__global__ void vtx_k_pair_start_explicit(uint32_t n_loci, uint32_t n_pairs, const uint32_t* __restrict__ pair_locus,
+                                          uint32_t* __restrict__ pair_start)
+{
+    const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l > n_loci) return;
+    uint32_t lo = 0, hi = n_pairs;                 // first p with pair_locus[p] >= l
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (pair_locus[mid] < l) lo = mid + 1; else hi = mid; }
+    pair_start[l] = lo;
+}
+
+// one warp per locus: tile class from haplotype width and alphabet, tiles per class
+__global__ void vtx_k_locus_prep(uint32_t n_loci, const uint8_t* __restrict__ hap_bytes,
+                                 const uint32_t* __restrict__ ref_off, const uint32_t* __restrict__ ref_len,
+                                 const uint32_t* __restrict__ alt_off, const uint32_t* __restrict__ alt_len,
+                                 const uint32_t* __restrict__ pair_start, int force_slow,
+                                 uint32_t* __restrict__ tcount /* [kNumClasses][n_loci + 1] */)
+{
+    const uint32_t l = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (l >= n_loci) return;
+    const uint32_t nr = ref_len[l], na = alt_len[l];
+    const uint8_t* rh = hap_bytes + ref_off[l];
+    const uint8_t* ah = hap_bytes + alt_off[l];
+    bool exotic = false;
+    // bytes that a decoded read base other than A/C/G/T could equal: "=MRSVWYHKDBN"
+    auto is_exotic = [](uint8_t b) {
+        return b == '=' || b == 'M' || b == 'R' || b == 'S' || b == 'V' || b == 'W' || b == 'Y' || b == 'H' ||
+               b == 'K' || b == 'D' || b == 'B' || b == 'N';
+    };
+    for (uint32_t j = lane; j < nr; j += 32) exotic |= is_exotic(rh[j]);
+    for (uint32_t j = lane; j < na; j += 32) exotic |= is_exotic(ah[j]);
+    exotic = __any_sync(0xffffffffu, exotic);
+    if (lane != 0) return;
+    const uint32_t nmax = max(nr, na);
+    int cls = kSlowClass;
+    if (!exotic && !force_slow) {
+#pragma unroll
+        for (int c = kNumFastClasses - 1; c >= 0; --c) if (nmax <= uint32_t(class_max_n(c))) cls = c;
+    }
+    const uint32_t np = pair_start[l + 1] - pair_start[l];
+#pragma unroll
+    for (int c = 0; c < kNumClasses; ++c) {
+        const uint32_t ppw = (c == kSlowClass) ? kSlowPairsPerWarp : 4u;
+        tcount[size_t(c) * (n_loci + 1) + l] = (c == cls) ? (np + ppw - 1) / ppw : 0u;
+    }
+}
+
+// One CTA per locus: rank every pair's cell (and, with --umi, its (cell, UMI)) among the distinct keys
+// of the locus.  slot = pair_start[locus] + rank, so slots of a locus are col-ascending and the final
+// triplets come out row-major sorted without a global sort.  O(d^2) compares per locus of depth d
+// (d ~ 50 here); keys staged through shared memory in chunks.
+constexpr int kSlotThreads = 128;
+constexpr int kSlotChunk = 1024;
+__global__ void __launch_bounds__(kSlotThreads) vtx_k_slots(
+    uint32_t n_loci, const uint32_t* __restrict__ pair_start, const uint32_t* __restrict__ pair_col,
+    const uint64_t* __restrict__ pair_umi, int use_umi, uint8_t* __restrict__ pair_first,
+    uint32_t* __restrict__ pair_cslot, uint32_t* __restrict__ pair_uslot, uint32_t* __restrict__ cslot_col,
+    uint32_t* __restrict__ cslot_locus, uint32_t* __restrict__ uslot_cslot)
+{
+    __shared__ uint32_t s_col[kSlotChunk];
+    __shared__ uint64_t s_umi[kSlotChunk];
+    __shared__ uint8_t s_first[kSlotChunk];
+    for (uint32_t l = blockIdx.x; l < n_loci; l += gridDim.x) {
+        const uint32_t ps = pair_start[l], d = pair_start[l + 1] - ps;
+        if (d == 0) continue;
+        // pass 1: is this pair the first occurrence of its cell / of its (cell, umi)?
+        for (uint32_t base = 0; base < d; base += kSlotThreads) {
+            const uint32_t p = base + threadIdx.x;
+            uint32_t colp = 0; uint64_t umip = 0; bool fc = true, fu = true;
+            if (p < d) { colp = pair_col[ps + p]; if (use_umi) umip = pair_umi[ps + p]; }
+            const uint32_t q_end = min(d, base + kSlotThreads);     // only q < p matter
+            for (uint32_t q0 = 0; q0 < q_end; q0 += kSlotChunk) {
+                __syncthreads();
+                for (uint32_t i = threadIdx.x; i < kSlotChunk && q0 + i < q_end; i += kSlotThreads) {
+                    s_col[i] = pair_col[ps + q0 + i];
+                    if (use_umi) s_umi[i] = pair_umi[ps + q0 + i];
+                }
+                __syncthreads();
+                if (p < d) {
+                    const uint32_t lim = min(uint32_t(kSlotChunk), min(q_end, p) > q0 ? min(q_end, p) - q0 : 0u);
+                    for (uint32_t i = 0; i < lim; ++i) {
+                        if (s_col[i] == colp) { fc = false; if (!use_umi || s_umi[i] == umip) fu = false; }
+                    }
+                }
+            }
+            if (p < d) pair_first[ps + p] = uint8_t((fc ? 1 : 0) | (fu ? 2 : 0));
+        }
+        __syncthreads();
+        // pass 2: rank = number of distinct smaller keys
+        for (uint32_t base = 0; base < d; base += kSlotThreads) {
+            const uint32_t p = base + threadIdx.x;
+            uint32_t colp = 0; uint64_t umip = 0; uint32_t cs = 0, us = 0;
+            if (p < d) { colp = pair_col[ps + p]; if (use_umi) umip = pair_umi[ps + p]; }
+            for (uint32_t q0 = 0; q0 < d; q0 += kSlotChunk) {
+                __syncthreads();
+                for (uint32_t i = threadIdx.x; i < kSlotChunk && q0 + i < d; i += kSlotThreads) {
+                    s_col[i] = pair_col[ps + q0 + i];
+                    s_first[i] = pair_first[ps + q0 + i];
+                    if (use_umi) s_umi[i] = pair_umi[ps + q0 + i];
+                }
+                __syncthreads();
+                if (p < d) {
+                    const uint32_t lim = min(uint32_t(kSlotChunk), d - q0);
+                    for (uint32_t i = 0; i < lim; ++i) {
+                        const uint32_t cq = s_col[i]; const uint8_t fq = s_first[i];
+                        cs += ((fq & 1) && cq < colp) ? 1u : 0u;
+                        if (use_umi) us += ((fq & 2) && (cq < colp || (cq == colp && s_umi[i] < umip))) ? 1u : 0u;
+                    }
+                }
+            }
+            if (p < d) {
+                const uint8_t fp = pair_first[ps + p];
+                pair_cslot[ps + p] = ps + cs;
+                if (fp & 1) { cslot_col[ps + cs] = colp; cslot_locus[ps + cs] = l; }
+                if (use_umi) {
+                    pair_uslot[ps + p] = ps + us;
+                    if (fp & 2) uslot_cslot[ps + us] = ps + cs;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// one thread per UMI slot: collapse the reads of one (locus, cell, UMI) -- main.rs:1058-1082.
+// ref_frac/alt_frac >= 0.75 in f64 is exactly 4*count >= 3*total for these integer ranges.
+__global__ void vtx_k_umi_collapse(uint32_t n_slots_ub, const uint32_t* __restrict__ n_pairs_ptr,
+                                   const uint32_t* __restrict__ uslot_cslot, const uint32_t* __restrict__ ucnt,
+                                   uint32_t* __restrict__ ccnt)
+{
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_slots_ub || q >= *n_pairs_ptr) return;
+    const uint32_t cs = uslot_cslot[q];
+    if (cs == kInvalid) return;
+    const uint4 c = reinterpret_cast<const uint4*>(ucnt)[q];
+    const uint32_t r = c.x, a = c.y, u = c.z, t = r + a + u;
+    if (t == 0) return;                               // every read of this UMI evaluated to None
+    uint32_t k;
+    if (4ull * a >= 3ull * t) k = 1;                  // ALT
+    else if (4ull * r >= 3ull * t) k = 0;             // REF
+    else k = 2;                                       // UNKNOWN
+    atomicAdd(ccnt + size_t(cs) * 4 + k, 1u);
+}
+
+// one thread per cell slot: mode value + keep flag
+__global__ void vtx_k_finalize(uint32_t n_slots_ub, const uint32_t* __restrict__ n_pairs_ptr, int mode,
+                               const uint32_t* __restrict__ cslot_col, const uint32_t* __restrict__ ccnt,
+                               uint32_t* __restrict__ keep)
+{
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_slots_ub) return;
+    uint32_t k = 0;
+    if (q < *n_pairs_ptr && cslot_col[q] != kInvalid) {
+        if (mode == 0) {                               // consensus drops cells without ref/alt evidence, main.rs:1120-1126
+            const uint4 c = reinterpret_cast<const uint4*>(ccnt)[q];
+            k = (c.x > 0 || c.y > 0) ? 1u : 0u;
+        } else k = 1u;                                 // alt_frac / coverage emit every present cell
+    }
+    keep[q] = k;
+}
+
+struct ResultArrays {
+    uint32_t* row; uint32_t* col; uint32_t* ref_cnt; uint32_t* alt_cnt; uint32_t* unk_cnt;
+    double* val; double* val2;
+};
+
+__global__ void vtx_k_emit(uint32_t n_slots_ub, int mode, const uint32_t* __restrict__ keep,
+                           const uint32_t* __restrict__ oidx, const unsigned long long* __restrict__ res_base,
+                           const uint32_t* __restrict__ cslot_col, const uint32_t* __restrict__ cslot_locus,
+                           const uint32_t* __restrict__ locus_row, const uint32_t* __restrict__ ccnt, ResultArrays out)
+{
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_slots_ub || !keep[q]) return;
+    const uint64_t o = *res_base + oidx[q];
+    const uint4 c = reinterpret_cast<const uint4*>(ccnt)[q];
+    const uint32_t r = c.x, a = c.y, u = c.z;
+    out.row[o] = locus_row[cslot_locus[q]];
+    out.col[o] = cslot_col[q];
+    out.ref_cnt[o] = r; out.alt_cnt[o] = a; out.unk_cnt[o] = u;
+    double v = 0.0, v2 = 0.0;
+    if (mode == 0) v = (r > 0 && a > 0) ? 3.0 : (a > 0 ? 2.0 : 1.0);                 // main.rs:1120-1126
+    else if (mode == 2) v = double(a) / (double(r) + double(a) + double(u));        // main.rs:1140-1141 (0/0 = NaN)
+    else { v = double(a); v2 = double(r); }                                           // main.rs:1160-1161
+    out.val[o] = v; out.val2[o] = v2;
+}
+
+__global__ void vtx_k_bump(unsigned long long* res_n, const uint32_t* __restrict__ total)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) *res_n += *total;
+}
+
+// ---------------------------------------------------------------------------------------------
+// exclusive scan of uint32 (out has n + 1 entries; out[n] = total).  Three small kernels.
+// ---------------------------------------------------------------------------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total)
+{
+    __shared__ uint32_t warp_sums[kScanThreads / 32];
+    __shared__ uint32_t s_total;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) warp_sums[w] = x;
+    __syncthreads();
+    if (w == 0) {
+        uint32_t s = lane < kScanThreads / 32 ? warp_sums[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
+        if (lane < kScanThreads / 32) warp_sums[lane] = s;
+        if (lane == kScanThreads / 32 - 1) s_total = s;
+    }
+    __syncthreads();
+    const uint32_t prefix = (w ? warp_sums[w - 1] : 0) + x - v;
+    *total = s_total;
+    __syncthreads();
+    return prefix;
+}
+
+__global__ void __launch_bounds__(kScanThreads) vtx_k_scan_tiles(const uint32_t* __restrict__ in, uint64_t n,
+                                                                 uint32_t* __restrict__ out, uint32_t* __restrict__ sums)
+{
+    const uint64_t base = uint64_t(blockIdx.x) * kScanTile + uint64_t(threadIdx.x) * kScanItems;
+    uint32_t v[kScanItems], s = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) { v[i] = (base + i < n) ? in[base + i] : 0; s += v[i]; }
+    uint32_t total;
+    uint32_t p = block_exclusive_scan(s, &total);
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) { if (base + i < n) out[base + i] = p; p += v[i]; }
+    if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kScanThreads) vtx_k_scan_sums(uint32_t* __restrict__ sums, uint32_t n_blocks,
+                                                                uint32_t* __restrict__ total_out)
+{
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < n_blocks; base += kScanThreads) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < n_blocks ? sums[i] : 0;
+        uint32_t total;
+        const uint32_t p = block_exclusive_scan(v, &total);
+        if (i < n_blocks) sums[i] = carry + p;
+        carry += total;
+    }
+    if (threadIdx.x == 0) *total_out = carry;
+}
+
+__global__ void __launch_bounds__(kScanThreads) vtx_k_scan_add(uint32_t* __restrict__ out, uint64_t n,
+                                                               const uint32_t* __restrict__ sums)
+{
+    const uint64_t base = uint64_t(blockIdx.x) * kScanTile + uint64_t(threadIdx.x) * kScanItems;
+    const uint32_t add = sums[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) if (base + i < n) out[base + i] += add;
+}
+
+}  // namespace vtx

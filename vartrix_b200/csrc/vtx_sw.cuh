@@ -1,0 +1,297 @@
+// vtx_sw.cuh -- Smith-Waterman kernels (sm_100a) of the vartrix read-scoring path.
+//
+// Replaces bio::alignment::pairwise::banded::Aligner::local x2 per (read, locus) pair
+// (/root/reference/src/main.rs:898-901) and fuses evaluate_scores (main.rs:1019-1030) plus the
+// count-matrix increment as an epilogue.  Integer DP, no tensor cores:
+//
+//  * ref and alt haplotype scores travel in the two int16 lanes of one 32-bit word and every cell
+//    update is 5 native DPX/SIMD instructions: 2x VIADDMNMX.S16x2 (E, F), VIADD.16x2 (diag + s),
+//    VIMNMX3.S16x2.RELU (H) and VIADD.16x2 (H + gap_open + gap_extend), plus half a VIMNMX3 for the
+//    running maximum.
+//  * LPP (=8) lanes cooperate on one pair: lane g owns C consecutive haplotype columns whose H/F
+//    state lives in registers; rows are skewed by one step per lane (anti-diagonal wavefront) and the
+//    boundary column travels to lane g+1 with two __shfl_up_sync per step.  A warp scores 32/LPP pairs
+//    of the SAME locus at a time (a "tile").
+//  * the substitution scores come from a per-locus profile in shared memory (5 read-base rows x
+//    columns, words = {s_ref, s_alt}), built once per locus per warp and read with conflict-free
+//    LDS.128; the read itself is turned into a per-row byte offset into that profile.
+//  * out-of-range rows/columns are all-mismatch sentinels, which can never raise a local maximum, so the
+//    inner loop carries no bounds predicates.
+//
+// Exactness: H <= read length < 32768 and E/F >= -16384 - (rows + cols), so int16 never saturates for
+// reads up to kFastMaxRead bases; longer reads, haplotypes wider than the largest tile class or with
+// IUPAC/"=" bytes go to vtx_k_sw_generic (plain per-thread DP with byte equality).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace vtx {
+
+constexpr int kMatch = 1, kMismatch = -5, kGapOpen = -5, kGapExtend = -1;   // main.rs:35-38
+constexpr int kGoe = kGapOpen + kGapExtend;                                 // cost of the first gap base
+
+__host__ __device__ constexpr uint32_t pack2(int lo, int hi)
+{
+    return (uint32_t(uint16_t(int16_t(hi))) << 16) | uint32_t(uint16_t(int16_t(lo)));
+}
+constexpr uint32_t kGE2 = pack2(kGapExtend, kGapExtend);
+constexpr uint32_t kGOE2 = pack2(kGoe, kGoe);
+constexpr uint32_t kNEG2 = pack2(-16384, -16384);
+// profile entries are biased by -kGoe because the stored state is H + kGoe
+constexpr int kProfMatch = kMatch - kGoe, kProfMis = kMismatch - kGoe;     // 7, 1
+
+constexpr int kFastMaxRead = 1024;       // longest read the fast kernels take (smem row-code buffer)
+constexpr int kNumFastClasses = 4;
+constexpr int kSlowClass = kNumFastClasses;
+constexpr int kNumClasses = kNumFastClasses + 1;
+constexpr int kTileChunk = 8;            // tiles grabbed per atomic
+
+// fast tile classes: lanes per pair, columns per lane, storage stride (words; CS % 4 == 0, (CS/4) odd
+// so the 8 lanes of an LDS.128 wavefront hit 8 distinct 16-byte bank groups)
+template <int CLS> struct TileClass;
+template <> struct TileClass<0> { static constexpr int LPP = 8, C = 26, CS = 28; };   // n <= 208 (SNV, pad 100)
+template <> struct TileClass<1> { static constexpr int LPP = 8, C = 29, CS = 36; };   // n <= 232 (indels <= 30)
+template <> struct TileClass<2> { static constexpr int LPP = 8, C = 32, CS = 36; };   // n <= 256
+template <> struct TileClass<3> { static constexpr int LPP = 8, C = 40, CS = 44; };   // n <= 320
+__host__ __device__ constexpr int class_max_n(int cls)
+{
+    return cls == 0 ? 208 : cls == 1 ? 232 : cls == 2 ? 256 : cls == 3 ? 320 : 0x7fffffff;
+}
+constexpr int kSlowPairsPerWarp = 16;    // generic kernel: one thread per (pair, haplotype)
+
+struct SwArgs {
+    // staged batch
+    const uint8_t* hap_bytes;
+    const uint32_t* ref_off; const uint32_t* ref_len; const uint32_t* alt_off; const uint32_t* alt_len;
+    const uint8_t* read_nib; const uint64_t* read_off; const uint32_t* read_len;
+    // pairs (locus-major) and tiles of this class
+    const uint32_t* pair_read;
+    const uint32_t* pair_start;     // [n_loci + 1]
+    const uint32_t* tile_start;     // [n_loci + 1] exclusive scan of this class's tiles per locus
+    uint32_t n_loci;
+    uint32_t* tile_counter;         // work-stealing cursor (zeroed before launch)
+    // epilogue
+    const uint32_t* pair_slot;      // counter slot of each pair (nullptr: no scatter)
+    uint32_t* counters;             // [slot][4] = {ref, alt, unk, -}
+    uint32_t* pair_scores;          // optional [pair] packed {ref, alt} int16 (nullptr: not kept)
+    int32_t min_score;              // MIN_SCORE main.rs:30
+    int32_t mcap;                   // row-code capacity (even, >= longest read in the batch)
+    // generic kernel only
+    uint32_t* scratch;              // [warps][max_hap + 1][32]
+    uint32_t max_hap;
+};
+
+__device__ __forceinline__ uint32_t hap_code(uint8_t b)
+{   // haplotype byte -> profile column code; anything but upper-case ACGT can never equal a fast-path read base
+    return b == 'A' ? 0u : b == 'C' ? 1u : b == 'G' ? 2u : b == 'T' ? 3u : 5u;
+}
+__device__ __forceinline__ uint32_t nib_code(uint32_t nib)
+{   // BAM nibble -> profile row: A(1) C(2) G(4) T(8) -> 0..3, everything else -> 4 (matches nothing)
+    return (0x4444444344424104ull >> (nib * 4)) & 0xF;
+}
+
+// largest l in [0, n) with a[l] <= v  (a ascending, a[0] == 0 <= v < a[n])
+__device__ __forceinline__ uint32_t upper_locus(const uint32_t* __restrict__ a, uint32_t n, uint32_t v)
+{
+    uint32_t lo = 0, hi = n;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(a + mid) <= v) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// main.rs:1019-1030 fused with the count increment that main.rs:1032-1039 / 1090-1098 perform later
+__device__ __forceinline__ void call_and_scatter(const SwArgs& a, uint32_t pair, uint32_t packed)
+{
+    const int ref_score = int(int16_t(packed & 0xFFFF)), alt_score = int(int16_t(packed >> 16));
+    if (a.pair_scores) a.pair_scores[pair] = packed;
+    if (!a.pair_slot) return;
+    if (ref_score < a.min_score && alt_score < a.min_score) return;            // None
+    const uint32_t k = ref_score > alt_score ? 0u : (alt_score > ref_score ? 1u : 2u);
+    atomicAdd(a.counters + size_t(a.pair_slot[pair]) * 4 + k, 1u);
+}
+
+template <int CLS>
+__global__ void __launch_bounds__(256, 2) vtx_k_sw_pairs(const SwArgs a)
+{
+    using TC = TileClass<CLS>;
+    constexpr int LPP = TC::LPP, C = TC::C, CS = TC::CS;
+    constexpr int PPW = 32 / LPP;              // pairs per warp tile
+    constexpr int RS = LPP * CS;               // profile row stride in words (multiple of 32)
+    constexpr int M = LPP;                     // sentinel margin of the row-code buffer
+    static_assert(CS % 4 == 0 && ((CS / 4) & 1) == 1 && CS >= C, "bank-conflict-free stride");
+    static_assert(RS % 32 == 0, "row stride keeps lanes on their banks");
+    constexpr uint32_t kSentinel = 4u * RS * 4u;   // byte offset of the all-mismatch row
+
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane % LPP, grp = lane / LPP;
+    const int code_stride = a.mcap + 2 * M;                      // u16 entries per group
+    const size_t warp_bytes = size_t(5 * RS) * 4 + size_t(PPW) * code_stride * 2;
+    uint8_t* wbase = smem_raw + warp * ((warp_bytes + 15) & ~size_t(15));
+    uint32_t* prof = reinterpret_cast<uint32_t*>(wbase);
+    uint16_t* codes = reinterpret_cast<uint16_t*>(wbase + size_t(5 * RS) * 4) + grp * code_stride;
+
+    const uint32_t n_tiles = __ldg(a.tile_start + a.n_loci);
+    uint32_t cached_locus = 0xFFFFFFFFu;
+
+    for (;;) {
+        uint32_t chunk = 0;
+        if (lane == 0) chunk = atomicAdd(a.tile_counter, 1u);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        const uint32_t t_begin = chunk * kTileChunk;
+        if (t_begin >= n_tiles) break;
+        const uint32_t t_end = min(t_begin + kTileChunk, n_tiles);
+
+        for (uint32_t tile = t_begin; tile < t_end; ++tile) {
+            const uint32_t locus = upper_locus(a.tile_start, a.n_loci, tile);
+            const uint32_t p0 = __ldg(a.pair_start + locus) + PPW * (tile - __ldg(a.tile_start + locus));
+            const uint32_t p_end = __ldg(a.pair_start + locus + 1);
+
+            __syncwarp();
+            // ---- per-locus substitution profile (only when the locus changes) ----
+            if (locus != cached_locus) {
+                cached_locus = locus;
+                const uint8_t* rh = a.hap_bytes + __ldg(a.ref_off + locus);
+                const uint8_t* ah = a.hap_bytes + __ldg(a.alt_off + locus);
+                const int n_ref = int(__ldg(a.ref_len + locus)), n_alt = int(__ldg(a.alt_len + locus));
+                for (int idx = lane; idx < RS; idx += 32) {
+                    const int gg = idx / CS, k = idx - gg * CS;
+                    const int j = gg * C + k;
+                    uint32_t rb = 5, ab = 5;
+                    if (k < C) {
+                        if (j < n_ref) rb = hap_code(__ldg(rh + j));
+                        if (j < n_alt) ab = hap_code(__ldg(ah + j));
+                    }
+#pragma unroll
+                    for (uint32_t r = 0; r < 5; ++r)
+                        prof[r * RS + idx] = pack2(r == rb ? kProfMatch : kProfMis, r == ab ? kProfMatch : kProfMis);
+                }
+            }
+            // ---- row codes of this group's read: byte offset of the profile row per read base ----
+            const uint32_t pair = p0 + grp;
+            const bool active = pair < p_end;
+            int m = 0;
+            const uint8_t* nib = nullptr;
+            if (active) {
+                const uint32_t r = __ldg(a.pair_read + pair);
+                m = int(__ldg(a.read_len + r));
+                nib = a.read_nib + __ldg(a.read_off + r);
+            }
+            for (int e = g; e < code_stride; e += LPP)
+                if (e < M || e >= M + m) codes[e] = uint16_t(kSentinel);
+            for (int b = g; 2 * b < m; b += LPP) {
+                const uint32_t by = __ldg(nib + b);
+                codes[M + 2 * b] = uint16_t(nib_code(by >> 4) * (RS * 4));
+                if (2 * b + 1 < m) codes[M + 2 * b + 1] = uint16_t(nib_code(by & 0xF) * (RS * 4));
+            }
+            int mmax = m;
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) mmax = max(mmax, __shfl_xor_sync(0xffffffffu, mmax, o));
+            __syncwarp();
+
+            // ---- anti-diagonal wavefront: lane g works on row (t - g) of its C columns ----
+            uint32_t hg[C], f[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) { hg[c] = kGOE2; f[c] = kNEG2; }
+            uint32_t hg_last = kGOE2, e_last = kNEG2, diag_save = kGOE2, best = 0;
+            const uint8_t* lane_prof = reinterpret_cast<const uint8_t*>(prof) + g * CS * 4;
+            const uint16_t* my_codes = codes + M - g;
+            const int steps = mmax + LPP - 1;
+            for (int t = 0; t < steps; ++t) {
+                uint32_t hl = __shfl_up_sync(0xffffffffu, hg_last, 1, LPP);
+                uint32_t el = __shfl_up_sync(0xffffffffu, e_last, 1, LPP);
+                if (g == 0) { hl = kGOE2; el = kNEG2; }
+                const uint4* prow = reinterpret_cast<const uint4*>(lane_prof + my_codes[t]);
+                uint32_t diag = diag_save;
+                diag_save = hl;
+                uint32_t e = el, hleft = hl;
+#pragma unroll
+                for (int q = 0; q < (C + 3) / 4; ++q) {
+                    const uint4 s4 = prow[q];
+                    const uint32_t sv[4] = { s4.x, s4.y, s4.z, s4.w };
+                    uint32_t hh[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int c = 4 * q + k;
+                        if (c < C) {
+                            const uint32_t fc = __viaddmax_s16x2(f[c], kGE2, hg[c]);     // F[i][c]
+                            e = __viaddmax_s16x2(e, kGE2, hleft);                       // E[i][c]
+                            const uint32_t tt = __vadd2(diag, sv[k]);                   // H[i-1][c-1] + s
+                            const uint32_t h = __vimax3_s16x2_relu(tt, e, fc);          // H[i][c]
+                            hh[k] = h;
+                            diag = hg[c];
+                            hleft = __vadd2(h, kGOE2);
+                            hg[c] = hleft;
+                            f[c] = fc;
+                        } else {
+                            hh[k] = 0;
+                        }
+                    }
+                    best = __vimax3_s16x2(best, hh[0], hh[1]);
+                    if (4 * q + 2 < C) best = __vimax3_s16x2(best, hh[2], hh[3]);
+                }
+                hg_last = hleft;
+                e_last = e;
+            }
+            // ---- epilogue: group maximum, call, atomic scatter ----
+#pragma unroll
+            for (int o = LPP / 2; o >= 1; o >>= 1) best = __vmaxs2(best, __shfl_xor_sync(0xffffffffu, best, o));
+            if (active && g == 0) call_and_scatter(a, pair, best);
+        }
+    }
+}
+
+// Generic kernel: any read length / haplotype width / byte alphabet.  One thread per (pair, haplotype),
+// plain row-by-row Gotoh DP with exact byte equality against "=ACMGRSVTWYHKDBN"[nibble] (main.rs:896-898).
+// Rare path (IUPAC bytes in a REF allele, --padding > 150, very long reads): clarity over speed.
+__global__ void __launch_bounds__(128) vtx_k_sw_generic(const SwArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint32_t* rowbuf = a.scratch + size_t(gwarp) * (size_t(a.max_hap) + 1) * 32 + lane;   // [(j)*32], {H, F} per column
+    const uint32_t n_tiles = __ldg(a.tile_start + a.n_loci);
+    const int sub = lane >> 1, which = lane & 1;
+    for (;;) {
+        uint32_t tile = 0;
+        if (lane == 0) tile = atomicAdd(a.tile_counter, 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= n_tiles) break;
+        const uint32_t locus = upper_locus(a.tile_start, a.n_loci, tile);
+        const uint32_t p0 = __ldg(a.pair_start + locus) + kSlowPairsPerWarp * (tile - __ldg(a.tile_start + locus));
+        const uint32_t p_end = __ldg(a.pair_start + locus + 1);
+        const uint32_t pair = p0 + sub;
+        int score = 0;
+        if (pair < p_end) {
+            const uint32_t r = __ldg(a.pair_read + pair);
+            const int m = int(__ldg(a.read_len + r));
+            const uint8_t* nib = a.read_nib + __ldg(a.read_off + r);
+            const uint8_t* hap = a.hap_bytes + (which ? __ldg(a.alt_off + locus) : __ldg(a.ref_off + locus));
+            const int n = int(which ? __ldg(a.alt_len + locus) : __ldg(a.ref_len + locus));
+            for (int j = 0; j <= n; ++j) rowbuf[size_t(j) * 32] = pack2(0, -30000);
+            for (int i = 0; i < m; ++i) {
+                const uint32_t by = __ldg(nib + (i >> 1));
+                const uint8_t xc = uint8_t("=ACMGRSVTWYHKDBN"[(i & 1) ? (by & 0xF) : (by >> 4)]);
+                int diag = 0, left = 0, e = -30000;
+                for (int j = 1; j <= n; ++j) {
+                    const uint32_t w = rowbuf[size_t(j) * 32];
+                    const int up = int(int16_t(w & 0xFFFF)), fup = int(int16_t(w >> 16));
+                    const int fv = max(fup + kGapExtend, up + kGoe);
+                    e = max(e + kGapExtend, left + kGoe);
+                    int h = diag + (xc == __ldg(hap + j - 1) ? kMatch : kMismatch);
+                    h = max(max(h, fv), max(e, 0));
+                    rowbuf[size_t(j) * 32] = pack2(h, max(fv, -30000));
+                    diag = up;
+                    left = h;
+                    e = max(e, -30000);
+                    score = max(score, h);
+                }
+            }
+        }
+        const int other = __shfl_xor_sync(0xffffffffu, score, 1);
+        if (pair < p_end && which == 0) call_and_scatter(a, pair, pack2(score, other));
+    }
+}
+
+}  // namespace vtx

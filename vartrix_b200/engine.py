@@ -1,0 +1,282 @@
+"""Python host mirror of the engine's C ABI (used by the tests and bench.py; a production host is
+the C++ CLI in csrc/host or any FFI binding of include/vartrix_b200.h).
+
+Names follow the reference (``/root/reference/src/main.rs``): a *locus* is one VCF record, a
+*candidate* one BAM record fetched for a locus that passed the record filters (main.rs:833-865), a
+*pair* a candidate whose cell barcode is in the barcode list (main.rs:867-877) -- the unit that
+reaches the aligner (main.rs:896-930).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _capi
+
+MODES = _capi.MODES
+NO_CB, NO_UMI = _capi.NO_CB, _capi.NO_UMI
+
+
+class VtxError(RuntimeError):
+    pass
+
+
+_FIELDS = ("locus_row", "hap_bytes", "ref_off", "ref_len", "alt_off", "alt_len", "cand_start", "read_nib",
+           "read_off", "read_len", "cb_bytes", "read_cb_off", "read_cb_len", "read_umi_key", "cand_read")
+_DTYPES = dict(locus_row=np.uint32, hap_bytes=np.uint8, ref_off=np.uint32, ref_len=np.uint32, alt_off=np.uint32,
+               alt_len=np.uint32, cand_start=np.uint64, read_nib=np.uint8, read_off=np.uint64, read_len=np.uint32,
+               cb_bytes=np.uint8, read_cb_off=np.uint32, read_cb_len=np.uint16, read_umi_key=np.uint64,
+               cand_read=np.uint32)
+
+
+@dataclass
+class StagedBatch:
+    """One shard of loci staged as the SoA `vtx_batch` of include/vartrix_b200.h (numpy, host)."""
+    locus_row: np.ndarray
+    hap_bytes: np.ndarray
+    ref_off: np.ndarray
+    ref_len: np.ndarray
+    alt_off: np.ndarray
+    alt_len: np.ndarray
+    cand_start: np.ndarray
+    read_nib: np.ndarray
+    read_off: np.ndarray
+    read_len: np.ndarray
+    cb_bytes: np.ndarray
+    read_cb_off: np.ndarray
+    read_cb_len: np.ndarray
+    read_umi_key: np.ndarray
+    cand_read: np.ndarray
+    n_rows: int = 0
+
+    FIELDS = _FIELDS
+
+    def __post_init__(self):
+        for f in _FIELDS:
+            setattr(self, f, np.ascontiguousarray(getattr(self, f), dtype=_DTYPES[f]))
+
+    @classmethod
+    def from_fields(cls, src, n_rows=None) -> "StagedBatch":
+        """Build from any object/dict exposing the same field names (e.g. the oracle's Batch)."""
+        get = (lambda k: src[k]) if isinstance(src, dict) else (lambda k: getattr(src, k))
+        nr = n_rows if n_rows is not None else int(src["n_rows"] if isinstance(src, dict) else getattr(src, "n_rows", 0))
+        return cls(n_rows=nr, **{f: get(f) for f in _FIELDS})
+
+    @property
+    def n_loci(self): return int(self.locus_row.size)
+    @property
+    def n_reads(self): return int(self.read_len.size)
+    @property
+    def n_cand(self): return int(self.cand_read.size)
+
+    def nbytes(self) -> int:
+        return int(sum(getattr(self, f).nbytes for f in _FIELDS))
+
+    def to_c(self) -> _capi.Batch:
+        b = _capi.Batch()
+        p = lambda a: a.ctypes.data if a.size else None
+        b.n_loci = self.n_loci; b.locus_row = p(self.locus_row)
+        b.hap_bytes = p(self.hap_bytes); b.hap_bytes_len = self.hap_bytes.size
+        b.ref_off = p(self.ref_off); b.ref_len = p(self.ref_len); b.alt_off = p(self.alt_off); b.alt_len = p(self.alt_len)
+        b.cand_start = p(self.cand_start)
+        b.n_reads = self.n_reads; b.read_nib = p(self.read_nib); b.read_nib_len = self.read_nib.size
+        b.read_off = p(self.read_off); b.read_len = p(self.read_len)
+        b.cb_bytes = p(self.cb_bytes); b.cb_bytes_len = self.cb_bytes.size
+        b.read_cb_off = p(self.read_cb_off); b.read_cb_len = p(self.read_cb_len); b.read_umi_key = p(self.read_umi_key)
+        b.n_cand = self.n_cand; b.cand_read = p(self.cand_read)
+        return b
+
+    def shard(self, lo: int, hi: int) -> "StagedBatch":
+        """Loci [lo, hi) as a self-contained shard (reads re-indexed) -- locus sharding across GPUs."""
+        cs = self.cand_start
+        c0, c1 = int(cs[lo]), int(cs[hi])
+        cr = self.cand_read[c0:c1]
+        used, inv = np.unique(cr, return_inverse=True)
+        # re-pack reads and CB bytes compactly (16-byte aligned reads)
+        rl = self.read_len[used]
+        nb = (rl.astype(np.uint64) + 1) // 2
+        stride = (nb + 15) // 16 * 16
+        new_off = np.zeros(len(used), np.uint64)
+        if len(used):
+            new_off[1:] = np.cumsum(stride)[:-1]
+        nib = np.zeros(int(stride.sum()) if len(used) else 0, np.uint8)
+        for i, r in enumerate(used):              # shards are cut once per run; clarity over speed
+            o = int(self.read_off[r]); n = int(nb[i])
+            nib[int(new_off[i]): int(new_off[i]) + n] = self.read_nib[o:o + n]
+        return StagedBatch(
+            locus_row=self.locus_row[lo:hi], hap_bytes=self.hap_bytes, ref_off=self.ref_off[lo:hi],
+            ref_len=self.ref_len[lo:hi], alt_off=self.alt_off[lo:hi], alt_len=self.alt_len[lo:hi],
+            cand_start=(cs[lo:hi + 1] - cs[lo]), read_nib=nib, read_off=new_off, read_len=rl,
+            cb_bytes=self.cb_bytes, read_cb_off=self.read_cb_off[used], read_cb_len=self.read_cb_len[used],
+            read_umi_key=self.read_umi_key[used], cand_read=inv.astype(np.uint32), n_rows=self.n_rows)
+
+
+@dataclass
+class Barcodes:
+    """De-duplicated barcode list in first-seen order (load_barcodes, main.rs:697-718)."""
+    keys: list
+    bytes_: np.ndarray = field(default=None)
+    off: np.ndarray = field(default=None)
+
+    def __post_init__(self):
+        off = np.zeros(len(self.keys) + 1, np.uint32)
+        if self.keys:
+            off[1:] = np.cumsum([len(k) for k in self.keys])
+        self.off = off
+        self.bytes_ = (np.frombuffer(b"".join(self.keys), np.uint8).copy() if self.keys else np.zeros(0, np.uint8))
+
+    def __len__(self): return len(self.keys)
+
+
+@dataclass
+class Triplets:
+    """Finished (row, col, value) entries in TriMat insertion order (main.rs:320-348)."""
+    row: np.ndarray
+    col: np.ndarray
+    ref_cnt: np.ndarray
+    alt_cnt: np.ndarray
+    unk_cnt: np.ndarray
+    val: np.ndarray
+    val2: np.ndarray
+    metrics: dict
+
+
+def _np_from(ptr, n, dt):
+    if n == 0 or not ptr:
+        return np.zeros(0, dt)
+    ct = np.ctypeslib.as_ctypes_type(dt)
+    return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), shape=(n,)).copy()
+
+
+class Engine:
+    """One engine context = one GPU (vtx_ctx).  Mirrors the role of the rayon pool + merge loop."""
+
+    def __init__(self, scoring_method: str = "consensus", umi: bool = False, device: int = 0, stream: int = 0,
+                 keep_scores: bool = False, min_score: int = 25):
+        self._L = _capi.load()
+        cfg = _capi.Config(device=device, mode=MODES[scoring_method], use_umi=int(bool(umi)), match=1, mismatch=-5,
+                           gap_open=-5, gap_extend=-1, min_score=min_score, stream=stream or None,
+                           flags=_capi.F_KEEP_SCORES if keep_scores else 0)
+        h = C.c_void_p()
+        rc = self._L.vtx_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise VtxError(f"vtx_create failed ({rc}): {self._L.vtx_last_error(None).decode()}")
+        self._h = h
+        self.scoring_method, self.umi, self.device = scoring_method, umi, device
+        self._keep = []     # host buffers that must outlive the asynchronous copies
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.vtx_destroy(self._h)
+            self._h = None
+
+    def __enter__(self): return self
+    def __exit__(self, *a): self.close()
+    def __del__(self):
+        try: self.close()
+        except Exception: pass
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise VtxError(f"{what} failed ({rc}): {self._L.vtx_last_error(self._h).decode()}")
+
+    def set_barcodes(self, bcs: Barcodes):
+        self._ck(self._L.vtx_set_barcodes(self._h, bcs.bytes_.ctypes.data if bcs.bytes_.size else None,
+                                          bcs.off.ctypes.data, len(bcs)), "vtx_set_barcodes")
+        self.n_cols = len(bcs)
+
+    def submit(self, batch: StagedBatch):
+        cb = batch.to_c()
+        self._keep.append(batch)
+        self._ck(self._L.vtx_submit(self._h, C.byref(cb)), "vtx_submit")
+
+    def submit_device(self, cbatch: _capi.Batch, max_read_len: int, max_hap_len: int):
+        self._ck(self._L.vtx_submit_device_ex(self._h, C.byref(cbatch), max_read_len, max_hap_len), "vtx_submit_device_ex")
+
+    def _triplets(self, res: _capi.Result) -> Triplets:
+        n = int(res.n)
+        m = res.metrics
+        return Triplets(_np_from(res.row, n, np.uint32), _np_from(res.col, n, np.uint32), _np_from(res.ref_cnt, n, np.uint32),
+                        _np_from(res.alt_cnt, n, np.uint32), _np_from(res.unk_cnt, n, np.uint32),
+                        _np_from(res.val, n, np.float64), _np_from(res.val2, n, np.float64),
+                        dict(num_not_cell_bc=int(m.num_not_cell_bc), num_non_umi=int(m.num_non_umi), num_scored=int(m.num_scored)))
+
+    def finish(self) -> Triplets:
+        res = _capi.Result()
+        self._ck(self._L.vtx_finish(self._h, C.byref(res)), "vtx_finish")
+        self._keep.clear()
+        return self._triplets(res)
+
+    def finish_device(self) -> _capi.Result:
+        res = _capi.Result()
+        self._ck(self._L.vtx_finish_device(self._h, C.byref(res)), "vtx_finish_device")
+        self._keep.clear()
+        return res
+
+    def sync(self):
+        self._ck(self._L.vtx_sync(self._h), "vtx_sync")
+
+    def timing(self) -> dict:
+        t = _capi.Timing()
+        self._ck(self._L.vtx_last_timing(self._h, C.byref(t)), "vtx_last_timing")
+        return dict(h2d_ms=t.h2d_ms, prep_ms=t.prep_ms, sw_ms=t.sw_ms, post_ms=t.post_ms, n_pairs=int(t.n_pairs),
+                    sw_launches=int(t.sw_launches), total_launches=int(t.total_launches))
+
+    def run(self, batch: StagedBatch) -> Triplets:
+        self.submit(batch)
+        return self.finish()
+
+    def score_pairs(self, batch: StagedBatch, pair_read, pair_locus):
+        pr = np.ascontiguousarray(pair_read, np.uint32); pl = np.ascontiguousarray(pair_locus, np.uint32)
+        rs = np.zeros(len(pr), np.int16); as_ = np.zeros(len(pr), np.int16)
+        cb = batch.to_c()
+        self._ck(self._L.vtx_score_pairs(self._h, C.byref(cb), len(pr), pr.ctypes.data if len(pr) else None,
+                                         pl.ctypes.data if len(pr) else None, rs.ctypes.data if len(pr) else None,
+                                         as_.ctypes.data if len(pr) else None), "vtx_score_pairs")
+        return rs, as_
+
+    # ---- multi-GPU ------------------------------------------------------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        L = _capi.load()
+        buf = (C.c_uint8 * 128)()
+        rc = L.vtx_comm_unique_id(buf)
+        if rc != 0:
+            raise VtxError(f"vtx_comm_unique_id failed ({rc}): {L.vtx_last_error(None).decode()}")
+        return bytes(buf)
+
+    def comm_init(self, uid: bytes, rank: int, n_ranks: int):
+        buf = (C.c_uint8 * 128).from_buffer_copy(uid)
+        self._ck(self._L.vtx_comm_init(self._h, buf, rank, n_ranks), "vtx_comm_init")
+
+    def gather(self) -> _capi.Result:
+        """Allgatherv of every rank's triplets (device-resident on return)."""
+        res = _capi.Result()
+        self._ck(self._L.vtx_gather(self._h, C.byref(res)), "vtx_gather")
+        return res
+
+    def fetch(self, dev_res: _capi.Result) -> Triplets:
+        out = _capi.Result()
+        self._ck(self._L.vtx_fetch(self._h, C.byref(dev_res), C.byref(out)), "vtx_fetch")
+        return self._triplets(out)
+
+
+def pack_umi(s: bytes) -> int:
+    return int(_capi.load().vtx_pack_umi(s, len(s)))
+
+
+def shard_bounds(cand_start: np.ndarray, n_shards: int):
+    """Contiguous locus ranges balanced by candidate count: -> list of (lo, hi)."""
+    n_loci = len(cand_start) - 1
+    total = int(cand_start[-1])
+    cuts = [0]
+    for s in range(1, n_shards):
+        target = total * s // n_shards
+        cuts.append(int(np.searchsorted(cand_start, target, side="left")))
+    cuts.append(n_loci)
+    cuts = [min(max(c, 0), n_loci) for c in cuts]
+    for i in range(1, len(cuts)):
+        cuts[i] = max(cuts[i], cuts[i - 1])
+    return [(cuts[i], cuts[i + 1]) for i in range(n_shards)]
