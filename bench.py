@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--loci", type=int, default=0, help="override loci per GPU (0 = the config's)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chunks", type=int, default=8, help="staged shards per step on the e2e path (copy/compute overlap)")
     return ap.parse_args()
 
 
@@ -77,6 +78,7 @@ def describe(args, cfg, world, info):
         "candidates_per_gpu": info["n_cand"], "scoring_method": cfg["scoring_method"], "umi": bool(cfg.get("umi")),
         "parallelism": f"loci sharded over {world} GPU(s), one allgatherv of triplets" if world > 1 else "1 GPU",
         "l2_policy": "inputs larger than L2 (staged shard >> 126 MB), no explicit flush",
+        "e2e_chunks": args.chunks,
     }
 
 
@@ -104,7 +106,7 @@ def cpu_sample_run(sb, bcs, cfg, n_loci_sample, threads):
 
 def cpu_baseline(sb, bcs, cfg, info, target_s):
     threads = cpu_threads()
-    probe_loci = min(sb.n_loci, max(threads * 4, 64))
+    probe_loci = min(sb.n_loci, max(threads * 16, 256))
     pairs, dt = cpu_sample_run(sb, bcs, cfg, probe_loci, threads)
     rate = pairs / max(dt, 1e-9)
     n_loci = int(min(sb.n_loci, max(probe_loci, target_s * rate / max(info["n_pairs"] / sb.n_loci, 1))))
@@ -122,7 +124,7 @@ def run_reference(args):
     cfg = workload_config(args, 0)
     # a bounded sample of the same workload per step, sized so the whole run ends within a few minutes
     threads = cpu_threads()
-    probe_cfg = dict(cfg); probe_cfg["n_loci"] = max(threads * 4, 64)
+    probe_cfg = dict(cfg); probe_cfg["n_loci"] = max(threads * 16, 256)
     sb, bcs, info = vb.synth.make_shard(**probe_cfg)
     pairs, dt = cpu_sample_run(sb, bcs, cfg, sb.n_loci, threads)
     rate = pairs / dt
@@ -233,11 +235,22 @@ def run_gpu(args):
         pinned[f] = t.pin_memory() if t.numel() else t
         dev[f] = pinned[f].cuda(non_blocking=False) if t.numel() else t.cuda()
     dbatch = sb.to_c()
-    hbatch = sb.to_c()
     for f in vb.StagedBatch.FIELDS:
         setattr(dbatch, f, dev[f].data_ptr() if dev[f].numel() else None)
-        setattr(hbatch, f, pinned[f].data_ptr() if pinned[f].numel() else None)
-    h2d_bytes = sb.nbytes()
+    # e2e: the staging producer hands the engine `chunks` self-contained shards in pinned memory; the engine
+    # double-buffers them so the copy of shard k+1 overlaps the kernels of shard k
+    del pinned
+    hparts, hkeep, h2d_bytes = [], [], 0
+    for lo, hi in vb.shard_bounds(sb.cand_start, max(1, args.chunks)):
+        part = sb.shard(lo, hi)
+        cb = part.to_c()
+        for f in vb.StagedBatch.FIELDS:
+            a = getattr(part, f)
+            t = torch.from_numpy(a.view(np.uint8).reshape(-1) if a.dtype.itemsize > 1 else a.reshape(-1))
+            t = t.pin_memory() if t.numel() else t
+            hkeep.append(t)
+            setattr(cb, f, t.data_ptr() if t.numel() else None)
+        hparts.append(cb); h2d_bytes += part.nbytes()
     max_read, max_hap = int(info["read_len"]), int(info["max_hap_len"])
 
     def step_device():
@@ -249,7 +262,8 @@ def run_gpu(args):
 
     import ctypes as C
     def step_e2e():
-        rc = eng._L.vtx_submit(eng._h, C.byref(hbatch)); eng._ck(rc, "vtx_submit")
+        for cb in hparts:
+            rc = eng._L.vtx_submit(eng._h, C.byref(cb)); eng._ck(rc, "vtx_submit")
         res = eng.finish_device()
         if world > 1:
             res = eng.gather()
@@ -312,6 +326,12 @@ def run_gpu(args):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0)); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6.65 TB/s"
         b_alg = vb.synth.algorithmic_bytes_per_pair(info)
+        traffic, traffic_src, alu_pct = None, None, None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "sw_kernel_traffic.json")))
+            traffic = tj["dram_bytes_per_pair"] * n_pairs; traffic_src = tj["source"]; alu_pct = tj.get("alu_pipe_active_pct")
+        except Exception:
+            pass
         sw_avg_ms = float(np.mean(sw_ms))
         achieved = n_pairs * b_alg / (sw_avg_ms / 1e3) / 1e9
         cells = info["read_len"] * 2 * (2 * 100 + 1)
@@ -323,7 +343,8 @@ def run_gpu(args):
                     "ms_per_step": ms_e / args.steps},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "vtx_k_sw_pairs<0>",
+                         "traffic": traffic, "traffic_source": traffic_src, "ncu_alu_pipe_active_pct": alu_pct,
+                         "peak_source": peak_src, "kernel": "vtx_k_sw_pairs<0>",
                          "kernel_ms": sw_avg_ms, "algorithmic_bytes_per_pair": b_alg, "pairs_per_launch": n_pairs,
                          "gcups": n_pairs * cells / (sw_avg_ms / 1e3) / 1e9,
                          "note": "integer DP: ~540 cell updates per algorithmic byte, so the kernel is DPX-issue bound, not HBM "

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace vtx;
@@ -22,7 +23,21 @@ struct DBuf {
     size_t cap = 0;
 };
 
-enum { EV_START = 0, EV_H2D, EV_PREP, EV_SW, EV_POST, EV_COUNT };
+enum { EV_START = 0, EV_H2D, EV_C0, EV_PREP, EV_SW, EV_POST, EV_COUNT };
+
+struct TimeRec {   // CUDA events of one submit
+    cudaEvent_t ev[EV_COUNT] = {};
+    bool had_h2d = false;
+    uint64_t sw_launches = 0, launches = 0;
+};
+
+// device copies of one staged shard; two slots so that the copy of shard k+1 overlaps the kernels of shard k
+struct InSlot {
+    DBuf locus_row, hap, ref_off, ref_len, alt_off, alt_len, cand_start, read_nib, read_off, read_len, cb_bytes,
+        read_cb_off, read_cb_len, read_umi, cand_read;
+    cudaEvent_t copy_done = nullptr, free_ev = nullptr;
+    bool used = false;
+};
 
 }  // namespace
 
@@ -39,9 +54,10 @@ struct vtx_ctx {
     uint32_t bc_cap = 0, n_barcodes = 0;
     bool have_barcodes = false;
 
-    // staged inputs (device copies for vtx_submit)
-    DBuf in_locus_row, in_hap, in_ref_off, in_ref_len, in_alt_off, in_alt_len, in_cand_start, in_read_nib, in_read_off,
-        in_read_len, in_cb_bytes, in_read_cb_off, in_read_cb_len, in_read_umi, in_cand_read;
+    // staged inputs (device copies for vtx_submit): double-buffered, filled on a separate copy stream
+    InSlot slot[2];
+    uint64_t n_submits = 0;
+    cudaStream_t copy_stream = nullptr;
     // work buffers
     DBuf read_col, keep, pidx, scan_sums, pair_read, pair_col, pair_umi, pair_locus, pair_start, tcount, tstart,
         pair_first, pair_cslot, pair_uslot, cslot_col, cslot_locus, uslot_cslot, ccnt, ucnt, keep2, oidx, tile_counters,
@@ -57,10 +73,10 @@ struct vtx_ctx {
     uint64_t last_n = 0;
     vtx_metrics last_metrics{};
 
-    cudaEvent_t ev[EV_COUNT] = {};
+    std::vector<TimeRec> trecs;     // one per submit since the last finish (events are reused)
+    size_t trec_used = 0;
     bool timing_valid = false;
-    uint64_t t_sw_launches = 0, t_total_launches = 0, t_pairs = 0;
-    bool t_had_h2d = false;
+    uint64_t t_pairs = 0;
 
     // multi-GPU (vtx_comm.cpp)
     void* comm = nullptr;
@@ -91,7 +107,11 @@ int set_err(vtx_ctx* c, int code, const char* fmt, ...)
 int ensure(vtx_ctx* ctx, DBuf& b, size_t bytes)
 {
     if (bytes <= b.cap) return VTX_OK;
-    if (b.p) { CK(cudaStreamSynchronize(ctx->stream)); CK(cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
+    if (b.p) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->copy_stream) CK(cudaStreamSynchronize(ctx->copy_stream));
+        CK(cudaFree(b.p)); b.p = nullptr; b.cap = 0;
+    }
     size_t want = bytes + bytes / 8 + 256;
     cudaError_t e = cudaMalloc(&b.p, want);
     if (e != cudaSuccess) { b.p = nullptr; return set_err(ctx, VTX_E_NOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e)); }
@@ -102,6 +122,19 @@ int ensure(vtx_ctx* ctx, DBuf& b, size_t bytes)
 #define ENS(buf, bytes) do { int rc_ = ensure(ctx, buf, (bytes)); if (rc_) return rc_; } while (0)
 
 template <typename T> T* P(DBuf& b) { return static_cast<T*>(b.p); }
+
+TimeRec* new_trec(vtx_ctx* ctx)
+{
+    if (ctx->finished) ctx->trec_used = 0;
+    if (ctx->trec_used == ctx->trecs.size()) {
+        TimeRec r;
+        for (auto& e : r.ev) if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+        ctx->trecs.push_back(r);
+    }
+    TimeRec* r = &ctx->trecs[ctx->trec_used++];
+    r->had_h2d = false; r->sw_launches = 0; r->launches = 0;
+    return r;
+}
 
 inline unsigned blocks_for(uint64_t n, unsigned threads) { return unsigned((n + threads - 1) / threads); }
 
@@ -147,7 +180,7 @@ int launch_sw_class(vtx_ctx* ctx, SwArgs a, uint64_t* launches)
 
 // classes + tiles + SW kernels, shared by submit and score_pairs.  pair_start must be ready.
 int run_sw(vtx_ctx* ctx, const DevBatch& b, uint32_t n_pairs_ub, const uint32_t* pair_slot, uint32_t* counters,
-           uint32_t* pair_scores, uint64_t* launches, uint64_t* sw_launches, bool record_events)
+           uint32_t* pair_scores, uint64_t* launches, uint64_t* sw_launches, TimeRec* tr)
 {
     const uint32_t nl = b.n_loci;
     ENS(ctx->tcount, size_t(kNumClasses) * (nl + 1) * 4);
@@ -164,7 +197,7 @@ int run_sw(vtx_ctx* ctx, const DevBatch& b, uint32_t n_pairs_ub, const uint32_t*
         if (rc) return rc;
     }
     CK(cudaMemsetAsync(ctx->tile_counters.p, 0, 64, ctx->stream));
-    if (record_events) CK(cudaEventRecord(ctx->ev[EV_PREP], ctx->stream));
+    if (tr) CK(cudaEventRecord(tr->ev[EV_PREP], ctx->stream));
 
     SwArgs a{};
     a.hap_bytes = b.hap; a.ref_off = b.ref_off; a.ref_len = b.ref_len; a.alt_off = b.alt_off; a.alt_len = b.alt_len;
@@ -225,7 +258,7 @@ int grow_results(vtx_ctx* ctx, size_t need)
     return VTX_OK;
 }
 
-int process_batch(vtx_ctx* ctx, const DevBatch& b)
+int process_batch(vtx_ctx* ctx, const DevBatch& b, TimeRec* tr)
 {
     const uint64_t nc = b.n_cand;
     const uint32_t nl = b.n_loci, nr = b.n_reads;
@@ -257,8 +290,8 @@ int process_batch(vtx_ctx* ctx, const DevBatch& b)
     if (ctx->cfg.flags & VTX_F_KEEP_SCORES) { ENS(ctx->pair_scores, ncp * 4); pair_scores = P<uint32_t>(ctx->pair_scores); }
 
     if (nl == 0 || nc == 0) {
-        CK(cudaEventRecord(ctx->ev[EV_PREP], st)); CK(cudaEventRecord(ctx->ev[EV_SW], st)); CK(cudaEventRecord(ctx->ev[EV_POST], st));
-        ctx->timing_valid = true; ctx->t_sw_launches = 0; ctx->t_total_launches = 0;
+        CK(cudaEventRecord(tr->ev[EV_PREP], st)); CK(cudaEventRecord(tr->ev[EV_SW], st)); CK(cudaEventRecord(tr->ev[EV_POST], st));
+        ctx->timing_valid = true;
         return VTX_OK;
     }
 
@@ -293,9 +326,9 @@ int process_batch(vtx_ctx* ctx, const DevBatch& b)
 
     // ---- K2 + K3: Smith-Waterman, call, atomic scatter ----------------------------------------------
     rc = run_sw(ctx, b, uint32_t(nc), use_umi ? P<uint32_t>(ctx->pair_uslot) : P<uint32_t>(ctx->pair_cslot),
-                use_umi ? P<uint32_t>(ctx->ucnt) : P<uint32_t>(ctx->ccnt), pair_scores, &launches, &sw_launches, true);
+                use_umi ? P<uint32_t>(ctx->ucnt) : P<uint32_t>(ctx->ccnt), pair_scores, &launches, &sw_launches, tr);
     if (rc) return rc;
-    CK(cudaEventRecord(ctx->ev[EV_SW], st));
+    CK(cudaEventRecord(tr->ev[EV_SW], st));
 
     // ---- K4 + K5: UMI collapse, mode value, row-major emit ------------------------------------------
     if (use_umi) {
@@ -316,11 +349,11 @@ int process_batch(vtx_ctx* ctx, const DevBatch& b)
     vtx_k_bump<<<1, 32, 0, st>>>(P<unsigned long long>(ctx->d_res_n), P<uint32_t>(ctx->oidx) + nc);
     launches += 2;
     CK(cudaGetLastError());
-    CK(cudaEventRecord(ctx->ev[EV_POST], st));
+    CK(cudaEventRecord(tr->ev[EV_POST], st));
     ctx->res_ub += nc;
     ctx->timing_valid = true;
-    ctx->t_sw_launches = sw_launches;
-    ctx->t_total_launches = launches;
+    tr->sw_launches = sw_launches;
+    tr->launches = launches;
     return VTX_OK;
 }
 
@@ -337,10 +370,11 @@ int validate_batch(vtx_ctx* ctx, const vtx_batch* b)
     return VTX_OK;
 }
 
-// host-side checks that need to touch the (host) arrays; also returns max lengths
+// host-side checks that need to touch the (host) arrays; also returns max lengths.  Runs on a few host
+// threads while the shard's H2D copies are already in flight (the kernels are only enqueued afterwards).
 int scan_host_batch(vtx_ctx* ctx, const vtx_batch* b, uint32_t* max_read, uint32_t* max_hap, bool check_cands)
 {
-    uint32_t mr = 0, mh = 0;
+    uint32_t mh = 0;
     for (uint32_t l = 0; l < b->n_loci; ++l) {
         if ((b->ref_off[l] & 15) || (b->alt_off[l] & 15)) return set_err(ctx, VTX_E_INVALID, "locus %u: haplotype offsets must be multiples of 16", l);
         if (uint64_t(b->ref_off[l]) + b->ref_len[l] > b->hap_bytes_len || uint64_t(b->alt_off[l]) + b->alt_len[l] > b->hap_bytes_len)
@@ -352,18 +386,51 @@ int scan_host_batch(vtx_ctx* ctx, const vtx_batch* b, uint32_t* max_read, uint32
     if (check_cands && b->n_loci && (b->cand_start[0] != 0 || b->cand_start[b->n_loci] != b->n_cand))
         return set_err(ctx, VTX_E_INVALID, "cand_start must span [0, n_cand]");
     if (check_cands && !b->n_loci && b->n_cand) return set_err(ctx, VTX_E_INVALID, "candidates without loci");
-    for (uint32_t r = 0; r < b->n_reads; ++r) {
-        if (b->read_off[r] & 15) return set_err(ctx, VTX_E_INVALID, "read %u: read_off must be a multiple of 16", r);
-        if (b->read_off[r] + (uint64_t(b->read_len[r]) + 1) / 2 > b->read_nib_len) return set_err(ctx, VTX_E_INVALID, "read %u outside read_nib", r);
-        if (b->read_cb_off[r] != VTX_NO_CB && uint64_t(b->read_cb_off[r]) + b->read_cb_len[r] > b->cb_bytes_len)
-            return set_err(ctx, VTX_E_INVALID, "read %u: CB outside cb_bytes", r);
-        if (b->read_umi_key[r] != VTX_NO_UMI && b->read_umi_key[r] > VTX_UMI_KEY_MAX) return set_err(ctx, VTX_E_INVALID, "read %u: UMI key exceeds VTX_UMI_KEY_MAX", r);
-        mr = std::max(mr, b->read_len[r]);
+
+    const uint64_t work = uint64_t(b->n_reads) + (check_cands ? b->n_cand : 0);
+    unsigned nt = std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency()));
+    if (work < (1u << 16)) nt = 1;
+    struct Part { uint32_t mr = 0; int bad = 0; uint64_t where = 0; };
+    std::vector<Part> parts(nt);
+    auto worker = [&](unsigned t) {
+        Part& pt = parts[t];
+        const uint32_t r0 = uint32_t(uint64_t(b->n_reads) * t / nt), r1 = uint32_t(uint64_t(b->n_reads) * (t + 1) / nt);
+        for (uint32_t r = r0; r < r1; ++r) {
+            int bad = 0;
+            if (b->read_off[r] & 15) bad = 1;
+            else if (b->read_off[r] + (uint64_t(b->read_len[r]) + 1) / 2 > b->read_nib_len) bad = 2;
+            else if (b->read_cb_off[r] != VTX_NO_CB && uint64_t(b->read_cb_off[r]) + b->read_cb_len[r] > b->cb_bytes_len) bad = 3;
+            else if (b->read_umi_key[r] != VTX_NO_UMI && b->read_umi_key[r] > VTX_UMI_KEY_MAX) bad = 4;
+            if (bad && !pt.bad) { pt.bad = bad; pt.where = r; }
+            pt.mr = std::max(pt.mr, b->read_len[r]);
+        }
+        if (check_cands) {
+            const uint64_t c0 = b->n_cand * t / nt, c1 = b->n_cand * (t + 1) / nt;
+            uint32_t worst = 0;
+            for (uint64_t c = c0; c < c1; ++c) worst = std::max(worst, b->cand_read[c]);
+            if (c1 > c0 && worst >= b->n_reads && !pt.bad) { pt.bad = 5; pt.where = c0; }
+        }
+    };
+    if (nt == 1) worker(0);
+    else {
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < nt; ++t) th.emplace_back(worker, t);
+        worker(0);
+        for (auto& x : th) x.join();
+    }
+    uint32_t mr = 0;
+    for (const Part& pt : parts) {
+        mr = std::max(mr, pt.mr);
+        switch (pt.bad) {
+        case 1: return set_err(ctx, VTX_E_INVALID, "read %llu: read_off must be a multiple of 16", (unsigned long long)pt.where);
+        case 2: return set_err(ctx, VTX_E_INVALID, "read %llu outside read_nib", (unsigned long long)pt.where);
+        case 3: return set_err(ctx, VTX_E_INVALID, "read %llu: CB outside cb_bytes", (unsigned long long)pt.where);
+        case 4: return set_err(ctx, VTX_E_INVALID, "read %llu: UMI key exceeds VTX_UMI_KEY_MAX", (unsigned long long)pt.where);
+        case 5: return set_err(ctx, VTX_E_INVALID, "cand_read out of range near candidate %llu", (unsigned long long)pt.where);
+        default: break;
+        }
     }
     if (mr > 32000) return set_err(ctx, VTX_E_UNSUPPORTED, "reads longer than 32000 bases (int16 DP) are not supported (%u)", mr);
-    if (check_cands)
-        for (uint64_t c = 0; c < b->n_cand; ++c)
-            if (b->cand_read[c] >= b->n_reads) return set_err(ctx, VTX_E_INVALID, "cand_read[%llu] out of range", (unsigned long long)c);
     *max_read = mr; *max_hap = mh;
     return VTX_OK;
 }
@@ -371,26 +438,37 @@ int scan_host_batch(vtx_ctx* ctx, const vtx_batch* b, uint32_t* max_read, uint32
 int upload(vtx_ctx* ctx, DBuf& d, const void* h, size_t bytes)
 {
     ENS(d, bytes ? bytes : 16);
-    if (bytes) CK(cudaMemcpyAsync(d.p, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (bytes) CK(cudaMemcpyAsync(d.p, h, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
     return VTX_OK;
 }
 
 #define UP(buf, ptr, bytes) do { int rc_ = upload(ctx, buf, ptr, (bytes)); if (rc_) return rc_; } while (0)
 
-int upload_common(vtx_ctx* ctx, const vtx_batch* hb, DevBatch& d)
+// claim the next input slot: its previous user's kernels must have finished before the copy may overwrite it
+int claim_slot(vtx_ctx* ctx, InSlot** out)
+{
+    InSlot* sl = &ctx->slot[ctx->n_submits & 1];
+    ++ctx->n_submits;
+    if (sl->used) CK(cudaStreamWaitEvent(ctx->copy_stream, sl->free_ev, 0));
+    sl->used = true;
+    *out = sl;
+    return VTX_OK;
+}
+
+int upload_common(vtx_ctx* ctx, InSlot* sl, const vtx_batch* hb, DevBatch& d)
 {
     const uint32_t nl = hb->n_loci, nr = hb->n_reads;
-    UP(ctx->in_locus_row, hb->locus_row, size_t(nl) * 4);
-    UP(ctx->in_hap, hb->hap_bytes, hb->hap_bytes_len);
-    UP(ctx->in_ref_off, hb->ref_off, size_t(nl) * 4); UP(ctx->in_ref_len, hb->ref_len, size_t(nl) * 4);
-    UP(ctx->in_alt_off, hb->alt_off, size_t(nl) * 4); UP(ctx->in_alt_len, hb->alt_len, size_t(nl) * 4);
-    UP(ctx->in_read_nib, hb->read_nib, hb->read_nib_len);
-    UP(ctx->in_read_off, hb->read_off, size_t(nr) * 8); UP(ctx->in_read_len, hb->read_len, size_t(nr) * 4);
+    UP(sl->locus_row, hb->locus_row, size_t(nl) * 4);
+    UP(sl->hap, hb->hap_bytes, hb->hap_bytes_len);
+    UP(sl->ref_off, hb->ref_off, size_t(nl) * 4); UP(sl->ref_len, hb->ref_len, size_t(nl) * 4);
+    UP(sl->alt_off, hb->alt_off, size_t(nl) * 4); UP(sl->alt_len, hb->alt_len, size_t(nl) * 4);
+    UP(sl->read_nib, hb->read_nib, hb->read_nib_len);
+    UP(sl->read_off, hb->read_off, size_t(nr) * 8); UP(sl->read_len, hb->read_len, size_t(nr) * 4);
     d.n_loci = nl; d.n_reads = nr;
-    d.locus_row = P<uint32_t>(ctx->in_locus_row); d.hap = P<uint8_t>(ctx->in_hap);
-    d.ref_off = P<uint32_t>(ctx->in_ref_off); d.ref_len = P<uint32_t>(ctx->in_ref_len);
-    d.alt_off = P<uint32_t>(ctx->in_alt_off); d.alt_len = P<uint32_t>(ctx->in_alt_len);
-    d.read_nib = P<uint8_t>(ctx->in_read_nib); d.read_off = P<uint64_t>(ctx->in_read_off); d.read_len = P<uint32_t>(ctx->in_read_len);
+    d.locus_row = P<uint32_t>(sl->locus_row); d.hap = P<uint8_t>(sl->hap);
+    d.ref_off = P<uint32_t>(sl->ref_off); d.ref_len = P<uint32_t>(sl->ref_len);
+    d.alt_off = P<uint32_t>(sl->alt_off); d.alt_len = P<uint32_t>(sl->alt_len);
+    d.read_nib = P<uint8_t>(sl->read_nib); d.read_off = P<uint64_t>(sl->read_off); d.read_len = P<uint32_t>(sl->read_len);
     return VTX_OK;
 }
 
@@ -431,7 +509,12 @@ int vtx_create(const vtx_config* cfg, vtx_ctx** out)
         if (pe != cudaSuccess) { g_create_error = cudaGetErrorString(pe); delete ctx; return VTX_E_CUDA; }
         ctx->own_stream = true;
     }
-    for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+    pe = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    if (pe != cudaSuccess) { g_create_error = cudaGetErrorString(pe); vtx_destroy(ctx); return VTX_E_CUDA; }
+    for (auto& sl : ctx->slot) {
+        cudaEventCreateWithFlags(&sl.copy_done, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&sl.free_ev, cudaEventDisableTiming);
+    }
     bool ok = cudaMalloc(&ctx->d_metrics.p, 64) == cudaSuccess && cudaMalloc(&ctx->d_res_n.p, 64) == cudaSuccess &&
               cudaHostAlloc(&ctx->h_scalars, 64, cudaHostAllocDefault) == cudaSuccess;
     if (!ok) { g_create_error = "allocation of context scalars failed"; vtx_destroy(ctx); return VTX_E_NOMEM; }
@@ -450,9 +533,15 @@ void vtx_destroy(vtx_ctx* ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     vtx_comm_destroy_internal(ctx);
-    DBuf* all[] = { &ctx->bc_slot, &ctx->bc_bytes, &ctx->bc_off, &ctx->in_locus_row, &ctx->in_hap, &ctx->in_ref_off, &ctx->in_ref_len,
-                    &ctx->in_alt_off, &ctx->in_alt_len, &ctx->in_cand_start, &ctx->in_read_nib, &ctx->in_read_off, &ctx->in_read_len,
-                    &ctx->in_cb_bytes, &ctx->in_read_cb_off, &ctx->in_read_cb_len, &ctx->in_read_umi, &ctx->in_cand_read, &ctx->read_col,
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    for (auto& sl : ctx->slot) {
+        DBuf* sb[] = { &sl.locus_row, &sl.hap, &sl.ref_off, &sl.ref_len, &sl.alt_off, &sl.alt_len, &sl.cand_start, &sl.read_nib,
+                       &sl.read_off, &sl.read_len, &sl.cb_bytes, &sl.read_cb_off, &sl.read_cb_len, &sl.read_umi, &sl.cand_read };
+        for (DBuf* b : sb) if (b->p) cudaFree(b->p);
+        if (sl.copy_done) cudaEventDestroy(sl.copy_done);
+        if (sl.free_ev) cudaEventDestroy(sl.free_ev);
+    }
+    DBuf* all[] = { &ctx->bc_slot, &ctx->bc_bytes, &ctx->bc_off, &ctx->read_col,
                     &ctx->keep, &ctx->pidx, &ctx->scan_sums, &ctx->pair_read, &ctx->pair_col, &ctx->pair_umi, &ctx->pair_locus,
                     &ctx->pair_start, &ctx->tcount, &ctx->tstart, &ctx->pair_first, &ctx->pair_cslot, &ctx->pair_uslot, &ctx->cslot_col,
                     &ctx->cslot_locus, &ctx->uslot_cslot, &ctx->ccnt, &ctx->ucnt, &ctx->keep2, &ctx->oidx, &ctx->tile_counters,
@@ -463,7 +552,8 @@ void vtx_destroy(vtx_ctx* ctx)
     for (void* h : ctx->h_res) if (h) cudaFreeHost(h);
     for (void* h : ctx->g_host) if (h) cudaFreeHost(h);
     if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
-    for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& tr : ctx->trecs) for (auto& ev : tr.ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -504,7 +594,7 @@ int vtx_set_barcodes(vtx_ctx* ctx, const uint8_t* bytes, const uint32_t* off, ui
     UP(ctx->bc_slot, slot.data(), size_t(cap) * 4);
     UP(ctx->bc_bytes, bytes, off[n]);
     UP(ctx->bc_off, off, size_t(n + 1) * 4);
-    CK(cudaStreamSynchronize(ctx->stream));   // `slot` is a local
+    CK(cudaStreamSynchronize(ctx->copy_stream));   // `slot` is a local; the table must be resident before any submit
     ctx->bc_cap = cap; ctx->n_barcodes = n; ctx->have_barcodes = true;
     return VTX_OK;
 }
@@ -515,26 +605,40 @@ int vtx_submit(vtx_ctx* ctx, const vtx_batch* hb)
     if (!ctx->have_barcodes) return set_err(ctx, VTX_E_STATE, "vtx_set_barcodes must be called before vtx_submit");
     int rc = validate_batch(ctx, hb);
     if (rc) return rc;
-    DevBatch d{};
-    rc = scan_host_batch(ctx, hb, &d.max_read_len, &d.max_hap_len, true);
-    if (rc) return rc;
     CK(cudaSetDevice(ctx->device));
-    CK(cudaEventRecord(ctx->ev[EV_START], ctx->stream));
-    rc = upload_common(ctx, hb, d);
+    TimeRec* tr = new_trec(ctx);
+    if (!tr) return set_err(ctx, VTX_E_CUDA, "cudaEventCreate failed");
+    InSlot* sl = nullptr;
+    rc = claim_slot(ctx, &sl);
+    if (rc) return rc;
+    // 1. start the copies of this shard on the copy stream (they overlap the previous shard's kernels) ...
+    DevBatch d{};
+    CK(cudaEventRecord(tr->ev[EV_START], ctx->copy_stream));
+    rc = upload_common(ctx, sl, hb, d);
     if (rc) return rc;
     const uint32_t nl = hb->n_loci, nr = hb->n_reads;
-    UP(ctx->in_cand_start, hb->cand_start, size_t(nl + 1) * 8);
-    UP(ctx->in_cb_bytes, hb->cb_bytes, hb->cb_bytes_len);
-    UP(ctx->in_read_cb_off, hb->read_cb_off, size_t(nr) * 4); UP(ctx->in_read_cb_len, hb->read_cb_len, size_t(nr) * 2);
-    UP(ctx->in_read_umi, hb->read_umi_key, size_t(nr) * 8);
-    UP(ctx->in_cand_read, hb->cand_read, size_t(hb->n_cand) * 4);
+    UP(sl->cand_start, hb->cand_start, size_t(nl + 1) * 8);
+    UP(sl->cb_bytes, hb->cb_bytes, hb->cb_bytes_len);
+    UP(sl->read_cb_off, hb->read_cb_off, size_t(nr) * 4); UP(sl->read_cb_len, hb->read_cb_len, size_t(nr) * 2);
+    UP(sl->read_umi, hb->read_umi_key, size_t(nr) * 8);
+    UP(sl->cand_read, hb->cand_read, size_t(hb->n_cand) * 4);
+    CK(cudaEventRecord(tr->ev[EV_H2D], ctx->copy_stream));
+    CK(cudaEventRecord(sl->copy_done, ctx->copy_stream));
+    tr->had_h2d = true;
     d.n_cand = hb->n_cand;
-    d.cand_start = P<uint64_t>(ctx->in_cand_start); d.cb_bytes = P<uint8_t>(ctx->in_cb_bytes);
-    d.read_cb_off = P<uint32_t>(ctx->in_read_cb_off); d.read_cb_len = P<uint16_t>(ctx->in_read_cb_len);
-    d.read_umi = P<uint64_t>(ctx->in_read_umi); d.cand_read = P<uint32_t>(ctx->in_cand_read);
-    CK(cudaEventRecord(ctx->ev[EV_H2D], ctx->stream));
-    ctx->t_had_h2d = true;
-    return process_batch(ctx, d);
+    d.cand_start = P<uint64_t>(sl->cand_start); d.cb_bytes = P<uint8_t>(sl->cb_bytes);
+    d.read_cb_off = P<uint32_t>(sl->read_cb_off); d.read_cb_len = P<uint16_t>(sl->read_cb_len);
+    d.read_umi = P<uint64_t>(sl->read_umi); d.cand_read = P<uint32_t>(sl->cand_read);
+    // 2. ... validate the host arrays meanwhile; nothing has been launched on them yet
+    rc = scan_host_batch(ctx, hb, &d.max_read_len, &d.max_hap_len, true);
+    if (rc) { cudaStreamSynchronize(ctx->copy_stream); --ctx->trec_used; return rc; }
+    // 3. kernels wait for the copy, and release the slot when done
+    CK(cudaStreamWaitEvent(ctx->stream, sl->copy_done, 0));
+    CK(cudaEventRecord(tr->ev[EV_C0], ctx->stream));
+    rc = process_batch(ctx, d, tr);
+    if (rc) return rc;
+    CK(cudaEventRecord(sl->free_ev, ctx->stream));
+    return VTX_OK;
 }
 
 // device batches carry their own bounds in the (otherwise unused) *_len fields of the pools:
@@ -554,10 +658,10 @@ int vtx_submit_device_ex(vtx_ctx* ctx, const vtx_batch* db, uint32_t max_read_le
     d.read_off = db->read_off; d.read_len = db->read_len; d.cb_bytes = db->cb_bytes; d.read_cb_off = db->read_cb_off;
     d.read_cb_len = db->read_cb_len; d.read_umi = db->read_umi_key; d.cand_read = db->cand_read;
     d.max_read_len = max_read_len; d.max_hap_len = max_hap_len;
-    CK(cudaEventRecord(ctx->ev[EV_START], ctx->stream));
-    CK(cudaEventRecord(ctx->ev[EV_H2D], ctx->stream));
-    ctx->t_had_h2d = false;
-    return process_batch(ctx, d);
+    TimeRec* tr = new_trec(ctx);
+    if (!tr) return set_err(ctx, VTX_E_CUDA, "cudaEventCreate failed");
+    CK(cudaEventRecord(tr->ev[EV_C0], ctx->stream));
+    return process_batch(ctx, d, tr);
 }
 
 int vtx_submit_device(vtx_ctx* ctx, const vtx_batch* db)
@@ -653,15 +757,20 @@ int vtx_finish(vtx_ctx* ctx, vtx_result* out)
 int vtx_last_timing(vtx_ctx* ctx, vtx_timing* t)
 {
     if (!ctx || !t) return VTX_E_INVALID;
-    if (!ctx->timing_valid) return set_err(ctx, VTX_E_STATE, "no finished submit to time");
+    if (!ctx->timing_valid || ctx->trec_used == 0) return set_err(ctx, VTX_E_STATE, "no finished submit to time");
     CK(cudaSetDevice(ctx->device));
-    CK(cudaEventSynchronize(ctx->ev[EV_POST]));
     memset(t, 0, sizeof(*t));
-    if (ctx->t_had_h2d) CK(cudaEventElapsedTime(&t->h2d_ms, ctx->ev[EV_START], ctx->ev[EV_H2D]));
-    CK(cudaEventElapsedTime(&t->prep_ms, ctx->ev[EV_H2D], ctx->ev[EV_PREP]));
-    CK(cudaEventElapsedTime(&t->sw_ms, ctx->ev[EV_PREP], ctx->ev[EV_SW]));
-    CK(cudaEventElapsedTime(&t->post_ms, ctx->ev[EV_SW], ctx->ev[EV_POST]));
-    t->n_pairs = ctx->t_pairs; t->sw_launches = ctx->t_sw_launches; t->total_launches = ctx->t_total_launches;
+    for (size_t i = 0; i < ctx->trec_used; ++i) {      // summed over every submit since the last finish
+        TimeRec& r = ctx->trecs[i];
+        CK(cudaEventSynchronize(r.ev[EV_POST]));
+        float ms = 0;
+        if (r.had_h2d) { CK(cudaEventElapsedTime(&ms, r.ev[EV_START], r.ev[EV_H2D])); t->h2d_ms += ms; }
+        CK(cudaEventElapsedTime(&ms, r.ev[EV_C0], r.ev[EV_PREP])); t->prep_ms += ms;
+        CK(cudaEventElapsedTime(&ms, r.ev[EV_PREP], r.ev[EV_SW])); t->sw_ms += ms;
+        CK(cudaEventElapsedTime(&ms, r.ev[EV_SW], r.ev[EV_POST])); t->post_ms += ms;
+        t->sw_launches += r.sw_launches; t->total_launches += r.launches;
+    }
+    t->n_pairs = ctx->t_pairs;
     return VTX_OK;
 }
 
@@ -690,8 +799,13 @@ int vtx_score_pairs(vtx_ctx* ctx, const vtx_batch* hb, uint64_t n_pairs, const u
         for (uint64_t i = 0; i < n_pairs; ++i) { const uint32_t p = cur[pair_locus[i]]++; order[p] = uint32_t(i); s_read[p] = pair_read[i]; s_locus[p] = pair_locus[i]; }
     }
     CK(cudaSetDevice(ctx->device));
-    rc = upload_common(ctx, hb, d);
+    InSlot* sl = nullptr;
+    rc = claim_slot(ctx, &sl);
     if (rc) return rc;
+    rc = upload_common(ctx, sl, hb, d);
+    if (rc) return rc;
+    CK(cudaEventRecord(sl->copy_done, ctx->copy_stream));
+    CK(cudaStreamWaitEvent(ctx->stream, sl->copy_done, 0));
     ENS(ctx->pair_read, n_pairs * 4 + 4); ENS(ctx->pair_locus, n_pairs * 4 + 4); ENS(ctx->pair_start, size_t(nl + 1) * 4);
     ENS(ctx->pair_scores, n_pairs * 4 + 4);
     CK(cudaMemcpyAsync(ctx->pair_read.p, s_read.data(), n_pairs * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -699,8 +813,9 @@ int vtx_score_pairs(vtx_ctx* ctx, const vtx_batch* hb, uint64_t n_pairs, const u
     vtx_k_pair_start_explicit<<<blocks_for(nl + 1, 256), 256, 0, ctx->stream>>>(nl, uint32_t(n_pairs), P<uint32_t>(ctx->pair_locus),
                                                                                 P<uint32_t>(ctx->pair_start));
     uint64_t launches = 1, sw_launches = 0;
-    rc = run_sw(ctx, d, uint32_t(n_pairs), nullptr, nullptr, P<uint32_t>(ctx->pair_scores), &launches, &sw_launches, false);
+    rc = run_sw(ctx, d, uint32_t(n_pairs), nullptr, nullptr, P<uint32_t>(ctx->pair_scores), &launches, &sw_launches, nullptr);
     if (rc) return rc;
+    CK(cudaEventRecord(sl->free_ev, ctx->stream));
     std::vector<uint32_t> packed(n_pairs);
     CK(cudaMemcpyAsync(packed.data(), ctx->pair_scores.p, n_pairs * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));

@@ -89,27 +89,64 @@ class StagedBatch:
         return b
 
     def shard(self, lo: int, hi: int) -> "StagedBatch":
-        """Loci [lo, hi) as a self-contained shard (reads re-indexed) -- locus sharding across GPUs."""
+        """Loci [lo, hi) as a self-contained shard (reads, CB bytes and windows re-packed and re-indexed) --
+        what a staging producer emits per chunk, and how loci are sharded across GPUs."""
         cs = self.cand_start
         c0, c1 = int(cs[lo]), int(cs[hi])
-        cr = self.cand_read[c0:c1]
-        used, inv = np.unique(cr, return_inverse=True)
-        # re-pack reads and CB bytes compactly (16-byte aligned reads)
+        used, inv = np.unique(self.cand_read[c0:c1], return_inverse=True)
+        nu = len(used)
+        # reads (16-byte aligned)
         rl = self.read_len[used]
-        nb = (rl.astype(np.uint64) + 1) // 2
+        nb = (rl.astype(np.int64) + 1) // 2
         stride = (nb + 15) // 16 * 16
-        new_off = np.zeros(len(used), np.uint64)
-        if len(used):
-            new_off[1:] = np.cumsum(stride)[:-1]
-        nib = np.zeros(int(stride.sum()) if len(used) else 0, np.uint8)
-        for i, r in enumerate(used):              # shards are cut once per run; clarity over speed
-            o = int(self.read_off[r]); n = int(nb[i])
-            nib[int(new_off[i]): int(new_off[i]) + n] = self.read_nib[o:o + n]
+        new_off = np.zeros(nu, np.uint64)
+        if nu:
+            new_off[1:] = np.cumsum(stride)[:-1].astype(np.uint64)
+        n_reads = self.n_reads
+        st0 = int(self.read_off[1] - self.read_off[0]) if n_reads > 1 else 0
+        uniform = (n_reads > 1 and st0 > 0 and self.read_nib.size == st0 * n_reads and
+                   bool((np.diff(self.read_off.astype(np.int64)) == st0).all()) and bool((stride == st0).all()))
+        if uniform:
+            nib = self.read_nib.reshape(n_reads, st0)[used].reshape(-1)
+        else:
+            nib = np.zeros(int(stride.sum()) if nu else 0, np.uint8)
+            for i, r in enumerate(used):
+                o = int(self.read_off[r]); n = int(nb[i])
+                nib[int(new_off[i]): int(new_off[i]) + n] = self.read_nib[o:o + n]
+        # CB bytes
+        cbo = self.read_cb_off[used]; cbl = self.read_cb_len[used].astype(np.int64)
+        has = cbo != NO_CB
+        new_cbo = np.full(nu, NO_CB, np.uint32)
+        L0 = int(cbl[0]) if nu else 0
+        if nu and L0 > 0 and bool(has.all()) and bool((cbl == L0).all()) and bool((cbo % L0 == 0).all()) and \
+                self.cb_bytes.size % L0 == 0:
+            cb = self.cb_bytes.reshape(-1, L0)[cbo // L0].reshape(-1)
+            new_cbo = (np.arange(nu, dtype=np.uint32) * np.uint32(L0))
+        else:
+            tot = int(cbl[has].sum()) if nu else 0
+            cb = np.zeros(tot, np.uint8); pos = 0
+            for i in np.nonzero(has)[0]:
+                n = int(cbl[i]); cb[pos:pos + n] = self.cb_bytes[int(cbo[i]): int(cbo[i]) + n]; new_cbo[i] = pos; pos += n
+        # haplotype windows
+        nl = hi - lo
+        ro, ra = self.ref_off[lo:hi].astype(np.int64), self.alt_off[lo:hi].astype(np.int64)
+        rln, aln = self.ref_len[lo:hi].astype(np.int64), self.alt_len[lo:hi].astype(np.int64)
+        hs = int(ra[0] - ro[0]) if nl else 0
+        if nl and hs > 0 and hs % 16 == 0 and bool((ra - ro == hs).all()) and bool((np.diff(ro) == 2 * hs).all()) and \
+                bool((rln <= hs).all()) and bool((aln <= hs).all()) and int(ro[-1]) + 2 * hs <= self.hap_bytes.size:
+            hap = self.hap_bytes[int(ro[0]): int(ro[-1]) + 2 * hs].copy()
+            n_ro = (np.arange(nl, dtype=np.uint32) * np.uint32(2 * hs)); n_ra = n_ro + np.uint32(hs)
+        else:
+            pieces, n_ro, n_ra, pos = [], np.zeros(nl, np.uint32), np.zeros(nl, np.uint32), 0
+            for i in range(nl):
+                for off, ln, dst in ((ro[i], rln[i], n_ro), (ra[i], aln[i], n_ra)):
+                    dst[i] = pos; w = np.zeros(int((ln + 15) // 16 * 16), np.uint8)
+                    w[:int(ln)] = self.hap_bytes[int(off): int(off + ln)]; pieces.append(w); pos += w.size
+            hap = np.concatenate(pieces) if pieces else np.zeros(0, np.uint8)
         return StagedBatch(
-            locus_row=self.locus_row[lo:hi], hap_bytes=self.hap_bytes, ref_off=self.ref_off[lo:hi],
-            ref_len=self.ref_len[lo:hi], alt_off=self.alt_off[lo:hi], alt_len=self.alt_len[lo:hi],
-            cand_start=(cs[lo:hi + 1] - cs[lo]), read_nib=nib, read_off=new_off, read_len=rl,
-            cb_bytes=self.cb_bytes, read_cb_off=self.read_cb_off[used], read_cb_len=self.read_cb_len[used],
+            locus_row=self.locus_row[lo:hi], hap_bytes=hap, ref_off=n_ro, ref_len=self.ref_len[lo:hi],
+            alt_off=n_ra, alt_len=self.alt_len[lo:hi], cand_start=(cs[lo:hi + 1] - cs[lo]), read_nib=nib,
+            read_off=new_off, read_len=rl, cb_bytes=cb, read_cb_off=new_cbo, read_cb_len=self.read_cb_len[used],
             read_umi_key=self.read_umi_key[used], cand_read=inv.astype(np.uint32), n_rows=self.n_rows)
 
 
