@@ -6,18 +6,26 @@ CSRC      := vartrix_b200/csrc
 LIBDIR    := vartrix_b200/lib
 LIB       := $(LIBDIR)/libvartrix_b200.so
 
-all: $(LIB) oracle
+CLI       := vartrix_b200/bin/vartrix_b200
+HOSTSRC   := $(CSRC)/host
+
+all: $(LIB) $(CLI) oracle
 
 $(LIB): $(CSRC)/vtx_api.cu $(CSRC)/vtx_sw.cuh $(CSRC)/vtx_pipeline.cuh include/vartrix_b200.h
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(CSRC)/vtx_api.cu -ldl 2> $(LIBDIR)/ptxas.log || (cat $(LIBDIR)/ptxas.log; exit 1)
 	@grep -E "error|warning" $(LIBDIR)/ptxas.log | grep -v "ptxas info" || true
 
+# C++ host: BAM/VCF/FASTA decode + staging + CLI with the vartrix flag surface, on top of the C ABI
+$(CLI): $(HOSTSRC)/main.cpp $(HOSTSRC)/stager.hpp $(HOSTSRC)/inputs.hpp $(HOSTSRC)/bam_reader.hpp include/vartrix_b200.h $(LIB)
+	@mkdir -p vartrix_b200/bin
+	g++ -O2 -std=c++17 -Wall -Wextra -o $@ $(HOSTSRC)/main.cpp -L$(LIBDIR) -lvartrix_b200 -lz -lpthread -Wl,-rpath,'$$ORIGIN/../lib'
+
 oracle:
 	$(MAKE) -s -C oracle
 
 clean:
-	rm -f $(LIB) $(LIBDIR)/ptxas.log
+	rm -f $(LIB) $(LIBDIR)/ptxas.log $(CLI)
 	$(MAKE) -s -C oracle clean
 
 .PHONY: all oracle clean

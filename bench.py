@@ -59,14 +59,11 @@ def dist_env():
 
 def workload_config(args, rank):
     import vartrix_b200 as vb
+    from vartrix_b200 import dist as vdist
     cfg = dict(vb.synth.CONFIGS[args.workload])
     if args.loci:
         cfg["n_loci"] = args.loci
-    base_seed = cfg["seed"]
-    cfg["barcode_seed"] = 1000 + base_seed           # every rank sees the same barcode list
-    cfg["seed"] = base_seed + 7919 * rank           # ... and its own loci / reads
-    cfg["row_offset"] = rank * cfg["n_loci"]
-    return cfg
+    return vdist.rank_workload(cfg, rank)      # same barcode list everywhere, own loci/reads, rows offset by rank
 
 
 def describe(args, cfg, world, info):
@@ -221,11 +218,9 @@ def run_gpu(args):
     eng = vb.Engine(cfg["scoring_method"], umi=bool(cfg.get("umi")), device=local, stream=stream.cuda_stream)
     eng.set_barcodes(bcs)
     if world > 1:       # ship the NCCL unique id of the engine's own communicator over torch.distributed
-        uid = torch.zeros(128, dtype=torch.uint8)
-        if rank == 0:
-            uid = torch.frombuffer(bytearray(vb.Engine.comm_unique_id()), dtype=torch.uint8).clone()
-        uid = uid.cuda(); dist.broadcast(uid, 0)
-        eng.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
+        from vartrix_b200 import dist as vdist
+        uid = vdist.broadcast_bytes(vb.Engine.comm_unique_id() if rank == 0 else None, 128, device="cuda")
+        eng.comm_init(uid, rank, world)
 
     # device-resident copy of the shard (for `value`) and pinned host copy (for `e2e`)
     dev, pinned = {}, {}
@@ -268,9 +263,9 @@ def run_gpu(args):
         if world > 1:
             res = eng.gather()
             if rank == 0:
-                return eng.fetch(res)        # rank 0 writes the matrix: it alone needs the triplets on the host
+                return eng.fetch(res, copy=False)   # rank 0 writes the matrix: it alone needs the triplets on the host
             return res
-        return eng.fetch(res)
+        return eng.fetch(res, copy=False)    # triplets land in the library's pinned host arrays
 
     def barrier():
         if world > 1:
@@ -313,6 +308,7 @@ def run_gpu(args):
     for _ in range(max(args.warmup, 3)):
         step_e2e()
     ms_e, _, _, last_e, _ = timed(step_e2e, args.steps)
+    t_e = eng.timing()
     e2e_value = total_pairs * args.steps / (ms_e / 1e3)
     n_out = int(last_e.n) if hasattr(last_e, "n") else len(last_e.row)
     d2h_bytes = n_out * 36 + 32
@@ -340,7 +336,8 @@ def run_gpu(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int16x2", "data": "synthetic", "config": describe(args, cfg, world, info),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                    "ms_per_step": ms_e / args.steps},
+                    "ms_per_step": ms_e / args.steps,
+                    "last_step_device_ms": {k: round(t_e[k], 3) for k in ("h2d_ms", "prep_ms", "sw_ms", "post_ms")}},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "ncu_alu_pipe_active_pct": alu_pct,

@@ -165,6 +165,9 @@ int         vtx_finish_device(vtx_ctx* ctx, vtx_result* out);
 /* Copy a device-resident result (from vtx_finish_device or vtx_gather) into library-owned pinned host arrays. */
 int         vtx_fetch(vtx_ctx* ctx, const vtx_result* device_result, vtx_result* out);
 int         vtx_sync(vtx_ctx* ctx);
+/* Wait until every host->device copy enqueued by vtx_submit so far has landed, i.e. until the host buffers
+ * of all previous submits may be reused (kernels may still be running). */
+int         vtx_wait_copies(vtx_ctx* ctx);
 
 /* Raw scores (Scores.ref_score / alt_score, main.rs:996-1001, 926-927) for an explicit pair list:
  * pair i = (read pair_read[i], locus pair_locus[i]) of `host_batch` (cand_* fields ignored).

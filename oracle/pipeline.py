@@ -449,7 +449,7 @@ def construct_haplotypes(fa: Fasta, chrom: str, start: int, end: int, alt: bytes
 
 def stage_from_files(vcf: str, bam: str, fasta: str, padding: int = 100, mapq: int = 0,
                      primary_only: bool = False, no_duplicates: bool = False, bam_tag: str = "CB",
-                     valid_chars: str = "ATGCatgc") -> Batch:
+                     valid_chars: str = "ATGCatgc", rec_lo: int = 0, rec_hi: int | None = None) -> Batch:
     L = lib()
     recs = read_vcf(vcf)
     fa = Fasta(fasta)
@@ -466,6 +466,8 @@ def stage_from_files(vcf: str, bam: str, fasta: str, padding: int = 100, mapq: i
     cand_read = []
     tag = bam_tag.encode()
     for i, rec in enumerate(recs):
+        if i < rec_lo or (rec_hi is not None and i >= rec_hi):
+            continue
         start = rec.pos0; end = start + len(rec.alleles[0])              # main.rs:619-623
         if len(rec.alleles) > 2:                                         # main.rs:646-653
             met["num_multiallelic_recs"] += 1; continue

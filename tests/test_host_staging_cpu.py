@@ -1,0 +1,77 @@
+"""The C++ staging host (csrc/host: BGZF/BAM/BAI, .fai FASTA, VCF, filters) against the oracle's independent
+pure-Python decode, on the reference's own fixtures (present in the build container only)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import REF_TEST_DIR, ROOT
+
+CLI = os.path.join(ROOT, "vartrix_b200", "bin", "vartrix_b200")
+needs_ref = pytest.mark.skipif(not os.path.isdir(REF_TEST_DIR), reason="reference fixtures only exist in the build container")
+
+
+def _labels(keys):
+    """equal key <=> equal label, labels numbered by first appearance"""
+    _, first, inv = np.unique(keys, return_index=True, return_inverse=True)
+    order = np.argsort(np.argsort(first))
+    return order[inv]
+
+
+def _same_staging(sb, ob):
+    for f in ("locus_row", "ref_len", "alt_len", "cand_start", "read_len", "read_cb_len", "cand_read", "ref_off",
+              "alt_off", "read_off", "cb_bytes", "read_cb_off"):
+        assert np.array_equal(getattr(sb, f), getattr(ob, f)), f
+    for f in ("hap_bytes", "read_nib"):          # pools may differ by trailing 16-byte padding only
+        a, b = getattr(sb, f), getattr(ob, f)
+        n = min(len(a), len(b))
+        assert np.array_equal(a[:n], b[:n]) and not a[n:].any() and not b[n:].any() and abs(len(a) - len(b)) < 16, f
+    none = np.uint64(0xFFFFFFFFFFFFFFFF)
+    assert np.array_equal(sb.read_umi_key == none, ob.read_umi_key == none)
+    assert np.array_equal(_labels(sb.read_umi_key), _labels(ob.read_umi_key))       # same UB equivalence classes
+
+
+def _dump(tmp_path, pre, bcs, *extra):
+    out = tmp_path / f"{pre}.staged"
+    cmd = [CLI, "-v", f"{REF_TEST_DIR}/{pre}.vcf", "-b", f"{REF_TEST_DIR}/{pre}.bam", "-f", f"{REF_TEST_DIR}/{pre}.fa",
+           "-c", f"{REF_TEST_DIR}/{bcs}", "--dump-staged", str(out), *extra]
+    subprocess.run(cmd, check=True, cwd=str(tmp_path))
+    from vartrix_b200.staged_io import read_dump
+    return read_dump(str(out))
+
+
+@needs_ref
+@pytest.mark.parametrize("pre,bcs", [("test", "barcodes.tsv"), ("test_dna", "dna_barcodes.tsv")])
+def test_cpp_staging_equals_oracle_decode(oracle, tmp_path, pre, bcs):
+    n_rows, n_cols, shards = _dump(tmp_path, pre, bcs, "--shard-loci", "1000000", "--threads", "2")
+    assert len(shards) == 1
+    sb, met = shards[0]
+    ob = oracle.stage_from_files(f"{REF_TEST_DIR}/{pre}.vcf", f"{REF_TEST_DIR}/{pre}.bam", f"{REF_TEST_DIR}/{pre}.fa")
+    _same_staging(sb, ob)
+    assert met == {k: ob.host_metrics[k] for k in met}
+    assert n_rows == ob.n_rows and n_cols == len(oracle.load_barcodes(f"{REF_TEST_DIR}/{bcs}"))
+
+
+@needs_ref
+def test_cpp_staging_in_shards_and_with_filters(oracle, tmp_path):
+    kw = dict(mapq=30, primary_only=True, no_duplicates=True, padding=60)
+    n_rows, _, shards = _dump(tmp_path, "test_dna", "dna_barcodes.tsv", "--shard-loci", "7", "--threads", "3", "--mapq", "30",
+                              "--primary-alignments", "--no-duplicates", "--padding", "60")
+    assert len(shards) == (46 + 6) // 7
+    for k, (sb, met) in enumerate(shards):
+        ob = oracle.stage_from_files(f"{REF_TEST_DIR}/test_dna.vcf", f"{REF_TEST_DIR}/test_dna.bam", f"{REF_TEST_DIR}/test_dna.fa",
+                                     rec_lo=7 * k, rec_hi=7 * k + 7, **kw)
+        _same_staging(sb, ob)
+        assert met == {m: ob.host_metrics[m] for m in met}, k
+
+
+@needs_ref
+def test_cli_refuses_to_overwrite_and_missing_inputs(tmp_path):
+    (tmp_path / "out_matrix.mtx").write_text("x")
+    base = [CLI, "-v", f"{REF_TEST_DIR}/test.vcf", "-b", f"{REF_TEST_DIR}/test.bam", "-f", f"{REF_TEST_DIR}/test.fa",
+            "-c", f"{REF_TEST_DIR}/barcodes.tsv"]
+    r = subprocess.run(base, cwd=str(tmp_path), capture_output=True, text=True)
+    assert r.returncode == 1 and "Output path already exists" in r.stderr            # main.rs:475-480
+    r = subprocess.run([*base[:2], "/nonexistent.vcf", *base[3:]], cwd=str(tmp_path), capture_output=True, text=True)
+    assert r.returncode == 1 and "does not exist" in r.stderr                        # main.rs:501-506

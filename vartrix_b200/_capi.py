@@ -23,7 +23,7 @@ F_KEEP_SCORES = 1
 SYMBOLS = [
     "vtx_abi_version", "vtx_create", "vtx_destroy", "vtx_last_error", "vtx_host_alloc", "vtx_host_free",
     "vtx_set_barcodes", "vtx_submit", "vtx_submit_device", "vtx_submit_device_ex", "vtx_finish",
-    "vtx_finish_device", "vtx_fetch", "vtx_sync", "vtx_score_pairs", "vtx_pack_umi", "vtx_last_timing",
+    "vtx_finish_device", "vtx_fetch", "vtx_sync", "vtx_wait_copies", "vtx_score_pairs", "vtx_pack_umi", "vtx_last_timing",
     "vtx_comm_unique_id", "vtx_comm_init", "vtx_gather",
 ]
 
@@ -98,6 +98,8 @@ def load():
     L.vtx_fetch.argtypes = [C.c_void_p, C.POINTER(Result), C.POINTER(Result)]
     L.vtx_sync.restype = C.c_int
     L.vtx_sync.argtypes = [C.c_void_p]
+    L.vtx_wait_copies.restype = C.c_int
+    L.vtx_wait_copies.argtypes = [C.c_void_p]
     L.vtx_score_pairs.restype = C.c_int
     L.vtx_score_pairs.argtypes = [C.c_void_p, C.POINTER(Batch), C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.vtx_pack_umi.restype = C.c_uint64

@@ -1,0 +1,190 @@
+// stager.hpp -- the host half of evaluate_rec / evaluate_alns (/root/reference/src/main.rs:610-695,
+// 809-894): per VCF record build the haplotype windows, fetch the overlapping BAM records, apply the
+// four record filters and stage the survivors as one `vtx_batch` shard.  Alignment, barcode lookup, UMI
+// gate and aggregation happen on the GPU behind include/vartrix_b200.h.
+#pragma once
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../../include/vartrix_b200.h"
+#include "bam_reader.hpp"
+#include "inputs.hpp"
+
+namespace vtxhost {
+
+struct HostMetrics {             // the host-side share of main.rs:449-459
+    uint64_t num_reads = 0, num_low_mapq = 0, num_non_primary = 0, num_duplicates = 0, num_not_useful = 0,
+             num_invalid_recs = 0, num_multiallelic_recs = 0;
+    void add(const HostMetrics& o)
+    {
+        num_reads += o.num_reads; num_low_mapq += o.num_low_mapq; num_non_primary += o.num_non_primary;
+        num_duplicates += o.num_duplicates; num_not_useful += o.num_not_useful; num_invalid_recs += o.num_invalid_recs;
+        num_multiallelic_recs += o.num_multiallelic_recs;
+    }
+};
+
+struct StageArgs {
+    int64_t padding = 100;       // --padding
+    uint32_t mapq = 0;           // --mapq
+    bool primary_only = false;   // --primary-alignments
+    bool no_duplicates = false;  // --no-duplicates
+    char bam_tag[2] = { 'C', 'B' };
+    bool valid[256] = {};        // --valid-chars
+};
+
+struct StagedShard {
+    std::vector<uint32_t> locus_row, ref_off, ref_len, alt_off, alt_len, read_len, read_cb_off, cand_read;
+    std::vector<uint64_t> cand_start, read_off, read_umi_key;
+    std::vector<uint16_t> read_cb_len;
+    std::vector<uint8_t> hap_bytes, read_nib, cb_bytes;
+    HostMetrics met;
+
+    size_t bytes() const
+    {
+        return (locus_row.size() + ref_off.size() * 4 + read_len.size() * 2 + cand_read.size()) * 4 +
+               (cand_start.size() + read_off.size() * 2) * 8 + read_cb_len.size() * 2 + hap_bytes.size() + read_nib.size() +
+               cb_bytes.size() + 16 * 16;
+    }
+    void fill(vtx_batch* b) const
+    {
+        memset(b, 0, sizeof(*b));
+        b->n_loci = uint32_t(locus_row.size()); b->locus_row = locus_row.data();
+        b->hap_bytes = hap_bytes.data(); b->hap_bytes_len = hap_bytes.size();
+        b->ref_off = ref_off.data(); b->ref_len = ref_len.data(); b->alt_off = alt_off.data(); b->alt_len = alt_len.data();
+        b->cand_start = cand_start.data();
+        b->n_reads = uint32_t(read_len.size()); b->read_nib = read_nib.data(); b->read_nib_len = read_nib.size();
+        b->read_off = read_off.data(); b->read_len = read_len.data();
+        b->cb_bytes = cb_bytes.data(); b->cb_bytes_len = cb_bytes.size();
+        b->read_cb_off = read_cb_off.data(); b->read_cb_len = read_cb_len.data(); b->read_umi_key = read_umi_key.data();
+        b->n_cand = cand_read.size(); b->cand_read = cand_read.data();
+    }
+};
+
+// UB strings that do not fit vtx_pack_umi's alphabet/length get a process-wide interned id
+class UmiInterner {
+public:
+    uint64_t key(const uint8_t* s, uint32_t len)
+    {
+        const uint64_t k = pack(s, len);
+        if (k != VTX_NO_UMI) return k;
+        std::lock_guard<std::mutex> g(mu_);
+        auto it = map_.emplace(std::string(reinterpret_cast<const char*>(s), len), map_.size()).first;
+        return (1ull << 61) | it->second;
+    }
+    // same encoding as vtx_pack_umi (kept local so that staging can run without the CUDA library)
+    static uint64_t pack(const uint8_t* s, uint32_t len)
+    {
+        if (len > 18) return VTX_NO_UMI;
+        uint64_t k = 0;
+        for (uint32_t i = 0; i < len; ++i) {
+            uint64_t c;
+            switch (s[i]) { case 'A': c = 0; break; case 'C': c = 1; break; case 'G': c = 2; break; case 'T': c = 3; break; case 'N': c = 4; break; default: return VTX_NO_UMI; }
+            k = (k << 3) | c;
+        }
+        return (k << 5) | len;
+    }
+private:
+    std::mutex mu_;
+    std::unordered_map<std::string, uint64_t> map_;
+};
+
+// rust-htslib 0.36 CigarStringView::read_pos(p, include_softclips = false, include_dels = true) folded
+// into useful_alignment (main.rs:790-806): is there a p in start..=end with an aligned base or a deletion?
+inline bool useful_alignment(const BamRecord& rec, int64_t start, int64_t end)
+{
+    const uint8_t* cg = rec.cigar();
+    const uint32_t nc = rec.n_cigar();
+    auto op_at = [&](uint32_t i) { return rd32(cg + 4 * i) & 0xF; };
+    auto len_at = [&](uint32_t i) { return int64_t(rd32(cg + 4 * i) >> 4); };
+    // leading section: first of M,=,X,I,S starts the walk; leading D/N or an interior H is an error (read skipped)
+    uint32_t i0 = 0;
+    while (i0 < nc) {
+        const uint32_t op = op_at(i0);
+        if (op == 0 || op == 7 || op == 8 || op == 1 || op == 4) break;
+        if (op == 2 || op == 3) return false;
+        if (op == 5 && i0 != 0 && i0 != nc - 1) return false;
+        ++i0;
+    }
+    if (i0 >= nc) return false;
+    for (int64_t p = start; p <= end; ++p) {          // inclusive end, main.rs:794
+        int64_t rpos = rec.pos();
+        for (uint32_t i = i0; i < nc && rpos <= p; ++i) {
+            const uint32_t op = op_at(i); const int64_t len = len_at(i);
+            if (op == 0 || op == 7 || op == 8 || op == 2) { if (p >= rpos && p < rpos + len) return true; rpos += len; }
+            else if (op == 3) rpos += len;
+            else if (op == 5) { if (i != nc - 1) return false; break; }
+        }
+    }
+    return false;
+}
+
+inline void pad16(std::vector<uint8_t>& v) { while (v.size() & 15) v.push_back(0); }
+
+// Records [lo, hi) of the VCF -> one shard.  Mirrors evaluate_rec + the head of evaluate_alns.
+inline bool stage_loci(const std::vector<VcfRecord>& recs, size_t lo, size_t hi, const Fasta& fa, BamFile& bam,
+                       const StageArgs& a, UmiInterner& umis, StagedShard* out, std::string* err)
+{
+    std::unordered_map<uint64_t, uint32_t> read_index;      // record virtual offset -> staged read id
+    BamRecord rec;
+    std::string left, right, ref_hap, alt_hap;
+    out->cand_start.push_back(0);
+    for (size_t i = lo; i < hi; ++i) {
+        const VcfRecord& v = recs[i];
+        const int64_t start = v.pos0, end = v.pos0 + int64_t(v.alleles[0].size());      // main.rs:619-623
+        if (v.alleles.size() > 2) { out->met.num_multiallelic_recs++; continue; }       // main.rs:646-653
+        const std::string alt = v.alleles.size() == 2 ? v.alleles[1] : std::string();   // main.rs:656-659
+        const int64_t L = fa.length(v.chrom);
+        if (L < 0) { *err = "Requested chromosome " + v.chrom + " was not found in fasta"; return false; }
+        // construct_haplotypes, main.rs:958-994
+        if (!fa.fetch_upper(v.chrom, std::max<int64_t>(start - a.padding, 0), start, &left) ||
+            !fa.fetch_upper(v.chrom, end, std::min(end + a.padding, L), &right) ||
+            !fa.fetch_upper(v.chrom, std::max<int64_t>(0, start - a.padding), std::min(end + a.padding, L), &ref_hap)) {
+            *err = "FASTA fetch failed at " + v.chrom + ":" + std::to_string(v.pos0);
+            return false;
+        }
+        alt_hap = left + alt + right;
+        bool ok = true;
+        for (unsigned char c : alt_hap) if (!a.valid[c]) { ok = false; break; }         // main.rs:675-684
+        if (!ok) { out->met.num_invalid_recs++; continue; }
+        out->locus_row.push_back(uint32_t(i));
+        pad16(out->hap_bytes); out->ref_off.push_back(uint32_t(out->hap_bytes.size())); out->ref_len.push_back(uint32_t(ref_hap.size()));
+        out->hap_bytes.insert(out->hap_bytes.end(), ref_hap.begin(), ref_hap.end());
+        pad16(out->hap_bytes); out->alt_off.push_back(uint32_t(out->hap_bytes.size())); out->alt_len.push_back(uint32_t(alt_hap.size()));
+        out->hap_bytes.insert(out->hap_bytes.end(), alt_hap.begin(), alt_hap.end());
+
+        const int tid = bam.tid_of(v.chrom);
+        if (tid >= 0 && bam.fetch(tid, start, end)) {                                    // main.rs:822-826
+            while (bam.next(&rec)) {
+                out->met.num_reads++;
+                const uint32_t fl = rec.flag();
+                if (rec.mapq() < a.mapq) { out->met.num_low_mapq++; continue; }                               // 833
+                if (a.primary_only && (fl & 0x100 || fl & 0x800)) { out->met.num_non_primary++; continue; }   // 841
+                if (a.no_duplicates && (fl & 0x400)) { out->met.num_duplicates++; continue; }                 // 849
+                if (!useful_alignment(rec, start, end)) { out->met.num_not_useful++; continue; }              // 857
+                auto ins = read_index.emplace(rec.voff, uint32_t(out->read_len.size()));
+                if (ins.second) {
+                    const int32_t ls = rec.l_seq() < 0 ? 0 : rec.l_seq();
+                    pad16(out->read_nib);
+                    out->read_off.push_back(out->read_nib.size());
+                    out->read_len.push_back(uint32_t(ls));
+                    out->read_nib.insert(out->read_nib.end(), rec.seq(), rec.seq() + (ls + 1) / 2);
+                    uint32_t n = 0;
+                    const uint8_t* cb = rec.aux_z(a.bam_tag, &n);                                             // main.rs:737-750
+                    if (cb && n <= 0xFFFF) { out->read_cb_off.push_back(uint32_t(out->cb_bytes.size())); out->read_cb_len.push_back(uint16_t(n)); out->cb_bytes.insert(out->cb_bytes.end(), cb, cb + n); }
+                    else { out->read_cb_off.push_back(VTX_NO_CB); out->read_cb_len.push_back(0); }
+                    const uint8_t* ub = rec.aux_z("UB", &n);                                                  // main.rs:752-757
+                    out->read_umi_key.push_back(ub ? umis.key(ub, n) : VTX_NO_UMI);
+                }
+                out->cand_read.push_back(ins.first->second);
+            }
+        }
+        out->cand_start.push_back(out->cand_read.size());
+    }
+    pad16(out->read_nib);
+    pad16(out->hap_bytes);
+    return true;
+}
+
+}  // namespace vtxhost

@@ -679,6 +679,14 @@ int vtx_sync(vtx_ctx* ctx)
     return VTX_OK;
 }
 
+int vtx_wait_copies(vtx_ctx* ctx)
+{
+    if (!ctx) return VTX_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->copy_stream));
+    return VTX_OK;
+}
+
 static int finish_scalars(vtx_ctx* ctx)
 {
     CK(cudaSetDevice(ctx->device));

@@ -180,11 +180,12 @@ class Triplets:
     metrics: dict
 
 
-def _np_from(ptr, n, dt):
+def _np_from(ptr, n, dt, copy=True):
     if n == 0 or not ptr:
         return np.zeros(0, dt)
     ct = np.ctypeslib.as_ctypes_type(dt)
-    return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), shape=(n,)).copy()
+    a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), shape=(n,))
+    return a.copy() if copy else a
 
 
 class Engine:
@@ -232,12 +233,14 @@ class Engine:
     def submit_device(self, cbatch: _capi.Batch, max_read_len: int, max_hap_len: int):
         self._ck(self._L.vtx_submit_device_ex(self._h, C.byref(cbatch), max_read_len, max_hap_len), "vtx_submit_device_ex")
 
-    def _triplets(self, res: _capi.Result) -> Triplets:
+    def _triplets(self, res: _capi.Result, copy: bool = True) -> Triplets:
+        """copy=False returns views of the library-owned pinned arrays (valid until the next engine call)."""
         n = int(res.n)
         m = res.metrics
-        return Triplets(_np_from(res.row, n, np.uint32), _np_from(res.col, n, np.uint32), _np_from(res.ref_cnt, n, np.uint32),
-                        _np_from(res.alt_cnt, n, np.uint32), _np_from(res.unk_cnt, n, np.uint32),
-                        _np_from(res.val, n, np.float64), _np_from(res.val2, n, np.float64),
+        return Triplets(_np_from(res.row, n, np.uint32, copy), _np_from(res.col, n, np.uint32, copy),
+                        _np_from(res.ref_cnt, n, np.uint32, copy), _np_from(res.alt_cnt, n, np.uint32, copy),
+                        _np_from(res.unk_cnt, n, np.uint32, copy), _np_from(res.val, n, np.float64, copy),
+                        _np_from(res.val2, n, np.float64, copy),
                         dict(num_not_cell_bc=int(m.num_not_cell_bc), num_non_umi=int(m.num_non_umi), num_scored=int(m.num_scored)))
 
     def finish(self) -> Triplets:
@@ -294,10 +297,10 @@ class Engine:
         self._ck(self._L.vtx_gather(self._h, C.byref(res)), "vtx_gather")
         return res
 
-    def fetch(self, dev_res: _capi.Result) -> Triplets:
+    def fetch(self, dev_res: _capi.Result, copy: bool = True) -> Triplets:
         out = _capi.Result()
         self._ck(self._L.vtx_fetch(self._h, C.byref(dev_res), C.byref(out)), "vtx_fetch")
-        return self._triplets(out)
+        return self._triplets(out, copy)
 
 
 def pack_umi(s: bytes) -> int:
