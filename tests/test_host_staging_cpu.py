@@ -75,3 +75,31 @@ def test_cli_refuses_to_overwrite_and_missing_inputs(tmp_path):
     assert r.returncode == 1 and "Output path already exists" in r.stderr            # main.rs:475-480
     r = subprocess.run([*base[:2], "/nonexistent.vcf", *base[3:]], cwd=str(tmp_path), capture_output=True, text=True)
     assert r.returncode == 1 and "does not exist" in r.stderr                        # main.rs:501-506
+
+
+# ---- synthetic files (no reference needed: also runs on the GPU box) ------------------------------------
+@pytest.fixture(scope="module")
+def dataset(tmp_path_factory):
+    from vartrix_b200 import synth_files
+    d = tmp_path_factory.mktemp("synth_files")
+    return synth_files.write_dataset(str(d), n_loci=150, n_barcodes=40, depth=24, read_len=100, seed=5)
+
+
+@pytest.mark.parametrize("extra,kw", [
+    ([], {}),
+    (["--mapq", "20", "--primary-alignments", "--no-duplicates", "--padding", "80", "--valid-chars", "ATGC"],
+     dict(mapq=20, primary_only=True, no_duplicates=True, padding=80, valid_chars="ATGC")),
+])
+def test_cpp_staging_equals_oracle_on_synthetic_files(oracle, dataset, tmp_path, extra, kw):
+    out = tmp_path / "d.staged"
+    subprocess.run([CLI, "-v", dataset["vcf"], "-b", dataset["bam"], "-f", dataset["fasta"], "-c", dataset["barcodes"],
+                    "--dump-staged", str(out), "--shard-loci", "1000000", "--threads", "2", *extra], check=True, cwd=str(tmp_path))
+    from vartrix_b200.staged_io import read_dump
+    n_rows, n_cols, shards = read_dump(str(out))
+    sb, met = shards[0]
+    ob = oracle.stage_from_files(dataset["vcf"], dataset["bam"], dataset["fasta"], **kw)
+    _same_staging(sb, ob)
+    assert met == {k: ob.host_metrics[k] for k in met}
+    assert n_rows == 150 and n_cols == 40                      # duplicate barcode line dropped (main.rs:706-709)
+    assert met["num_multiallelic_recs"] > 0 and met["num_invalid_recs"] > 0 and met["num_not_useful"] > 0
+    assert sb.n_cand > 1000 and (sb.read_cb_off == 0xFFFFFFFF).any()
