@@ -1,7 +1,8 @@
 # vartrix_b200 -- build the sm_100a engine library (and the oracle used by the tests).
 NVCC      ?= /usr/local/cuda/bin/nvcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVCCFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-Wall,-Wextra -Xptxas -v
+EXTRA     ?=
+NVCCFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-Wall,-Wextra -Xptxas -v $(EXTRA)
 CSRC      := vartrix_b200/csrc
 LIBDIR    := vartrix_b200/lib
 LIB       := $(LIBDIR)/libvartrix_b200.so

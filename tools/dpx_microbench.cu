@@ -28,6 +28,12 @@ __global__ void __launch_bounds__(1024, 1) k(uint32_t* out, int iters, long long
             if (OP == 8) x[i] = __viaddmax_s16x2_relu(x[i], y, z);
             if (OP == 9) { x[i] = __viaddmax_s16x2(x[i], 0xFFFFFFFFu, y); asm volatile("mov.b32 %0, %1;" : "=r"(z) : "r"(x[i])); }
             if (OP == 10) x[i] = (x[i] + y) ^ z;       // IADD3/LOP3 (alu)
+            if (OP == 11) x[i] = __byte_perm(x[i], y, 0x7610);                       // PRMT
+            if (OP == 12) { x[i] = __viaddmax_s16x2(x[i], 0xFFFFFFFFu, y); z = __byte_perm(z, x[i], 0x7610); }   // DPX + PRMT 1:1
+            if (OP == 13) { x[i] = __viaddmax_s16x2(x[i], 0xFFFFFFFFu, y); z = (z ^ x[i]) | 0x80008000u; }       // DPX + LOP3 1:1
+            if (OP == 14) { x[i] = __viaddmax_s16x2(x[i], 0xFFFFFFFFu, y); z = (z & x[i]) + 0x10001u; y = y ^ (z >> 3); }  // DPX + 3 alu
+            if (OP == 15) x[i] = __vcmpeq2(x[i], y) + z;                             // packed compare (emulated?)
+            if (OP == 16) x[i] = max((int)x[i], (int)y) + 1;                         // 32-bit max
         }
     }
     long long t1 = clock64();
@@ -64,6 +70,12 @@ int main()
     run<4>("IMAD", 8);
     run<5>("VIADDMNMX + IMAD 2:1 (12 per iter)", 12);
     run<9>("VIADDMNMX + MOV 1:1 (16 per iter)", 16);
+    run<11>("PRMT", 8);
+    run<12>("VIADDMNMX + PRMT 1:1 (16 per iter)", 16);
+    run<13>("VIADDMNMX + LOP3 1:1 (16 per iter)", 16);
+    run<14>("VIADDMNMX + 3-4 int ops (per DPX)", 8);
+    run<15>("__vcmpeq2 (+IADD)", 8);
+    run<16>("IMNMX.S32 (+IADD)", 8);
     run<6>("SHFL.UP", 8);
     run<7>("LDS.128 (+3 IADD)", 8);
     return 0;

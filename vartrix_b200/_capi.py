@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libvartrix_b200.so")
+# VTX_LIB lets kernel-tuning experiments load an alternative build of the same library
+LIB_PATH = os.environ.get("VTX_LIB") or os.path.join(_HERE, "lib", "libvartrix_b200.so")
 
 VTX_OK = 0
 MODE_CONSENSUS, MODE_COVERAGE, MODE_ALT_FRAC = 0, 1, 2

@@ -166,13 +166,14 @@ int launch_sw_class(vtx_ctx* ctx, SwArgs a, uint64_t* launches)
     using TC = TileClass<CLS>;
     constexpr int PPW = 32 / TC::LPP, RS = TC::LPP * TC::CS;
     const size_t warp_bytes = (size_t(5 * RS) * 4 + size_t(PPW) * (a.mcap + 2 * TC::LPP) * 2 + 15) & ~size_t(15);
-    const size_t smem = warp_bytes * 8;
+    constexpr int kSwThreads = TC::THREADS;
+    const size_t smem = warp_bytes * (kSwThreads / 32);
     auto kern = vtx_k_sw_pairs<CLS>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSwThreads, smem));
     if (per_sm < 1) return set_err(ctx, VTX_E_CUDA, "SW kernel class %d does not fit on an SM (smem %zu)", CLS, smem);
-    kern<<<ctx->n_sm * per_sm, 256, smem, ctx->stream>>>(a);
+    kern<<<ctx->n_sm * per_sm, kSwThreads, smem, ctx->stream>>>(a);
     CK(cudaGetLastError());
     ++*launches;
     return VTX_OK;

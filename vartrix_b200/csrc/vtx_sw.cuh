@@ -45,14 +45,19 @@ constexpr int kNumFastClasses = 4;
 constexpr int kSlowClass = kNumFastClasses;
 constexpr int kNumClasses = kNumFastClasses + 1;
 constexpr int kTileChunk = 8;            // tiles grabbed per atomic
+#ifndef VTX_SW_CHAIN
+#define VTX_SW_CHAIN 1                   // 1: keep max(diag + s, F, 0) off the E -> H -> H+gap dependency chain
+#endif
 
 // fast tile classes: lanes per pair, columns per lane, storage stride (words; CS % 4 == 0, (CS/4) odd
 // so the 8 lanes of an LDS.128 wavefront hit 8 distinct 16-byte bank groups)
 template <int CLS> struct TileClass;
-template <> struct TileClass<0> { static constexpr int LPP = 8, C = 26, CS = 28; };   // n <= 208 (SNV, pad 100)
-template <> struct TileClass<1> { static constexpr int LPP = 8, C = 29, CS = 36; };   // n <= 232 (indels <= 30)
-template <> struct TileClass<2> { static constexpr int LPP = 8, C = 32, CS = 36; };   // n <= 256
-template <> struct TileClass<3> { static constexpr int LPP = 8, C = 40, CS = 44; };   // n <= 320
+// THREADS x MINB = CTA shape / CTAs per SM the register allocator must leave room for (measured on B200,
+// profiles/r01_sw_variants.txt: 20 warps/SM at <= 102 registers beats 16 warps at 108 by ~4 %)
+template <> struct TileClass<0> { static constexpr int LPP = 8, C = 26, CS = 28, THREADS = 320, MINB = 2; };   // n <= 208 (SNV, pad 100)
+template <> struct TileClass<1> { static constexpr int LPP = 8, C = 29, CS = 36, THREADS = 320, MINB = 2; };   // n <= 232 (indels <= 30)
+template <> struct TileClass<2> { static constexpr int LPP = 8, C = 32, CS = 36, THREADS = 256, MINB = 2; };   // n <= 256
+template <> struct TileClass<3> { static constexpr int LPP = 8, C = 40, CS = 44, THREADS = 384, MINB = 1; };   // n <= 320
 __host__ __device__ constexpr int class_max_n(int cls)
 {
     return cls == 0 ? 208 : cls == 1 ? 232 : cls == 2 ? 256 : cls == 3 ? 320 : 0x7fffffff;
@@ -113,7 +118,7 @@ __device__ __forceinline__ void call_and_scatter(const SwArgs& a, uint32_t pair,
 }
 
 template <int CLS>
-__global__ void __launch_bounds__(256, 2) vtx_k_sw_pairs(const SwArgs a)
+__global__ void __launch_bounds__(TileClass<CLS>::THREADS, TileClass<CLS>::MINB) vtx_k_sw_pairs(const SwArgs a)
 {
     using TC = TileClass<CLS>;
     constexpr int LPP = TC::LPP, C = TC::C, CS = TC::CS;
@@ -144,8 +149,9 @@ __global__ void __launch_bounds__(256, 2) vtx_k_sw_pairs(const SwArgs a)
         if (t_begin >= n_tiles) break;
         const uint32_t t_end = min(t_begin + kTileChunk, n_tiles);
 
+        uint32_t locus = upper_locus(a.tile_start, a.n_loci, t_begin);
         for (uint32_t tile = t_begin; tile < t_end; ++tile) {
-            const uint32_t locus = upper_locus(a.tile_start, a.n_loci, tile);
+            while (tile >= __ldg(a.tile_start + locus + 1)) ++locus;      // tiles of a chunk are consecutive
             const uint32_t p0 = __ldg(a.pair_start + locus) + PPW * (tile - __ldg(a.tile_start + locus));
             const uint32_t p_end = __ldg(a.pair_start + locus + 1);
 
@@ -217,9 +223,15 @@ __global__ void __launch_bounds__(256, 2) vtx_k_sw_pairs(const SwArgs a)
                         const int c = 4 * q + k;
                         if (c < C) {
                             const uint32_t fc = __viaddmax_s16x2(f[c], kGE2, hg[c]);     // F[i][c]
+#if VTX_SW_CHAIN
+                            const uint32_t tf = __viaddmax_s16x2_relu(diag, sv[k], fc); // max(H[i-1][c-1] + s, F, 0): off the chain
+                            e = __viaddmax_s16x2(e, kGE2, hleft);                       // E[i][c]
+                            const uint32_t h = __vmaxs2(tf, e);                         // H[i][c]
+#else
                             e = __viaddmax_s16x2(e, kGE2, hleft);                       // E[i][c]
                             const uint32_t tt = __vadd2(diag, sv[k]);                   // H[i-1][c-1] + s
                             const uint32_t h = __vimax3_s16x2_relu(tt, e, fc);          // H[i][c]
+#endif
                             hh[k] = h;
                             diag = hg[c];
                             hleft = __vadd2(h, kGOE2);
