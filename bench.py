@@ -215,7 +215,7 @@ def run_gpu(args):
     n_pairs = info["n_pairs"]
 
     stream = torch.cuda.Stream()
-    eng = vb.Engine(cfg["scoring_method"], umi=bool(cfg.get("umi")), device=local, stream=stream.cuda_stream)
+    eng = vb.Engine(cfg["scoring_method"], umi=bool(cfg.get("umi")), device=local, stream=stream.cuda_stream, values_only=True)
     eng.set_barcodes(bcs)
     if world > 1:       # ship the NCCL unique id of the engine's own communicator over torch.distributed
         from vartrix_b200 import dist as vdist
@@ -311,7 +311,7 @@ def run_gpu(args):
     t_e = eng.timing()
     e2e_value = total_pairs * args.steps / (ms_e / 1e3)
     n_out = int(last_e.n) if hasattr(last_e, "n") else len(last_e.row)
-    d2h_bytes = n_out * 36 + 32
+    d2h_bytes = n_out * 16 + 32        # row, col (u32) + val (f64) per triplet (VTX_F_VALUES_ONLY) + counters
 
     line = None
     if rank == 0:

@@ -67,6 +67,9 @@ typedef struct vtx_config {
 } vtx_config;
 
 #define VTX_F_KEEP_SCORES 1u    /* also keep per-pair raw scores on the device (debug / parity) */
+#define VTX_F_NO_SPLIT    2u    /* do not use the two-phase (shared-prefix) Smith-Waterman kernels */
+#define VTX_F_VALUES_ONLY 4u    /* vtx_finish / vtx_fetch copy only row, col, val (and val2 in coverage mode) to the host;
+                                   ref_cnt / alt_cnt / unk_cnt come back NULL (halves the device->host traffic) */
 
 /*
  * One staged shard of loci.  SoA; for vtx_submit the pointers are HOST pointers (ideally pinned, see

@@ -110,6 +110,7 @@ def _random_pairs_batch(vb, rng, n_loci, reads_per_locus, m_lo, m_hi, n_lo, n_hi
 
 @pytest.mark.parametrize("name,kw", [
     ("class0_snv_shape", dict(n_loci=40, reads_per_locus=9, m_lo=100, m_hi=151, n_lo=190, n_hi=208)),
+    ("split_shapes_mixed_reads", dict(n_loci=60, reads_per_locus=13, m_lo=60, m_hi=256, n_lo=150, n_hi=232)),
     ("class1_indel_shape", dict(n_loci=30, reads_per_locus=7, m_lo=120, m_hi=150, n_lo=209, n_hi=232)),
     ("class2", dict(n_loci=20, reads_per_locus=6, m_lo=90, m_hi=160, n_lo=233, n_hi=256)),
     ("class3", dict(n_loci=20, reads_per_locus=6, m_lo=90, m_hi=250, n_lo=257, n_hi=320)),
@@ -124,14 +125,15 @@ def _random_pairs_batch(vb, rng, n_loci, reads_per_locus, m_lo, m_hi, n_lo, n_hi
     ("long_reads_generic", dict(n_loci=3, reads_per_locus=3, m_lo=1025, m_hi=1400, n_lo=180, n_hi=208)),
 ])
 def test_random_pairs_bit_exact(vb, oracle, name, kw):
-    rng = np.random.default_rng(abs(hash(name)) % (2**31) if False else sum(map(ord, name)))
+    rng = np.random.default_rng(sum(map(ord, name)))
     sb, pr, pl = _random_pairs_batch(vb, rng, **kw)
     perm = rng.permutation(len(pr))                 # arbitrary pair order is allowed
-    with vb.Engine("coverage") as eng:
-        rs, as_ = eng.score_pairs(sb, pr[perm], pl[perm])
     ors, oas = oracle.score_pairs(to_oracle_batch(oracle, sb), pr[perm], pl[perm], n_threads=8)
-    bad = np.nonzero((rs.astype(np.int32) != ors) | (as_.astype(np.int32) != oas))[0]
-    assert bad.size == 0, (name, bad[:5], rs[bad[:5]], ors[bad[:5]], as_[bad[:5]], oas[bad[:5]])
+    for no_split in (False, True):                  # two-phase (shared-prefix) kernels and the single-phase classes
+        with vb.Engine("coverage", no_split=no_split) as eng:
+            rs, as_ = eng.score_pairs(sb, pr[perm], pl[perm])
+        bad = np.nonzero((rs.astype(np.int32) != ors) | (as_.astype(np.int32) != oas))[0]
+        assert bad.size == 0, (name, no_split, bad[:5], rs[bad[:5]], ors[bad[:5]], as_[bad[:5]], oas[bad[:5]])
 
 
 # ------------------------------------------------------------------------------------------------
@@ -144,6 +146,7 @@ def test_synthetic_shard_matches_oracle(vb, oracle, mode, kind, umi):
     got = _run_engine(vb, sb, bcs, mode, umi)
     exp = _oracle_run(oracle, sb, bcs, mode, umi)
     assert_same_triplets(got, exp)
+    assert_same_triplets(_run_engine(vb, sb, bcs, mode, umi, no_split=True), exp)
     assert got.metrics == exp.metrics and got.metrics["num_scored"] == info["n_pairs"]
     # text output is byte-identical to the oracle's writer as well
     assert vb.mtx.mtx_text(sb.n_rows, len(bcs), got.row, got.col, got.val) == oracle.mtx_text(sb.n_rows, len(bcs), exp.row, exp.col, exp.val)

@@ -19,6 +19,8 @@ MODES = {"consensus": MODE_CONSENSUS, "coverage": MODE_COVERAGE, "alt_frac": MOD
 NO_CB = 0xFFFFFFFF
 NO_UMI = 0xFFFFFFFFFFFFFFFF
 F_KEEP_SCORES = 1
+F_NO_SPLIT = 2
+F_VALUES_ONLY = 4
 
 # every symbol include/vartrix_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [

@@ -77,9 +77,22 @@ public:
     bool at_eof() const { return eof_; }
 
 private:
+    // neighbouring loci fetch overlapping file ranges: keep the last few inflated blocks
+    struct Cached { uint64_t coff = ~0ull, next = 0; std::vector<uint8_t> data; };
+    static constexpr int kCache = 6;
+    Cached cache_[kCache];
+    int cache_rr_ = 0;
+
     bool load(uint64_t coff)
     {
         eof_ = false;
+        for (Cached& c : cache_)
+            if (c.coff == coff) {
+                if (ubuf_.size() < c.data.size()) ubuf_.resize(c.data.size());
+                memcpy(ubuf_.data(), c.data.data(), c.data.size());
+                block_coff_ = coff; block_len_ = uint32_t(c.data.size()); block_pos_ = 0; next_coff_ = c.next; have_block_ = true;
+                return true;
+            }
         if (coff >= size_) { eof_ = true; have_block_ = true; block_coff_ = coff; block_len_ = 0; block_pos_ = 0; next_coff_ = coff; return false; }
         uint8_t hdr[18];
         if (pread(fd_, hdr, 18, off_t(coff)) != 18) { eof_ = true; return false; }
@@ -111,6 +124,8 @@ private:
             if (inflate(&zs_, Z_FINISH) != Z_STREAM_END) return false;
         }
         block_coff_ = coff; block_len_ = isize; block_pos_ = 0; next_coff_ = coff + total; have_block_ = true;
+        Cached& c = cache_[cache_rr_]; cache_rr_ = (cache_rr_ + 1) % kCache;
+        c.coff = coff; c.next = next_coff_; c.data.assign(ubuf_.begin(), ubuf_.begin() + isize);
         return true;
     }
     int fd_ = -1;

@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <malloc.h>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -184,6 +185,10 @@ void stage_into_arena(const StagedShard& s, Arena& a, vtx_batch* b)
 
 int main(int argc, char** argv)
 {
+    // staging grows multi-megabyte vectors on many threads: keep them on the heap arenas instead of
+    // mmap/munmap per reallocation (which serialises the threads on the process address-space lock)
+    mallopt(M_MMAP_THRESHOLD, 1 << 30);
+    mallopt(M_TRIM_THRESHOLD, 1 << 30);
     Opts o;
     if (!parse(argc, argv, &o)) { usage(); return 1; }
     check_inputs_exist(o);
@@ -230,6 +235,7 @@ int main(int argc, char** argv)
     const size_t window = size_t(o.threads) * 2 + 2;
     bool failed = false; std::string fail_msg;
     UmiInterner umis;
+    std::vector<std::unique_ptr<StagedShard>> recycled;      // guarded by mu
     auto worker = [&]() {
         Fasta fa; BamFile bam; std::string e;
         if (!fa.open(o.fasta, &e) || !bam.open(o.bam, &e)) { std::lock_guard<std::mutex> g(mu); failed = true; fail_msg = e; cv.notify_all(); return; }
@@ -237,7 +243,9 @@ int main(int argc, char** argv)
             const size_t k = next.fetch_add(1);
             if (k >= n_shards) break;
             { std::unique_lock<std::mutex> g(mu); cv.wait(g, [&] { return failed || k < consumed + window; }); if (failed) return; }
-            auto sh = std::make_unique<StagedShard>();
+            std::unique_ptr<StagedShard> sh;
+            { std::lock_guard<std::mutex> g(mu); if (!recycled.empty()) { sh = std::move(recycled.back()); recycled.pop_back(); } }
+            if (!sh) sh = std::make_unique<StagedShard>();
             const size_t lo = k * size_t(o.shard_loci), hi = std::min(recs.size(), lo + size_t(o.shard_loci));
             if (!stage_loci(recs, lo, hi, fa, bam, sa, umis, sh.get(), &e)) { std::lock_guard<std::mutex> g(mu); failed = true; fail_msg = e; cv.notify_all(); return; }
             { std::lock_guard<std::mutex> g(mu); ready[k] = std::move(sh); }
@@ -260,6 +268,7 @@ int main(int argc, char** argv)
         vtx_config cfg{};
         cfg.device = int(o.device);
         cfg.mode = o.scoring == "consensus" ? VTX_MODE_CONSENSUS : o.scoring == "coverage" ? VTX_MODE_COVERAGE : VTX_MODE_ALT_FRAC;
+        cfg.flags = VTX_F_VALUES_ONLY;       // the writers need row, col and the matrix values only
         cfg.use_umi = o.umi; cfg.match = 1; cfg.mismatch = -5; cfg.gap_open = -5; cfg.gap_extend = -1; cfg.min_score = 25;
         if (vtx_create(&cfg, &ctx) != VTX_OK) { printf("Vartrix error.\nError: %s\n", vtx_last_error(nullptr)); return 1; }
         if (vtx_set_barcodes(ctx, bcs.bytes.data(), bcs.off.data(), uint32_t(bcs.keys.size())) != VTX_OK) { printf("Vartrix error.\nError: %s\n", vtx_last_error(ctx)); return 1; }
@@ -276,13 +285,15 @@ int main(int argc, char** argv)
         }
         cv.notify_all();
         hm.add(sh->met);
-        if (dump) { dump_shard(dump, *sh); continue; }
+        auto recycle = [&]() { sh->clear(); std::lock_guard<std::mutex> g(mu); recycled.push_back(std::move(sh)); };
+        if (dump) { dump_shard(dump, *sh); recycle(); continue; }
         Arena& ar = arenas[k % 3];
         if (k >= 3 && vtx_wait_copies(ctx) != VTX_OK) { rc = 1; break; }     // the arena's previous copy must have landed
         if (!ar.ensure(sh->bytes())) { LOG_ERR("pinned allocation failed"); rc = 1; break; }
         vtx_batch b;
         stage_into_arena(*sh, ar, &b);
         if (vtx_submit(ctx, &b) != VTX_OK) { printf("Vartrix error.\nError: %s\n", vtx_last_error(ctx)); rc = 1; }
+        recycle();
     }
     if (rc) { std::lock_guard<std::mutex> g(mu); failed = true; }
     cv.notify_all();

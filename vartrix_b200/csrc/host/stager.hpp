@@ -41,6 +41,12 @@ struct StagedShard {
     std::vector<uint8_t> hap_bytes, read_nib, cb_bytes;
     HostMetrics met;
 
+    void clear()          // keeps the capacity: shards are recycled so steady-state staging does not page-fault
+    {
+        locus_row.clear(); ref_off.clear(); ref_len.clear(); alt_off.clear(); alt_len.clear(); read_len.clear(); read_cb_off.clear();
+        cand_read.clear(); cand_start.clear(); read_off.clear(); read_umi_key.clear(); read_cb_len.clear(); hap_bytes.clear();
+        read_nib.clear(); cb_bytes.clear(); met = HostMetrics();
+    }
     size_t bytes() const
     {
         return (locus_row.size() + ref_off.size() * 4 + read_len.size() * 2 + cand_read.size()) * 4 +

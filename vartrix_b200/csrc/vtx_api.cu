@@ -179,6 +179,22 @@ int launch_sw_class(vtx_ctx* ctx, SwArgs a, uint64_t* launches)
     return VTX_OK;
 }
 
+template <int SCLS>
+int launch_sw_split(vtx_ctx* ctx, SwArgs a, uint64_t* launches)
+{
+    using SC = SplitClass<SCLS>;
+    const size_t smem = split_warp_bytes<SCLS>(a.mcap) * (SC::THREADS / 32);
+    auto kern = vtx_k_sw_split<SCLS>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SC::THREADS, smem));
+    if (per_sm < 1) return set_err(ctx, VTX_E_CUDA, "split SW kernel %d does not fit on an SM (smem %zu)", SCLS, smem);
+    kern<<<ctx->n_sm * per_sm, SC::THREADS, smem, ctx->stream>>>(a);
+    CK(cudaGetLastError());
+    ++*launches;
+    return VTX_OK;
+}
+
 // classes + tiles + SW kernels, shared by submit and score_pairs.  pair_start must be ready.
 int run_sw(vtx_ctx* ctx, const DevBatch& b, uint32_t n_pairs_ub, const uint32_t* pair_slot, uint32_t* counters,
            uint32_t* pair_scores, uint64_t* launches, uint64_t* sw_launches, TimeRec* tr)
@@ -188,8 +204,9 @@ int run_sw(vtx_ctx* ctx, const DevBatch& b, uint32_t n_pairs_ub, const uint32_t*
     ENS(ctx->tstart, size_t(kNumClasses) * (nl + 1) * 4);
     ENS(ctx->tile_counters, 64);
     const int force_slow = b.max_read_len > uint32_t(kFastMaxRead) ? 1 : 0;
+    const int allow_split = (b.max_read_len <= uint32_t(kSplitMaxRead) && !(ctx->cfg.flags & VTX_F_NO_SPLIT)) ? 1 : 0;
     vtx_k_locus_prep<<<blocks_for(uint64_t(nl) * 32, 256), 256, 0, ctx->stream>>>(
-        nl, b.hap, b.ref_off, b.ref_len, b.alt_off, b.alt_len, P<uint32_t>(ctx->pair_start), force_slow,
+        nl, b.hap, b.ref_off, b.ref_len, b.alt_off, b.alt_len, P<uint32_t>(ctx->pair_start), force_slow, allow_split,
         P<uint32_t>(ctx->tcount));
     ++*launches;
     for (int c = 0; c < kNumClasses; ++c) {
@@ -209,6 +226,7 @@ int run_sw(vtx_ctx* ctx, const DevBatch& b, uint32_t n_pairs_ub, const uint32_t*
     int mcap = int(std::min<uint32_t>(b.max_read_len, kFastMaxRead));
     mcap = std::max(2, (mcap + 1) & ~1);
     a.mcap = mcap;
+    a.k64k = 65536u;
     a.max_hap = b.max_hap_len;
 
     uint64_t before = *launches;
@@ -223,6 +241,14 @@ int run_sw(vtx_ctx* ctx, const DevBatch& b, uint32_t n_pairs_ub, const uint32_t*
         case 3: rc = launch_sw_class<3>(ctx, a, launches); break;
         }
         if (rc) return rc;
+    }
+    if (allow_split) {
+        for (int c = 0; c < kNumSplitClasses; ++c) {
+            a.tile_start = P<uint32_t>(ctx->tstart) + size_t(kSplitClass0 + c) * (nl + 1);
+            a.tile_counter = P<uint32_t>(ctx->tile_counters) + kSplitClass0 + c;
+            int rc = c == 0 ? launch_sw_split<0>(ctx, a, launches) : launch_sw_split<1>(ctx, a, launches);
+            if (rc) return rc;
+        }
     }
     {   // generic class (rare)
         const unsigned blocks = unsigned(ctx->n_sm) * 4, threads = 128;
@@ -731,15 +757,18 @@ static int fetch_to(vtx_ctx* ctx, const vtx_result* dev, vtx_result* out, void**
         *hcap = ncap;
     }
     const void* src[7] = { dev->row, dev->col, dev->ref_cnt, dev->alt_cnt, dev->unk_cnt, dev->val, dev->val2 };
+    const bool values_only = (ctx->cfg.flags & VTX_F_VALUES_ONLY) != 0;
+    bool want[7] = { true, true, !values_only, !values_only, !values_only, true, !values_only || ctx->cfg.mode == VTX_MODE_COVERAGE };
     if (n) {
-        for (int i = 0; i < 7; ++i) CK(cudaMemcpyAsync(hbuf[i], src[i], n * esz[i], cudaMemcpyDeviceToHost, ctx->stream));
+        for (int i = 0; i < 7; ++i)
+            if (want[i]) CK(cudaMemcpyAsync(hbuf[i], src[i], n * esz[i], cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }
     out->n = n;
     out->row = static_cast<uint32_t*>(hbuf[0]); out->col = static_cast<uint32_t*>(hbuf[1]);
-    out->ref_cnt = static_cast<uint32_t*>(hbuf[2]); out->alt_cnt = static_cast<uint32_t*>(hbuf[3]);
-    out->unk_cnt = static_cast<uint32_t*>(hbuf[4]);
-    out->val = static_cast<double*>(hbuf[5]); out->val2 = static_cast<double*>(hbuf[6]);
+    out->ref_cnt = want[2] ? static_cast<uint32_t*>(hbuf[2]) : nullptr; out->alt_cnt = want[3] ? static_cast<uint32_t*>(hbuf[3]) : nullptr;
+    out->unk_cnt = want[4] ? static_cast<uint32_t*>(hbuf[4]) : nullptr;
+    out->val = static_cast<double*>(hbuf[5]); out->val2 = want[6] ? static_cast<double*>(hbuf[6]) : nullptr;
     out->metrics = dev->metrics;
     return VTX_OK;
 }

@@ -14,6 +14,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 #include "vtx_sw.cuh"
+#include "vtx_sw_split.cuh"
 
 namespace vtx {
 
@@ -134,7 +135,7 @@ __global__ void vtx_k_pair_start_explicit(uint32_t n_loci, uint32_t n_pairs, con
 __global__ void vtx_k_locus_prep(uint32_t n_loci, const uint8_t* __restrict__ hap_bytes,
                                  const uint32_t* __restrict__ ref_off, const uint32_t* __restrict__ ref_len,
                                  const uint32_t* __restrict__ alt_off, const uint32_t* __restrict__ alt_len,
-                                 const uint32_t* __restrict__ pair_start, int force_slow,
+                                 const uint32_t* __restrict__ pair_start, int force_slow, int allow_split,
                                  uint32_t* __restrict__ tcount /* [kNumClasses][n_loci + 1] */)
 {
     const uint32_t l = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -152,17 +153,25 @@ __global__ void vtx_k_locus_prep(uint32_t n_loci, const uint8_t* __restrict__ ha
     for (uint32_t j = lane; j < nr; j += 32) exotic |= is_exotic(rh[j]);
     for (uint32_t j = lane; j < na; j += 32) exotic |= is_exotic(ah[j]);
     exotic = __any_sync(0xffffffffu, exotic);
+    // is the first kSplitP-column prefix common to both haplotypes?  (construct_haplotypes: same left flank)
+    bool same = nr >= uint32_t(kSplitP) && na >= uint32_t(kSplitP);
+    if (same) for (uint32_t j = lane; j < uint32_t(kSplitP); j += 32) same &= (rh[j] == ah[j]);
+    same = __all_sync(0xffffffffu, same);
     if (lane != 0) return;
     const uint32_t nmax = max(nr, na);
     int cls = kSlowClass;
     if (!exotic && !force_slow) {
 #pragma unroll
         for (int c = kNumFastClasses - 1; c >= 0; --c) if (nmax <= uint32_t(class_max_n(c))) cls = c;
+        if (same && allow_split) {
+#pragma unroll
+            for (int c = kNumSplitClasses - 1; c >= 0; --c) if (nmax <= uint32_t(split_max_n(c))) cls = kSplitClass0 + c;
+        }
     }
     const uint32_t np = pair_start[l + 1] - pair_start[l];
 #pragma unroll
     for (int c = 0; c < kNumClasses; ++c) {
-        const uint32_t ppw = (c == kSlowClass) ? kSlowPairsPerWarp : 4u;
+        const uint32_t ppw = (c == kSlowClass) ? uint32_t(kSlowPairsPerWarp) : (c > kSlowClass ? uint32_t(kSplitPPW) : 4u);
         tcount[size_t(c) * (n_loci + 1) + l] = (c == cls) ? (np + ppw - 1) / ppw : 0u;
     }
 }

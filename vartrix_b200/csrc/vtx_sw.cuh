@@ -41,9 +41,11 @@ constexpr uint32_t kNEG2 = pack2(-16384, -16384);
 constexpr int kProfMatch = kMatch - kGoe, kProfMis = kMismatch - kGoe;     // 7, 1
 
 constexpr int kFastMaxRead = 1024;       // longest read the fast kernels take (smem row-code buffer)
-constexpr int kNumFastClasses = 4;
-constexpr int kSlowClass = kNumFastClasses;
-constexpr int kNumClasses = kNumFastClasses + 1;
+constexpr int kNumFastClasses = 4;                 // single-phase tile classes 0..3
+constexpr int kSlowClass = kNumFastClasses;        // 4: generic kernel
+constexpr int kNumSplitClasses = 2;                // 5, 6: two-phase kernels (vtx_sw_split.cuh)
+constexpr int kSplitClass0 = kSlowClass + 1;
+constexpr int kNumClasses = kSplitClass0 + kNumSplitClasses;
 constexpr int kTileChunk = 8;            // tiles grabbed per atomic
 #ifndef VTX_SW_CHAIN
 #define VTX_SW_CHAIN 1                   // 1: keep max(diag + s, F, 0) off the E -> H -> H+gap dependency chain
@@ -81,6 +83,7 @@ struct SwArgs {
     uint32_t* pair_scores;          // optional [pair] packed {ref, alt} int16 (nullptr: not kept)
     int32_t min_score;              // MIN_SCORE main.rs:30
     int32_t mcap;                   // row-code capacity (even, >= longest read in the batch)
+    uint32_t k64k;                  // 65536 as a run-time value (keeps a shift-add on the FMA pipe, see vtx_sw_split.cuh)
     // generic kernel only
     uint32_t* scratch;              // [warps][max_hap + 1][32]
     uint32_t max_hap;

@@ -192,11 +192,13 @@ class Engine:
     """One engine context = one GPU (vtx_ctx).  Mirrors the role of the rayon pool + merge loop."""
 
     def __init__(self, scoring_method: str = "consensus", umi: bool = False, device: int = 0, stream: int = 0,
-                 keep_scores: bool = False, min_score: int = 25):
+                 keep_scores: bool = False, min_score: int = 25, no_split: bool = False,
+                 values_only: bool = False):
         self._L = _capi.load()
         cfg = _capi.Config(device=device, mode=MODES[scoring_method], use_umi=int(bool(umi)), match=1, mismatch=-5,
                            gap_open=-5, gap_extend=-1, min_score=min_score, stream=stream or None,
-                           flags=_capi.F_KEEP_SCORES if keep_scores else 0)
+                           flags=(_capi.F_KEEP_SCORES if keep_scores else 0) | (_capi.F_NO_SPLIT if no_split else 0) |
+                           (_capi.F_VALUES_ONLY if values_only else 0))
         h = C.c_void_p()
         rc = self._L.vtx_create(C.byref(cfg), C.byref(h))
         if rc != 0:
