@@ -12,7 +12,7 @@ HOSTSRC   := $(CSRC)/host
 
 all: $(LIB) $(CLI) oracle
 
-$(LIB): $(CSRC)/vtx_api.cu $(CSRC)/vtx_sw.cuh $(CSRC)/vtx_pipeline.cuh include/vartrix_b200.h
+$(LIB): $(CSRC)/vtx_api.cu $(wildcard $(CSRC)/*.cuh) include/vartrix_b200.h
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(CSRC)/vtx_api.cu -ldl 2> $(LIBDIR)/ptxas.log || (cat $(LIBDIR)/ptxas.log; exit 1)
 	@grep -E "error|warning" $(LIBDIR)/ptxas.log | grep -v "ptxas info" || true

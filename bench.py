@@ -322,10 +322,11 @@ def run_gpu(args):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0)); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6.65 TB/s"
         b_alg = vb.synth.algorithmic_bytes_per_pair(info)
-        traffic, traffic_src, alu_pct = None, None, None
+        traffic, traffic_src, alu_pct, tj_kernel = None, None, None, "vtx_k_sw_split<0>"
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "sw_kernel_traffic.json")))
             traffic = tj["dram_bytes_per_pair"] * n_pairs; traffic_src = tj["source"]; alu_pct = tj.get("alu_pipe_active_pct")
+            tj_kernel = tj.get("kernel", tj_kernel)
         except Exception:
             pass
         sw_avg_ms = float(np.mean(sw_ms))
@@ -341,7 +342,7 @@ def run_gpu(args):
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "ncu_alu_pipe_active_pct": alu_pct,
-                         "peak_source": peak_src, "kernel": "vtx_k_sw_pairs<0>",
+                         "peak_source": peak_src, "kernel": tj_kernel,
                          "kernel_ms": sw_avg_ms, "algorithmic_bytes_per_pair": b_alg, "pairs_per_launch": n_pairs,
                          "gcups": n_pairs * cells / (sw_avg_ms / 1e3) / 1e9,
                          "note": "integer DP: ~540 cell updates per algorithmic byte, so the kernel is DPX-issue bound, not HBM "

@@ -46,7 +46,7 @@ constexpr int kSlowClass = kNumFastClasses;        // 4: generic kernel
 constexpr int kNumSplitClasses = 2;                // 5, 6: two-phase kernels (vtx_sw_split.cuh)
 constexpr int kSplitClass0 = kSlowClass + 1;
 constexpr int kNumClasses = kSplitClass0 + kNumSplitClasses;
-constexpr int kTileChunk = 8;            // tiles grabbed per atomic
+constexpr int kTileChunk = 8;            // most tiles grabbed per atomic
 #ifndef VTX_SW_CHAIN
 #define VTX_SW_CHAIN 1                   // 1: keep max(diag + s, F, 0) off the E -> H -> H+gap dependency chain
 #endif
@@ -143,14 +143,17 @@ __global__ void __launch_bounds__(TileClass<CLS>::THREADS, TileClass<CLS>::MINB)
 
     const uint32_t n_tiles = __ldg(a.tile_start + a.n_loci);
     uint32_t cached_locus = 0xFFFFFFFFu;
+    // tiles grabbed per atomic: up to kTileChunk for locality of the per-locus profile, fewer when the shard is
+    // small so that every warp still gets >= ~16 grabs (tail balance)
+    const uint32_t tile_chunk = max(1u, min(uint32_t(kTileChunk), n_tiles / (gridDim.x * (blockDim.x >> 5) * 16u)));
 
     for (;;) {
         uint32_t chunk = 0;
         if (lane == 0) chunk = atomicAdd(a.tile_counter, 1u);
         chunk = __shfl_sync(0xffffffffu, chunk, 0);
-        const uint32_t t_begin = chunk * kTileChunk;
+        const uint32_t t_begin = chunk * tile_chunk;
         if (t_begin >= n_tiles) break;
-        const uint32_t t_end = min(t_begin + kTileChunk, n_tiles);
+        const uint32_t t_end = min(t_begin + tile_chunk, n_tiles);
 
         uint32_t locus = upper_locus(a.tile_start, a.n_loci, t_begin);
         for (uint32_t tile = t_begin; tile < t_end; ++tile) {

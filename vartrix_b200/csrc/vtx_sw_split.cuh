@@ -5,8 +5,8 @@
 // halves of vtx_k_sw_pairs carry the same numbers.  Here a warp tile is 8 pairs of one locus:
 //
 //   phase 1  columns [0, 96): the two halves hold two DIFFERENT READS (A, B) against the common prefix.
-//            4 units x 8 lanes, 12 columns per lane.  The substitution word is the low half of read A's
-//            profile row and the high half of read B's (one PRMT).  The last column of every row
+//            4 units x 8 lanes, 12 columns per lane.  The substitution word is s_A + (s_B << 16), formed
+//            with an IMAD so that it stays off the DPX pipe (PRMT/LOP3 share it).  The last column of every row
 //            (H + gap, E) is parked in shared memory, the prefix maximum per read too.
 //   phase 2  columns [96, n): halves are (ref, alt) of ONE read again.  8 reads x 4 lanes, C2 columns per
 //            lane; lane 0 of a read picks its half of the parked boundary and duplicates it (PRMT).
@@ -26,11 +26,12 @@ constexpr int kSplitMaxRead = 256;     // longer reads use the single-phase clas
 template <int SCLS> struct SplitClass;
 // COPIES: 2 = the phase-2 profile is stored twice, 16 banks apart, so the two reads of an LDS wavefront never
 // collide; 1 = single copy (2-way conflicts on those loads, 3 KB less shared memory per warp)
+// defaults = the best of profiles/r01_split_variants.txt (B200): one copy and 20 warps/SM for the SNV class
 #ifndef VTX_SPLIT0_COPIES
-#define VTX_SPLIT0_COPIES 2
+#define VTX_SPLIT0_COPIES 1
 #endif
 #ifndef VTX_SPLIT0_THREADS
-#define VTX_SPLIT0_THREADS 256
+#define VTX_SPLIT0_THREADS 320
 #endif
 #ifndef VTX_SPLIT1_COPIES
 #define VTX_SPLIT1_COPIES 1
@@ -79,15 +80,18 @@ __global__ void __launch_bounds__(SplitClass<SCLS>::THREADS, SplitClass<SCLS>::M
 
     const uint32_t n_tiles = __ldg(a.tile_start + a.n_loci);
     uint32_t cached_locus = 0xFFFFFFFFu;
+    // tiles grabbed per atomic: up to kTileChunk for locality of the per-locus profile, fewer when the shard is
+    // small so that every warp still gets >= ~16 grabs (tail balance)
+    const uint32_t tile_chunk = max(1u, min(uint32_t(kTileChunk), n_tiles / (gridDim.x * (blockDim.x >> 5) * 16u)));
     const uint32_t k64k = a.k64k;                                // 65536, opaque to ptxas so the merge stays an IMAD
 
     for (;;) {
         uint32_t chunk = 0;
         if (lane == 0) chunk = atomicAdd(a.tile_counter, 1u);
         chunk = __shfl_sync(0xffffffffu, chunk, 0);
-        const uint32_t t_begin = chunk * kTileChunk;
+        const uint32_t t_begin = chunk * tile_chunk;
         if (t_begin >= n_tiles) break;
-        const uint32_t t_end = min(t_begin + kTileChunk, n_tiles);
+        const uint32_t t_end = min(t_begin + tile_chunk, n_tiles);
         uint32_t locus = upper_locus(a.tile_start, a.n_loci, t_begin);
         for (uint32_t tile = t_begin; tile < t_end; ++tile) {
             while (tile >= __ldg(a.tile_start + locus + 1)) ++locus;
