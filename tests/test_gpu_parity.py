@@ -172,6 +172,18 @@ def test_edge_cases(vb, oracle):
     assert len(got.row) == 0
 
 
+@pytest.mark.parametrize("umi", [False, True])
+def test_deep_loci_use_the_hash_sort_slot_kernel(vb, oracle, umi):
+    """Loci deeper than 2 048 pairs (a variant in a highly expressed gene) leave the O(d^2) slot kernel."""
+    sb, bcs, info = vb.synth.make_shard(5, 700, depth=5000, seed=17, kind="snv", umi=umi, reads_per_umi=4, chunk_loci=1)
+    cs = sb.cand_start.copy(); cs[2] = cs[1] + 900          # mix: one shallow locus between deep ones
+    keep = np.concatenate([np.arange(int(cs[0]), int(cs[2])), np.arange(int(sb.cand_start[2]), sb.n_cand)])
+    sb.cand_read = sb.cand_read[keep]
+    cs[2:] = sb.cand_start[2:] - (sb.cand_start[2] - cs[2]); sb.cand_start = cs
+    for mode in ("coverage", "consensus"):
+        assert_same_triplets(_run_engine(vb, sb, bcs, mode, umi), _oracle_run(oracle, sb, bcs, mode, umi))
+
+
 def test_min_score_boundary_and_ties(vb, oracle):
     """evaluate_scores: strict '<' on MIN_SCORE 25 (main.rs:1020) and ties -> UNKNOWN."""
     hap = b"ACGTTGCAAGGCTTAACCGGATCGATCGTAGCTAGCTAGGATCCATTGGCA" * 4

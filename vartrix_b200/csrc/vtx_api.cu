@@ -61,7 +61,7 @@ struct vtx_ctx {
     // work buffers
     DBuf read_col, keep, pidx, scan_sums, pair_read, pair_col, pair_umi, pair_locus, pair_start, tcount, tstart,
         pair_first, pair_cslot, pair_uslot, cslot_col, cslot_locus, uslot_cslot, ccnt, ucnt, keep2, oidx, tile_counters,
-        scratch, pair_scores, d_metrics, d_res_n;
+        scratch, pair_scores, d_metrics, d_res_n, big_list, slot_scratch;
     // results (device) + host mirrors
     DBuf r_row, r_col, r_ref, r_alt, r_unk, r_val, r_val2;
     size_t res_cap = 0;        // entries
@@ -158,6 +158,7 @@ struct DevBatch {   // device pointers
     const uint8_t* cb_bytes; const uint32_t* read_cb_off; const uint16_t* read_cb_len; const uint64_t* read_umi;
     const uint32_t* cand_read;
     uint32_t max_read_len = 0, max_hap_len = 0;
+    uint64_t max_depth = ~0ull;      // most candidates of one locus (unknown for device batches: assume deep)
 };
 
 template <int CLS>
@@ -338,6 +339,9 @@ int process_batch(vtx_ctx* ctx, const DevBatch& b, TimeRec* tr)
     const uint32_t* n_pairs_ptr = P<uint32_t>(ctx->pidx) + nc;
 
     // ---- slots: the (row, col[, umi]) structure is independent of the alignment results ----------
+    ENS(ctx->big_list, size_t(nc / kSlotSmallMax + 2) * 4);
+    CK(cudaMemsetAsync(ctx->big_list.p, 0, 4, st));
+    if (b.max_depth > kSlotSmallMax) ENS(ctx->slot_scratch, size_t(kSlotBigWords) * nc * 4);
     CK(cudaMemsetAsync(ctx->cslot_col.p, 0xFF, size_t(nc) * 4, st));
     CK(cudaMemsetAsync(ctx->ccnt.p, 0, size_t(nc) * 16, st));
     if (use_umi) {
@@ -347,8 +351,15 @@ int process_batch(vtx_ctx* ctx, const DevBatch& b, TimeRec* tr)
     vtx_k_slots<<<std::min<uint32_t>(nl, 65535u * 8), kSlotThreads, 0, st>>>(
         nl, P<uint32_t>(ctx->pair_start), P<uint32_t>(ctx->pair_col), P<uint64_t>(ctx->pair_umi), use_umi,
         P<uint8_t>(ctx->pair_first), P<uint32_t>(ctx->pair_cslot), P<uint32_t>(ctx->pair_uslot),
-        P<uint32_t>(ctx->cslot_col), P<uint32_t>(ctx->cslot_locus), P<uint32_t>(ctx->uslot_cslot));
+        P<uint32_t>(ctx->cslot_col), P<uint32_t>(ctx->cslot_locus), P<uint32_t>(ctx->uslot_cslot), P<uint32_t>(ctx->big_list));
     ++launches;
+    if (nc > kSlotSmallMax) {       // a locus deeper than kSlotSmallMax pairs can only exist in such a shard
+        vtx_k_slots_big<<<ctx->n_sm, kSlotBigThreads, 0, st>>>(
+            P<uint32_t>(ctx->big_list), P<uint32_t>(ctx->pair_start), P<uint32_t>(ctx->pair_col), P<uint64_t>(ctx->pair_umi), use_umi,
+            P<uint32_t>(ctx->slot_scratch), P<uint32_t>(ctx->pair_cslot), P<uint32_t>(ctx->pair_uslot), P<uint32_t>(ctx->cslot_col),
+            P<uint32_t>(ctx->cslot_locus), P<uint32_t>(ctx->uslot_cslot));
+        ++launches;
+    }
     CK(cudaGetLastError());
 
     // ---- K2 + K3: Smith-Waterman, call, atomic scatter ----------------------------------------------
@@ -399,15 +410,18 @@ int validate_batch(vtx_ctx* ctx, const vtx_batch* b)
 
 // host-side checks that need to touch the (host) arrays; also returns max lengths.  Runs on a few host
 // threads while the shard's H2D copies are already in flight (the kernels are only enqueued afterwards).
-int scan_host_batch(vtx_ctx* ctx, const vtx_batch* b, uint32_t* max_read, uint32_t* max_hap, bool check_cands)
+int scan_host_batch(vtx_ctx* ctx, const vtx_batch* b, uint32_t* max_read, uint32_t* max_hap, bool check_cands,
+                    uint64_t* max_depth = nullptr)
 {
     uint32_t mh = 0;
+    uint64_t md = 0;
     for (uint32_t l = 0; l < b->n_loci; ++l) {
         if ((b->ref_off[l] & 15) || (b->alt_off[l] & 15)) return set_err(ctx, VTX_E_INVALID, "locus %u: haplotype offsets must be multiples of 16", l);
         if (uint64_t(b->ref_off[l]) + b->ref_len[l] > b->hap_bytes_len || uint64_t(b->alt_off[l]) + b->alt_len[l] > b->hap_bytes_len)
             return set_err(ctx, VTX_E_INVALID, "locus %u: haplotype window outside hap_bytes", l);
         if (l && b->locus_row[l] <= b->locus_row[l - 1]) return set_err(ctx, VTX_E_INVALID, "locus_row must be strictly ascending (locus %u)", l);
         if (check_cands && b->cand_start[l] > b->cand_start[l + 1]) return set_err(ctx, VTX_E_INVALID, "cand_start must be ascending (locus %u)", l);
+        if (check_cands) md = std::max<uint64_t>(md, b->cand_start[l + 1] - b->cand_start[l]);
         mh = std::max(mh, std::max(b->ref_len[l], b->alt_len[l]));
     }
     if (check_cands && b->n_loci && (b->cand_start[0] != 0 || b->cand_start[b->n_loci] != b->n_cand))
@@ -459,6 +473,7 @@ int scan_host_batch(vtx_ctx* ctx, const vtx_batch* b, uint32_t* max_read, uint32
     }
     if (mr > 32000) return set_err(ctx, VTX_E_UNSUPPORTED, "reads longer than 32000 bases (int16 DP) are not supported (%u)", mr);
     *max_read = mr; *max_hap = mh;
+    if (max_depth) *max_depth = md;
     return VTX_OK;
 }
 
@@ -572,7 +587,7 @@ void vtx_destroy(vtx_ctx* ctx)
                     &ctx->keep, &ctx->pidx, &ctx->scan_sums, &ctx->pair_read, &ctx->pair_col, &ctx->pair_umi, &ctx->pair_locus,
                     &ctx->pair_start, &ctx->tcount, &ctx->tstart, &ctx->pair_first, &ctx->pair_cslot, &ctx->pair_uslot, &ctx->cslot_col,
                     &ctx->cslot_locus, &ctx->uslot_cslot, &ctx->ccnt, &ctx->ucnt, &ctx->keep2, &ctx->oidx, &ctx->tile_counters,
-                    &ctx->scratch, &ctx->pair_scores, &ctx->d_metrics, &ctx->d_res_n, &ctx->r_row, &ctx->r_col, &ctx->r_ref,
+                    &ctx->scratch, &ctx->pair_scores, &ctx->big_list, &ctx->slot_scratch, &ctx->d_metrics, &ctx->d_res_n, &ctx->r_row, &ctx->r_col, &ctx->r_ref,
                     &ctx->r_alt, &ctx->r_unk, &ctx->r_val, &ctx->r_val2, &ctx->g_counts };
     for (DBuf* b : all) if (b->p) cudaFree(b->p);
     for (auto& b : ctx->g_dev) if (b.p) cudaFree(b.p);
@@ -657,7 +672,7 @@ int vtx_submit(vtx_ctx* ctx, const vtx_batch* hb)
     d.read_cb_off = P<uint32_t>(sl->read_cb_off); d.read_cb_len = P<uint16_t>(sl->read_cb_len);
     d.read_umi = P<uint64_t>(sl->read_umi); d.cand_read = P<uint32_t>(sl->cand_read);
     // 2. ... validate the host arrays meanwhile; nothing has been launched on them yet
-    rc = scan_host_batch(ctx, hb, &d.max_read_len, &d.max_hap_len, true);
+    rc = scan_host_batch(ctx, hb, &d.max_read_len, &d.max_hap_len, true, &d.max_depth);
     if (rc) { cudaStreamSynchronize(ctx->copy_stream); --ctx->trec_used; return rc; }
     // 3. kernels wait for the copy, and release the slot when done
     CK(cudaStreamWaitEvent(ctx->stream, sl->copy_done, 0));
@@ -761,7 +776,7 @@ static int fetch_to(vtx_ctx* ctx, const vtx_result* dev, vtx_result* out, void**
     bool want[7] = { true, true, !values_only, !values_only, !values_only, true, !values_only || ctx->cfg.mode == VTX_MODE_COVERAGE };
     if (n) {
         for (int i = 0; i < 7; ++i)
-            if (want[i]) CK(cudaMemcpyAsync(hbuf[i], src[i], n * esz[i], cudaMemcpyDeviceToHost, ctx->stream));
+            if (want[i] && src[i]) CK(cudaMemcpyAsync(hbuf[i], src[i], n * esz[i], cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }
     out->n = n;
@@ -982,22 +997,27 @@ int vtx_gather(vtx_ctx* ctx, vtx_result* out)
         offs[r] = total; total += counts[size_t(r) * 4];
         met.num_not_cell_bc += counts[size_t(r) * 4 + 1]; met.num_non_umi += counts[size_t(r) * 4 + 2]; met.num_scored += counts[size_t(r) * 4 + 3];
     }
-    const void* src[7];
+    const bool values_only = (ctx->cfg.flags & VTX_F_VALUES_ONLY) != 0;     // then only row / col / val (/ val2) travel
+    const bool want[7] = { true, true, !values_only, !values_only, !values_only, true, !values_only || ctx->cfg.mode == VTX_MODE_COVERAGE };
+    const void* src[7] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
     if (nrk == 1) {
-        for (int i = 0; i < 7; ++i) src[i] = loc[i]->p;
+        for (int i = 0; i < 7; ++i) if (want[i]) src[i] = loc[i]->p;
     } else {
-        for (int i = 0; i < 7; ++i) ENS(ctx->g_dev[i], (total ? total : 1) * esz[i]);
+        for (int i = 0; i < 7; ++i) if (want[i]) ENS(ctx->g_dev[i], (total ? total : 1) * esz[i]);
         NK(g_nccl.GroupStart());
-        for (int i = 0; i < 7; ++i)
+        for (int i = 0; i < 7; ++i) {
+            if (!want[i]) continue;
             for (int r = 0; r < nrk; ++r) {
                 const size_t n = counts[size_t(r) * 4];
                 if (!n) continue;
                 NK(g_nccl.Broadcast(loc[i]->p, static_cast<uint8_t*>(ctx->g_dev[i].p) + offs[r] * esz[i], n * esz[i], kNcclUint8, r,
                                     static_cast<nccl_comm>(ctx->comm), ctx->stream));
             }
+        }
         NK(g_nccl.GroupEnd());
-        for (int i = 0; i < 7; ++i) src[i] = ctx->g_dev[i].p;
+        for (int i = 0; i < 7; ++i) if (want[i]) src[i] = ctx->g_dev[i].p;
     }
+    CK(cudaStreamSynchronize(ctx->stream));
     out->n = total;
     out->row = static_cast<const uint32_t*>(src[0]); out->col = static_cast<const uint32_t*>(src[1]);
     out->ref_cnt = static_cast<const uint32_t*>(src[2]); out->alt_cnt = static_cast<const uint32_t*>(src[3]);

@@ -182,11 +182,14 @@ __global__ void vtx_k_locus_prep(uint32_t n_loci, const uint8_t* __restrict__ ha
 // (d ~ 50 here); keys staged through shared memory in chunks.
 constexpr int kSlotThreads = 128;
 constexpr int kSlotChunk = 1024;
+constexpr uint32_t kSlotSmallMax = 2048;      // deeper loci are enlisted for vtx_k_slots_big
+constexpr int kSlotBigThreads = 1024;
+constexpr int kSlotBigWords = 7;              // scratch words per pair for vtx_k_slots_big
 __global__ void __launch_bounds__(kSlotThreads) vtx_k_slots(
     uint32_t n_loci, const uint32_t* __restrict__ pair_start, const uint32_t* __restrict__ pair_col,
     const uint64_t* __restrict__ pair_umi, int use_umi, uint8_t* __restrict__ pair_first,
     uint32_t* __restrict__ pair_cslot, uint32_t* __restrict__ pair_uslot, uint32_t* __restrict__ cslot_col,
-    uint32_t* __restrict__ cslot_locus, uint32_t* __restrict__ uslot_cslot)
+    uint32_t* __restrict__ cslot_locus, uint32_t* __restrict__ uslot_cslot, uint32_t* __restrict__ big_list /* [0] = count */)
 {
     __shared__ uint32_t s_col[kSlotChunk];
     __shared__ uint64_t s_umi[kSlotChunk];
@@ -194,6 +197,10 @@ __global__ void __launch_bounds__(kSlotThreads) vtx_k_slots(
     for (uint32_t l = blockIdx.x; l < n_loci; l += gridDim.x) {
         const uint32_t ps = pair_start[l], d = pair_start[l + 1] - ps;
         if (d == 0) continue;
+        if (d > kSlotSmallMax) {                  // O(d^2) would be too slow: hand over to the hash + sort kernel
+            if (threadIdx.x == 0) big_list[1 + atomicAdd(big_list, 1u)] = l;
+            continue;
+        }
         // pass 1: is this pair the first occurrence of its cell / of its (cell, umi)?
         for (uint32_t base = 0; base < d; base += kSlotThreads) {
             const uint32_t p = base + threadIdx.x;
@@ -247,6 +254,108 @@ __global__ void __launch_bounds__(kSlotThreads) vtx_k_slots(
                     pair_uslot[ps + p] = ps + us;
                     if (fp & 2) uslot_cslot[ps + us] = ps + cs;
                 }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Deep loci (d > kSlotSmallMax pairs, e.g. a variant in a highly expressed gene): one 1024-thread CTA per
+// locus, O(d log^2 d).  Distinct cells through a hash set in global scratch, sorted with a bitonic network,
+// rank by binary search; (cell, UMI) slots only need to be distinct, so they get dense ids in hash-table order.
+// scratch region of a locus = kSlotBigWords * pair_start[l] words: ctab[2d] | dcols[d] | utab[2d] | uid[2d].
+__device__ __forceinline__ uint32_t mix32(uint32_t x) { x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16; return x; }
+
+__global__ void __launch_bounds__(kSlotBigThreads) vtx_k_slots_big(
+    const uint32_t* __restrict__ big_list, const uint32_t* __restrict__ pair_start, const uint32_t* __restrict__ pair_col,
+    const uint64_t* __restrict__ pair_umi, int use_umi, uint32_t* __restrict__ scratch, uint32_t* __restrict__ pair_cslot,
+    uint32_t* __restrict__ pair_uslot, uint32_t* __restrict__ cslot_col, uint32_t* __restrict__ cslot_locus,
+    uint32_t* __restrict__ uslot_cslot)
+{
+    __shared__ uint32_t s_count;
+    const uint32_t n_big = big_list[0];
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t bi = blockIdx.x; bi < n_big; bi += gridDim.x) {
+        const uint32_t l = big_list[1 + bi];
+        const uint32_t ps = pair_start[l], d = pair_start[l + 1] - ps;
+        const uint32_t cap = 2 * d;
+        uint32_t* ctab = scratch + size_t(kSlotBigWords) * ps;
+        uint32_t* dcols = ctab + cap;
+        uint32_t* utab = dcols + d;
+        uint32_t* uid = utab + cap;
+        for (uint32_t i = tid; i < cap; i += kSlotBigThreads) { ctab[i] = kInvalid; if (use_umi) utab[i] = kInvalid; }
+        if (tid == 0) s_count = 0;
+        __syncthreads();
+        // distinct cells
+        for (uint32_t p = tid; p < d; p += kSlotBigThreads) {
+            const uint32_t col = pair_col[ps + p];
+            uint32_t h = mix32(col) % cap;
+            for (;;) {
+                const uint32_t old = atomicCAS(&ctab[h], kInvalid, col);
+                if (old == kInvalid || old == col) break;
+                h = h + 1 == cap ? 0 : h + 1;
+            }
+        }
+        __syncthreads();
+        for (uint32_t i = tid; i < cap; i += kSlotBigThreads)
+            if (ctab[i] != kInvalid) dcols[atomicAdd(&s_count, 1u)] = ctab[i];
+        __syncthreads();
+        const uint32_t D = s_count;
+        uint32_t P = 1;
+        while (P < D) P <<= 1;                       // P < 2 D <= cap: the hash-set region doubles as the sort buffer
+        __syncthreads();
+        for (uint32_t i = tid; i < P; i += kSlotBigThreads) ctab[i] = i < D ? dcols[i] : kInvalid;
+        __syncthreads();
+        for (uint32_t k = 2; k <= P; k <<= 1)
+            for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                for (uint32_t i = tid; i < P; i += kSlotBigThreads) {
+                    const uint32_t q = i ^ j;
+                    if (q > i) {
+                        const uint32_t a = ctab[i], b = ctab[q];
+                        const bool up = (i & k) == 0;
+                        if ((a > b) == up) { ctab[i] = b; ctab[q] = a; }
+                    }
+                }
+                __syncthreads();
+            }
+        // cell slots: rank among the sorted distinct cells
+        for (uint32_t p = tid; p < d; p += kSlotBigThreads) {
+            const uint32_t col = pair_col[ps + p];
+            uint32_t lo = 0, hi = D;
+            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (ctab[mid] < col) lo = mid + 1; else hi = mid; }
+            pair_cslot[ps + p] = ps + lo;
+            cslot_col[ps + lo] = col;             // every pair of the cell writes the same values
+            cslot_locus[ps + lo] = l;
+        }
+        if (use_umi) {
+            if (tid == 0) s_count = 0;
+            __syncthreads();
+            // claim one table entry per distinct (cell, UMI); the entry remembers its first pair
+            for (uint32_t p = tid; p < d; p += kSlotBigThreads) {
+                const uint32_t col = pair_col[ps + p]; const uint64_t umi = pair_umi[ps + p];
+                uint32_t h = mix32(col ^ mix32(uint32_t(umi) ^ mix32(uint32_t(umi >> 32)))) % cap;
+                for (;;) {
+                    uint32_t cur = utab[h];
+                    if (cur == kInvalid) { cur = atomicCAS(&utab[h], kInvalid, p); if (cur == kInvalid) break; }
+                    if (pair_col[ps + cur] == col && pair_umi[ps + cur] == umi) break;
+                    h = h + 1 == cap ? 0 : h + 1;
+                }
+            }
+            __syncthreads();
+            for (uint32_t i = tid; i < cap; i += kSlotBigThreads)
+                if (utab[i] != kInvalid) uid[i] = atomicAdd(&s_count, 1u);
+            __syncthreads();
+            for (uint32_t p = tid; p < d; p += kSlotBigThreads) {
+                const uint32_t col = pair_col[ps + p]; const uint64_t umi = pair_umi[ps + p];
+                uint32_t h = mix32(col ^ mix32(uint32_t(umi) ^ mix32(uint32_t(umi >> 32)))) % cap;
+                for (;;) {
+                    const uint32_t cur = utab[h];
+                    if (pair_col[ps + cur] == col && pair_umi[ps + cur] == umi) break;
+                    h = h + 1 == cap ? 0 : h + 1;
+                }
+                const uint32_t us = ps + uid[h];
+                pair_uslot[ps + p] = us;
+                uslot_cslot[us] = pair_cslot[ps + p];
             }
         }
         __syncthreads();
