@@ -206,6 +206,11 @@ def run_gpu(args):
     rank, world, local = dist_env()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: vartrix_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    # stdout carries exactly one JSON line: anything native libraries print there (e.g. NCCL's version banner)
+    # goes to stderr instead
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -364,8 +369,10 @@ def run_gpu(args):
     eng.close()
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
     if line:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     return 0
 
 
