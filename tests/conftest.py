@@ -14,6 +14,12 @@ REF_TEST_DIR = "/root/reference/test"       # present only in the build containe
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
+    # the engine library, the CLI and the oracle are built in-tree; build them if a fresh checkout has none
+    import subprocess
+    need = [os.path.join(ROOT, "vartrix_b200", "lib", "libvartrix_b200.so"), os.path.join(ROOT, "vartrix_b200", "bin", "vartrix_b200"),
+            os.path.join(ROOT, "oracle", "libvtx_oracle.so")]
+    if not all(os.path.exists(p) for p in need):
+        subprocess.run(["make", "-s", "-C", ROOT, "all"], check=True)
 
 
 def _has_gpu():
