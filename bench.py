@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--chunks", type=int, default=8, help="staged shards per step on the e2e path (copy/compute overlap)")
+    ap.add_argument("--first-chunk", type=float, default=0.02, help="fraction of the candidates in the first (priming) shard")
     return ap.parse_args()
 
 
@@ -75,7 +76,7 @@ def describe(args, cfg, world, info):
         "candidates_per_gpu": info["n_cand"], "scoring_method": cfg["scoring_method"], "umi": bool(cfg.get("umi")),
         "parallelism": f"loci sharded over {world} GPU(s), one allgatherv of triplets" if world > 1 else "1 GPU",
         "l2_policy": "inputs larger than L2 (staged shard >> 126 MB), no explicit flush",
-        "e2e_chunks": args.chunks,
+        "e2e_chunks": args.chunks, "e2e_first_chunk_frac": args.first_chunk,
     }
 
 
@@ -241,7 +242,9 @@ def run_gpu(args):
     # double-buffers them so the copy of shard k+1 overlaps the kernels of shard k
     del pinned
     hparts, hkeep, h2d_bytes = [], [], 0
-    for lo, hi in vb.shard_bounds(sb.cand_start, max(1, args.chunks)):
+    for lo, hi in vb.shard_bounds(sb.cand_start, max(1, args.chunks), first_frac=args.first_chunk):
+        if hi <= lo:
+            continue
         part = sb.shard(lo, hi)
         cb = part.to_c()
         for f in vb.StagedBatch.FIELDS:

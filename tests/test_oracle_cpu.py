@@ -147,3 +147,15 @@ def test_synth_shapes_and_shard_invariance(oracle):
     for f in ("row", "col", "val", "val2"):
         assert np.array_equal(np.concatenate([getattr(p, f) for p in parts]), getattr(whole, f)), f
     assert vb.shard_bounds(sb.cand_start, 3)[0][0] == 0 and vb.shard_bounds(sb.cand_start, 3)[-1][1] == 30
+
+
+def test_band_model_equals_full_on_synthetic_shards(oracle):
+    """on the synthetic workloads (random context, SNVs and <= 30 bp indels) the best-effort model of
+    rust-bio's k=6 / w=20 band never clips the optimal path, so full-matrix scores are the banded scores."""
+    import vartrix_b200 as vb
+    for kind in ("snv", "indel"):
+        sb, bcs, _ = vb.synth.make_shard(24, 30, depth=20, seed=31, kind=kind)
+        ob = to_oracle_batch(oracle, sb); obc = oracle.Barcodes(bcs.keys)
+        full = oracle.run_batch(ob, obc, oracle.MODE_COVERAGE, False, n_threads=4)
+        band = oracle.run_batch(ob, obc, oracle.MODE_COVERAGE, False, n_threads=4, band_model=True)
+        assert np.array_equal(full.val, band.val) and np.array_equal(full.val2, band.val2) and np.array_equal(full.unk_cnt, band.unk_cnt), kind

@@ -309,13 +309,18 @@ def pack_umi(s: bytes) -> int:
     return int(_capi.load().vtx_pack_umi(s, len(s)))
 
 
-def shard_bounds(cand_start: np.ndarray, n_shards: int):
-    """Contiguous locus ranges balanced by candidate count: -> list of (lo, hi)."""
+def shard_bounds(cand_start: np.ndarray, n_shards: int, first_frac: float = 0.0):
+    """Contiguous locus ranges balanced by candidate count: -> list of (lo, hi).
+    first_frac > 0 makes the first shard that small a fraction of the candidates (a staging producer primes the
+    copy/compute pipeline with a small shard so the kernels start early) and balances the rest."""
     n_loci = len(cand_start) - 1
     total = int(cand_start[-1])
     cuts = [0]
     for s in range(1, n_shards):
-        target = total * s // n_shards
+        if first_frac > 0 and n_shards > 1:
+            target = int(total * (first_frac + (1.0 - first_frac) * (s - 1) / (n_shards - 1)))
+        else:
+            target = total * s // n_shards
         cuts.append(int(np.searchsorted(cand_start, target, side="left")))
     cuts.append(n_loci)
     cuts = [min(max(c, 0), n_loci) for c in cuts]
