@@ -249,3 +249,48 @@ def test_full_size_config2_properties(vb, oracle):
     exp = _oracle_run(oracle, win, bcs, "coverage", False)
     sel = (a.row >= 5000) & (a.row < 5400)
     assert np.array_equal(a.col[sel], exp.col) and np.array_equal(a.alt_cnt[sel], exp.alt_cnt) and np.array_equal(a.ref_cnt[sel], exp.ref_cnt)
+
+
+def test_api_rejects_malformed_input_with_messages(vb):
+    """Error behaviour across the boundary: negative code + message, never a crash or a silent wrong answer."""
+    import ctypes as C
+    from vartrix_b200 import _capi
+    sb, bcs, _ = vb.synth.make_shard(6, 5, depth=4, seed=1)
+    with vb.Engine("coverage") as eng:
+        with pytest.raises(vb.VtxError, match="vtx_set_barcodes must be called"):
+            eng.submit(sb)
+        with pytest.raises(vb.VtxError, match="duplicate barcode"):
+            eng.set_barcodes(vb.Barcodes([b"AAA-1", b"CCC-1", b"AAA-1"]))
+        eng.set_barcodes(bcs)
+        bad = sb.shard(0, 6); bad.cand_read[3] = 10_000
+        with pytest.raises(vb.VtxError, match="cand_read out of range"):
+            eng.submit(bad)
+        bad = sb.shard(0, 6); bad.ref_off[2] += 4
+        with pytest.raises(vb.VtxError, match="multiples of 16"):
+            eng.submit(bad)
+        bad = sb.shard(0, 6); bad.locus_row[3] = bad.locus_row[2]
+        with pytest.raises(vb.VtxError, match="strictly ascending"):
+            eng.submit(bad)
+        bad = sb.shard(0, 6); bad.read_umi_key[0] = 1 << 63
+        with pytest.raises(vb.VtxError, match="UMI key"):
+            eng.submit(bad)
+        bad = sb.shard(0, 6); bad.cand_start[-1] += 1
+        with pytest.raises(vb.VtxError, match="cand_start"):
+            eng.submit(bad)
+        assert len(eng.run(sb).row) > 0                      # the context survives rejected submits
+    cfg = _capi.Config(device=0, mode=0, use_umi=0, match=2, mismatch=-5, gap_open=-5, gap_extend=-1, min_score=25, stream=None, flags=0)
+    h = C.c_void_p()
+    L = _capi.load()
+    assert L.vtx_create(C.byref(cfg), C.byref(h)) == -4 and b"compiled in" in L.vtx_last_error(None)
+    cfg.match = 1; cfg.device = 99
+    assert L.vtx_create(C.byref(cfg), C.byref(h)) == -1 and b"out of range" in L.vtx_last_error(None)
+
+
+def test_values_only_fetch_and_raw_score_side_channel(vb, oracle):
+    sb, bcs, info = vb.synth.make_shard(40, 20, depth=10, seed=4)
+    exp = _oracle_run(oracle, sb, bcs, "coverage", False)
+    with vb.Engine("coverage", values_only=True) as eng:
+        eng.set_barcodes(bcs)
+        got = eng.run(sb)
+    assert np.array_equal(got.row, exp.row) and np.array_equal(got.col, exp.col)
+    assert np.array_equal(got.val, exp.val) and np.array_equal(got.val2, exp.val2) and got.ref_cnt.size == 0

@@ -13,6 +13,7 @@
 #include <mutex>
 #include <set>
 #include <sys/stat.h>
+#include <chrono>
 #include <thread>
 
 #include "stager.hpp"
@@ -31,6 +32,12 @@ void logf(int level, const char* tag, const char* fmt, ...)
 }
 #define LOG_ERR(...) logf(0, "ERROR", __VA_ARGS__)
 #define LOG_INFO(...) logf(1, "INFO", __VA_ARGS__)
+
+double now_s()
+{
+    static const auto t0 = std::chrono::steady_clock::now();
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
 
 bool exists(const std::string& p) { struct stat st; return stat(p.c_str(), &st) == 0; }
 
@@ -202,6 +209,7 @@ int main(int argc, char** argv)
     if (!read_vcf(o.vcf, &recs, &err)) { printf("Vartrix error.\nError: %s\n", err.c_str()); return 1; }
     if (recs.empty()) LOG_ERR("Warning! Zero variants found in input VCF. Output matrices will be by definition empty but will still be generated.");
     LOG_INFO("Initialized a %zu variants x %zu cell barcodes matrix", recs.size(), bcs.keys.size());
+    LOG_INFO("[%.3f s] inputs parsed", now_s());
 
     // validate_inputs (main.rs:545-594): contigs present in FASTA and BAM, record end inside the contig
     Fasta fa0;
@@ -273,6 +281,7 @@ int main(int argc, char** argv)
         if (vtx_create(&cfg, &ctx) != VTX_OK) { printf("Vartrix error.\nError: %s\n", vtx_last_error(nullptr)); return 1; }
         if (vtx_set_barcodes(ctx, bcs.bytes.data(), bcs.off.data(), uint32_t(bcs.keys.size())) != VTX_OK) { printf("Vartrix error.\nError: %s\n", vtx_last_error(ctx)); return 1; }
     }
+    LOG_INFO("[%.3f s] engine ready, staging on %ld thread(s)", now_s(), o.threads);
     int rc = 0;
     for (size_t k = 0; k < n_shards && rc == 0; ++k) {
         std::unique_ptr<StagedShard> sh;
@@ -302,9 +311,11 @@ int main(int argc, char** argv)
     if (dump) { fclose(dump); return rc; }
     if (rc) { vtx_destroy(ctx); return rc; }
 
+    LOG_INFO("[%.3f s] all shards staged and submitted", now_s());
     vtx_result res{};
     if (vtx_finish(ctx, &res) != VTX_OK) { printf("Vartrix error.\nError: %s\n", vtx_last_error(ctx)); vtx_destroy(ctx); return 1; }
 
+    LOG_INFO("[%.3f s] triplets on the host", now_s());
     // metrics (main.rs:350-379)
     LOG_INFO("Number of alignments evaluated: %llu", (unsigned long long)hm.num_reads);
     LOG_INFO("Number of alignments skipped due to low mapping quality: %llu", (unsigned long long)hm.num_low_mapq);
@@ -333,6 +344,7 @@ int main(int argc, char** argv)
         if (!f) { LOG_ERR("error writing barcodes file"); rc = 1; }
         else { for (const std::string& k : bcs.keys) { fwrite(k.data(), 1, k.size(), f); fputc('\n', f); } fclose(f); }
     }
+    LOG_INFO("[%.3f s] outputs written", now_s());
     double sum = 0;
     for (uint64_t k = 0; k < res.n; ++k) sum += res.val[k];
     if (sum == 0.0) LOG_ERR("The resulting matrix has a sum of 0. Did you use the --umi flag on data without UMIs?");   // main.rs:410-415
