@@ -36,7 +36,7 @@ def main():
             dt = time.time() - t0
             scored = [ln for ln in p.stderr.splitlines() if "pairs scored on the GPU" in ln]
             n = int(scored[0].rsplit(" ", 1)[1]) if scored else 0
-            phases = [ln.split("] ", 2)[-1] for ln in p.stderr.splitlines() if "[INFO] [" in ln]
+            phases = [ln.split("] ", 1)[1] for ln in p.stderr.splitlines() if "[INFO] [" in ln]
             out.append(dict(threads=th, shard_loci=shard, wall_s=round(dt, 3), pairs=n, pairs_per_s=round(n / dt) if dt else 0, rc=p.returncode,
                             phases=phases))
     print(json.dumps(dict(reads=ds["n_reads"], loci=a.loci, bam_bytes=os.path.getsize(ds["bam"]), gen_s=round(gen_s, 1), runs=out), indent=1))

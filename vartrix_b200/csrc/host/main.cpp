@@ -14,6 +14,7 @@
 #include <set>
 #include <sys/stat.h>
 #include <chrono>
+#include <future>
 #include <thread>
 
 #include "stager.hpp"
@@ -205,6 +206,24 @@ int main(int argc, char** argv)
     if (!load_barcodes(o.barcodes, &bcs, &err)) { LOG_ERR("%s", err.c_str()); return 1; }
     LOG_INFO("Loaded %zu barcodes", bcs.keys.size());
 
+    // CUDA context creation takes ~1 s: start it now, in the background, while the VCF is parsed and the first
+    // shards are staged
+    vtx_ctx* ctx = nullptr;
+    std::string engine_err;
+    std::future<int> engine_ready;
+    if (o.dump_staged.empty()) {
+        engine_ready = std::async(std::launch::async, [&]() -> int {
+            vtx_config cfg{};
+            cfg.device = int(o.device);
+            cfg.mode = o.scoring == "consensus" ? VTX_MODE_CONSENSUS : o.scoring == "coverage" ? VTX_MODE_COVERAGE : VTX_MODE_ALT_FRAC;
+            cfg.flags = VTX_F_VALUES_ONLY;       // the writers need row, col and the matrix values only
+            cfg.use_umi = o.umi; cfg.match = 1; cfg.mismatch = -5; cfg.gap_open = -5; cfg.gap_extend = -1; cfg.min_score = 25;
+            if (vtx_create(&cfg, &ctx) != VTX_OK) { engine_err = vtx_last_error(nullptr); return 1; }
+            if (vtx_set_barcodes(ctx, bcs.bytes.data(), bcs.off.data(), uint32_t(bcs.keys.size())) != VTX_OK) { engine_err = vtx_last_error(ctx); return 1; }
+            return 0;
+        });
+    }
+
     std::vector<VcfRecord> recs;
     if (!read_vcf(o.vcf, &recs, &err)) { printf("Vartrix error.\nError: %s\n", err.c_str()); return 1; }
     if (recs.empty()) LOG_ERR("Warning! Zero variants found in input VCF. Output matrices will be by definition empty but will still be generated.");
@@ -264,7 +283,6 @@ int main(int argc, char** argv)
     for (long t = 0; t < o.threads; ++t) pool.emplace_back(worker);
 
     HostMetrics hm;
-    vtx_ctx* ctx = nullptr;
     FILE* dump = nullptr;
     Arena arenas[3];
     if (!o.dump_staged.empty()) {
@@ -272,14 +290,12 @@ int main(int argc, char** argv)
         if (!dump) { LOG_ERR("cannot write %s", o.dump_staged.c_str()); return 1; }
         uint64_t hdr[2] = { recs.size(), bcs.keys.size() };
         fwrite(hdr, 8, 2, dump);
-    } else {
-        vtx_config cfg{};
-        cfg.device = int(o.device);
-        cfg.mode = o.scoring == "consensus" ? VTX_MODE_CONSENSUS : o.scoring == "coverage" ? VTX_MODE_COVERAGE : VTX_MODE_ALT_FRAC;
-        cfg.flags = VTX_F_VALUES_ONLY;       // the writers need row, col and the matrix values only
-        cfg.use_umi = o.umi; cfg.match = 1; cfg.mismatch = -5; cfg.gap_open = -5; cfg.gap_extend = -1; cfg.min_score = 25;
-        if (vtx_create(&cfg, &ctx) != VTX_OK) { printf("Vartrix error.\nError: %s\n", vtx_last_error(nullptr)); return 1; }
-        if (vtx_set_barcodes(ctx, bcs.bytes.data(), bcs.off.data(), uint32_t(bcs.keys.size())) != VTX_OK) { printf("Vartrix error.\nError: %s\n", vtx_last_error(ctx)); return 1; }
+    } else if (engine_ready.get() != 0) {
+        printf("Vartrix error.\nError: %s\n", engine_err.c_str());
+        { std::lock_guard<std::mutex> g(mu); failed = true; }
+        cv.notify_all();
+        for (auto& t : pool) t.join();
+        return 1;
     }
     LOG_INFO("[%.3f s] engine ready, staging on %ld thread(s)", now_s(), o.threads);
     int rc = 0;

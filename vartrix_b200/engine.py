@@ -144,8 +144,8 @@ class StagedBatch:
                     w[:int(ln)] = self.hap_bytes[int(off): int(off + ln)]; pieces.append(w); pos += w.size
             hap = np.concatenate(pieces) if pieces else np.zeros(0, np.uint8)
         return StagedBatch(
-            locus_row=self.locus_row[lo:hi], hap_bytes=hap, ref_off=n_ro, ref_len=self.ref_len[lo:hi],
-            alt_off=n_ra, alt_len=self.alt_len[lo:hi], cand_start=(cs[lo:hi + 1] - cs[lo]), read_nib=nib,
+            locus_row=self.locus_row[lo:hi].copy(), hap_bytes=hap, ref_off=n_ro, ref_len=self.ref_len[lo:hi].copy(),
+            alt_off=n_ra, alt_len=self.alt_len[lo:hi].copy(), cand_start=(cs[lo:hi + 1] - cs[lo]), read_nib=nib,
             read_off=new_off, read_len=rl, cb_bytes=cb, read_cb_off=new_cbo, read_cb_len=self.read_cb_len[used],
             read_umi_key=self.read_umi_key[used], cand_read=inv.astype(np.uint32), n_rows=self.n_rows)
 
