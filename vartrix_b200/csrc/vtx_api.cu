@@ -210,11 +210,9 @@ int run_sw(vtx_ctx* ctx, const DevBatch& b, uint32_t n_pairs_ub, const uint32_t*
         nl, b.hap, b.ref_off, b.ref_len, b.alt_off, b.alt_len, P<uint32_t>(ctx->pair_start), force_slow, allow_split,
         P<uint32_t>(ctx->tcount));
     ++*launches;
-    for (int c = 0; c < kNumClasses; ++c) {
-        int rc = scan_u32(ctx, P<uint32_t>(ctx->tcount) + size_t(c) * (nl + 1), nl,
-                          P<uint32_t>(ctx->tstart) + size_t(c) * (nl + 1), launches);
-        if (rc) return rc;
-    }
+    vtx_k_scan_rows<<<kNumClasses, kScanThreads, 0, ctx->stream>>>(P<uint32_t>(ctx->tcount), P<uint32_t>(ctx->tstart), nl, nl + 1);
+    ++*launches;
+    CK(cudaGetLastError());
     CK(cudaMemsetAsync(ctx->tile_counters.p, 0, 64, ctx->stream));
     if (tr) CK(cudaEventRecord(tr->ev[EV_PREP], ctx->stream));
 

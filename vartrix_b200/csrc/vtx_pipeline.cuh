@@ -489,6 +489,27 @@ __global__ void __launch_bounds__(kScanThreads) vtx_k_scan_sums(uint32_t* __rest
     if (threadIdx.x == 0) *total_out = carry;
 }
 
+// one CTA per row: exclusive scan of `rows` short arrays (the per-class tile counts) in a single launch
+__global__ void __launch_bounds__(kScanThreads) vtx_k_scan_rows(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
+                                                                uint32_t n, uint32_t stride)
+{
+    const uint32_t* src = in + size_t(blockIdx.x) * stride;
+    uint32_t* dst = out + size_t(blockIdx.x) * stride;
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < n; base += kScanTile) {
+        const uint32_t i0 = base + threadIdx.x * kScanItems;
+        uint32_t v[kScanItems], sum = 0;
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) { v[k] = (i0 + k < n) ? src[i0 + k] : 0; sum += v[k]; }
+        uint32_t total;
+        uint32_t p = carry + block_exclusive_scan(sum, &total);
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) { if (i0 + k < n) dst[i0 + k] = p; p += v[k]; }
+        carry += total;
+    }
+    if (threadIdx.x == 0) dst[n] = carry;
+}
+
 __global__ void __launch_bounds__(kScanThreads) vtx_k_scan_add(uint32_t* __restrict__ out, uint64_t n,
                                                                const uint32_t* __restrict__ sums)
 {
