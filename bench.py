@@ -340,13 +340,14 @@ def run_gpu(args):
         sw_avg_ms = float(np.mean(sw_ms))
         achieved = n_pairs * b_alg / (sw_avg_ms / 1e3) / 1e9
         cells = info["read_len"] * 2 * (2 * 100 + 1)
-        # the bound that actually binds: DPX-class instructions issue at 2 warp-instr/cycle/SM (profiles/r01_dpx_microbench.txt);
-        # two-phase SNV tile = 8 pairs: (m+7) steps x 12 cols + (m+3) steps x 27 cols, 5.5 DPX per cell
+        # the bound that actually binds: the ALU pipe.  DPX s16x2 instructions occupy it for 2 cycles per warp and SMSP,
+        # 32-bit VIADD for 1 (profiles/r01_dpx_microbench.txt).  SASS of the two-phase SNV tile (8 pairs): a phase-1
+        # warp-step (12 columns) = 54 DPX + 12 adds, a phase-2 warp-step (27 columns) = 122 DPX + 28 VIADD.
         m = info["read_len"]
-        dpx_per_pair = ((m + 7) * 12 + (m + 3) * 27) * 5.5 / 8.0
+        alu_cycles_per_pair = ((m + 7) * (54 * 2 + 12) + (m + 3) * (122 * 2 + 28)) / 8.0
         sm_mhz = (clocks or {}).get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
-        dpx_peak = torch.cuda.get_device_properties(local).multi_processor_count * 2.0 * sm_mhz * 1e6
-        dpx_ach = n_pairs * dpx_per_pair / (sw_avg_ms / 1e3)
+        dpx_peak = torch.cuda.get_device_properties(local).multi_processor_count * 4.0 * sm_mhz * 1e6
+        dpx_ach = n_pairs * alu_cycles_per_pair / (sw_avg_ms / 1e3)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -360,9 +361,9 @@ def run_gpu(args):
                          "peak_source": peak_src, "kernel": tj_kernel,
                          "kernel_ms": sw_avg_ms, "algorithmic_bytes_per_pair": b_alg, "pairs_per_launch": n_pairs,
                          "gcups": n_pairs * cells / (sw_avg_ms / 1e3) / 1e9,
-                         "issue_bound": {"what": "DPX s16x2 warp-instructions/s of the two-phase SW kernel (model: %.0f per pair)" % dpx_per_pair,
+                         "issue_bound": {"what": "ALU-pipe busy cycles/s of the two-phase SW kernel (SASS model: %.0f SMSP-cycles per pair)" % alu_cycles_per_pair,
                                          "achieved": dpx_ach, "peak": dpx_peak, "frac": dpx_ach / dpx_peak,
-                                         "peak_source": "n_SM x 2 per cycle (measured, profiles/r01_dpx_microbench.txt) x sampled SM clock"},
+                                         "peak_source": "n_SM x 4 SMSPs x sampled SM clock; DPX = 2 cycles, VIADD = 1 (measured, profiles/r01_dpx_microbench.txt)"},
                          "note": "integer DP: ~540 cell updates per algorithmic byte, so the kernel is DPX-issue bound, not HBM "
                                  "bound (DESIGN.md); gcups = DP cell updates/s of the SW kernel alone"},
             "clocks": clocks,

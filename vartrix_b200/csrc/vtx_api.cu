@@ -226,6 +226,7 @@ int run_sw(vtx_ctx* ctx, const DevBatch& b, uint32_t n_pairs_ub, const uint32_t*
     mcap = std::max(2, (mcap + 1) & ~1);
     a.mcap = mcap;
     a.k64k = 65536u;
+    a.one = 1u;
     a.max_hap = b.max_hap_len;
 
     uint64_t before = *launches;

@@ -34,9 +34,39 @@ __host__ __device__ constexpr uint32_t pack2(int lo, int hi)
 {
     return (uint32_t(uint16_t(int16_t(hi))) << 16) | uint32_t(uint16_t(int16_t(lo)));
 }
+// Every packed quantity (H, H+gap, E, F, running maximum) is stored with a bias of kBias in both halves.  Max and
+// fused add-max instructions are oblivious to a common bias, and it makes plain 32-bit adds of packed words exact:
+// adding a small positive pair never carries out of the low half, and adding (gap, gap) with gap < 0 to halves that
+// are >= kBias always carries exactly once, which the constant kGoeAdd already contains.  So the two packed adds of
+// a cell are ordinary integer adds (VIADD at full rate or IMAD.IADD on the FMA pipe) instead of half-rate VIADD.16x2.
+constexpr int kBias = 16384;
 constexpr uint32_t kGE2 = pack2(kGapExtend, kGapExtend);
-constexpr uint32_t kGOE2 = pack2(kGoe, kGoe);
-constexpr uint32_t kNEG2 = pack2(-16384, -16384);
+constexpr uint32_t kBIAS2 = pack2(kBias, kBias);                    // biased 0 (the floor of local alignment)
+constexpr uint32_t kGOE2 = pack2(kBias + kGoe, kBias + kGoe);       // biased (0 + gap): H = 0 seen through H + go + ge
+constexpr uint32_t kNEG2 = pack2(0, 0);                             // biased -16384 ("minus infinity")
+constexpr uint32_t kGoeAdd = (uint32_t(uint16_t(int16_t(kGoe - 1))) << 16) | uint32_t(uint16_t(int16_t(kGoe)));   // + (gap, gap) incl. the carry
+// measured (profiles/r01_add_variants.txt): letting ptxas split the packed adds between VIADD (ALU) and IMAD.IADD
+// (FMA) and chaining E through H + goe beats forcing full IMADs (those run on the half-width "FMA heavy" pipe)
+#ifndef VTX_SW_PADD
+#define VTX_SW_PADD 1        // 0: force IMAD (x * one + c); 1: plain add, ptxas balances VIADD / IMAD.IADD; 2: mad.lo with literal 1
+#endif
+#ifndef VTX_SW_EG
+#define VTX_SW_EG 0          // 1: E chain through tf + goe (one instruction per cell, one more add); 0: through H + goe
+#endif
+__device__ __forceinline__ uint32_t padd(uint32_t x, uint32_t one, uint32_t c)
+{
+#if VTX_SW_PADD == 0
+    return x * one + c;
+#elif VTX_SW_PADD == 2
+    (void)one;
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, 1, %2;" : "=r"(d) : "r"(x), "r"(c));
+    return d;
+#else
+    (void)one;
+    return x + c;
+#endif
+}
 // profile entries are biased by -kGoe because the stored state is H + kGoe
 constexpr int kProfMatch = kMatch - kGoe, kProfMis = kMismatch - kGoe;     // 7, 1
 
@@ -47,9 +77,6 @@ constexpr int kNumSplitClasses = 2;                // 5, 6: two-phase kernels (v
 constexpr int kSplitClass0 = kSlowClass + 1;
 constexpr int kNumClasses = kSplitClass0 + kNumSplitClasses;
 constexpr int kTileChunk = 8;            // most tiles grabbed per atomic
-#ifndef VTX_SW_CHAIN
-#define VTX_SW_CHAIN 1                   // 1: keep max(diag + s, F, 0) off the E -> H -> H+gap dependency chain
-#endif
 
 // fast tile classes: lanes per pair, columns per lane, storage stride (words; CS % 4 == 0, (CS/4) odd
 // so the 8 lanes of an LDS.128 wavefront hit 8 distinct 16-byte bank groups)
@@ -84,6 +111,7 @@ struct SwArgs {
     int32_t min_score;              // MIN_SCORE main.rs:30
     int32_t mcap;                   // row-code capacity (even, >= longest read in the batch)
     uint32_t k64k;                  // 65536 as a run-time value (keeps a shift-add on the FMA pipe, see vtx_sw_split.cuh)
+    uint32_t one;                   // 1 as a run-time value (keeps the packed adds on the FMA pipe)
     // generic kernel only
     uint32_t* scratch;              // [warps][max_hap + 1][32]
     uint32_t max_hap;
@@ -113,7 +141,7 @@ __device__ __forceinline__ uint32_t upper_locus(const uint32_t* __restrict__ a, 
 __device__ __forceinline__ void call_and_scatter(const SwArgs& a, uint32_t pair, uint32_t packed)
 {
     const int ref_score = int(int16_t(packed & 0xFFFF)), alt_score = int(int16_t(packed >> 16));
-    if (a.pair_scores) a.pair_scores[pair] = packed;
+    if (a.pair_scores) a.pair_scores[pair] = pack2(ref_score, alt_score);
     if (!a.pair_slot) return;
     if (ref_score < a.min_score && alt_score < a.min_score) return;            // None
     const uint32_t k = ref_score > alt_score ? 0u : (alt_score > ref_score ? 1u : 2u);
@@ -207,10 +235,11 @@ __global__ void __launch_bounds__(TileClass<CLS>::THREADS, TileClass<CLS>::MINB)
             uint32_t hg[C], f[C];
 #pragma unroll
             for (int c = 0; c < C; ++c) { hg[c] = kGOE2; f[c] = kNEG2; }
-            uint32_t hg_last = kGOE2, e_last = kNEG2, diag_save = kGOE2, best = 0;
+            uint32_t hg_last = kGOE2, e_last = kNEG2, diag_save = kGOE2, best = kBIAS2;
             const uint8_t* lane_prof = reinterpret_cast<const uint8_t*>(prof) + g * CS * 4;
             const uint16_t* my_codes = codes + M - g;
             const int steps = mmax + LPP - 1;
+            const uint32_t one = a.one;
             for (int t = 0; t < steps; ++t) {
                 uint32_t hl = __shfl_up_sync(0xffffffffu, hg_last, 1, LPP);
                 uint32_t el = __shfl_up_sync(0xffffffffu, e_last, 1, LPP);
@@ -218,7 +247,9 @@ __global__ void __launch_bounds__(TileClass<CLS>::THREADS, TileClass<CLS>::MINB)
                 const uint4* prow = reinterpret_cast<const uint4*>(lane_prof + my_codes[t]);
                 uint32_t diag = diag_save;
                 diag_save = hl;
-                uint32_t e = el, hleft = hl;
+                // E[i][c] = max(E[i][c-1] + ge, H[i][c-1] + goe) = max(E[i][c-1] + ge, tf[i][c-1] + goe): `eg` carries
+                // the second operand, so the E chain is one instruction per cell
+                uint32_t e = el, eg = hl, hleft = hl;
 #pragma unroll
                 for (int q = 0; q < (C + 3) / 4; ++q) {
                     const uint4 s4 = prow[q];
@@ -229,22 +260,23 @@ __global__ void __launch_bounds__(TileClass<CLS>::THREADS, TileClass<CLS>::MINB)
                         const int c = 4 * q + k;
                         if (c < C) {
                             const uint32_t fc = __viaddmax_s16x2(f[c], kGE2, hg[c]);     // F[i][c]
-#if VTX_SW_CHAIN
-                            const uint32_t tf = __viaddmax_s16x2_relu(diag, sv[k], fc); // max(H[i-1][c-1] + s, F, 0): off the chain
-                            e = __viaddmax_s16x2(e, kGE2, hleft);                       // E[i][c]
-                            const uint32_t h = __vmaxs2(tf, e);                         // H[i][c]
-#else
-                            e = __viaddmax_s16x2(e, kGE2, hleft);                       // E[i][c]
-                            const uint32_t tt = __vadd2(diag, sv[k]);                   // H[i-1][c-1] + s
-                            const uint32_t h = __vimax3_s16x2_relu(tt, e, fc);          // H[i][c]
+                            const uint32_t tt = padd(diag, one, sv[k]);                 // H[i-1][c-1] + s      (IMAD)
+                            const uint32_t tf = __vimax3_s16x2(tt, fc, kBIAS2);         // max(H[i-1][c-1] + s, F, 0)
+                            e = __viaddmax_s16x2(e, kGE2, eg);                          // E[i][c]
+#if VTX_SW_EG
+                            eg = padd(tf, one, kGoeAdd);                                // tf + goe             (IMAD)
 #endif
+                            const uint32_t h = __vmaxs2(tf, e);                         // H[i][c]
                             hh[k] = h;
                             diag = hg[c];
-                            hleft = __vadd2(h, kGOE2);
+                            hleft = padd(h, one, kGoeAdd);                              // H + goe              (IMAD)
+#if !VTX_SW_EG
+                            eg = hleft;
+#endif
                             hg[c] = hleft;
                             f[c] = fc;
                         } else {
-                            hh[k] = 0;
+                            hh[k] = kBIAS2;
                         }
                     }
                     best = __vimax3_s16x2(best, hh[0], hh[1]);
@@ -256,7 +288,7 @@ __global__ void __launch_bounds__(TileClass<CLS>::THREADS, TileClass<CLS>::MINB)
             // ---- epilogue: group maximum, call, atomic scatter ----
 #pragma unroll
             for (int o = LPP / 2; o >= 1; o >>= 1) best = __vmaxs2(best, __shfl_xor_sync(0xffffffffu, best, o));
-            if (active && g == 0) call_and_scatter(a, pair, best);
+            if (active && g == 0) call_and_scatter(a, pair, best - kBIAS2);           // un-bias both halves (no borrow: halves >= kBias)
         }
     }
 }

@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(SplitClass<SCLS>::THREADS, SplitClass<SCLS>::M
     // small so that every warp still gets >= ~16 grabs (tail balance)
     const uint32_t tile_chunk = max(1u, min(uint32_t(kTileChunk), n_tiles / (gridDim.x * (blockDim.x >> 5) * 16u)));
     const uint32_t k64k = a.k64k;                                // 65536, opaque to ptxas so the merge stays an IMAD
+    const uint32_t one = a.one;                                  // 1, likewise: packed adds as IMAD on the FMA pipe
 
     for (;;) {
         uint32_t chunk = 0;
@@ -159,7 +160,7 @@ __global__ void __launch_bounds__(SplitClass<SCLS>::THREADS, SplitClass<SCLS>::M
                 uint32_t hg[C1], f[C1];
 #pragma unroll
                 for (int c = 0; c < C1; ++c) { hg[c] = kGOE2; f[c] = kNEG2; }
-                uint32_t hg_last = kGOE2, e_last = kNEG2, diag_save = kGOE2, best = 0;
+                uint32_t hg_last = kGOE2, e_last = kNEG2, diag_save = kGOE2, best = kBIAS2;
                 const uint8_t* cA = codes + (2 * u) * code_stride + M - g;
                 const uint8_t* cB = codes + (2 * u + 1) * code_stride + M - g;
                 const uint32_t* lane_prof = prof1 + g * C1;
@@ -173,7 +174,7 @@ __global__ void __launch_bounds__(SplitClass<SCLS>::THREADS, SplitClass<SCLS>::M
                     const uint4* pb = reinterpret_cast<const uint4*>(lane_prof + uint32_t(cB[t]) * RS1);
                     uint32_t diag = diag_save;
                     diag_save = hl;
-                    uint32_t e = el, hleft = hl;
+                    uint32_t e = el, eg = hl, hleft = hl;
 #pragma unroll
                     for (int q = 0; q < C1 / 4; ++q) {
                         const uint4 a4 = pa[q], b4 = pb[q];
@@ -184,12 +185,18 @@ __global__ void __launch_bounds__(SplitClass<SCLS>::THREADS, SplitClass<SCLS>::M
                         for (int k = 0; k < 4; ++k) {
                             const int c = 4 * q + k;
                             const uint32_t fc = __viaddmax_s16x2(f[c], kGE2, hg[c]);
-                            const uint32_t tf = __viaddmax_s16x2_relu(diag, sv[k], fc);
-                            e = __viaddmax_s16x2(e, kGE2, hleft);
+                            const uint32_t tf = __vimax3_s16x2(padd(diag, one, sv[k]), fc, kBIAS2);
+                            e = __viaddmax_s16x2(e, kGE2, eg);
+#if VTX_SW_EG
+                            eg = padd(tf, one, kGoeAdd);
+#endif
                             const uint32_t h = __vmaxs2(tf, e);
                             hh[k] = h;
                             diag = hg[c];
-                            hleft = __vadd2(h, kGOE2);
+                            hleft = padd(h, one, kGoeAdd);
+#if !VTX_SW_EG
+                            eg = hleft;
+#endif
                             hg[c] = hleft;
                             f[c] = fc;
                         }
@@ -234,7 +241,7 @@ __global__ void __launch_bounds__(SplitClass<SCLS>::THREADS, SplitClass<SCLS>::M
                     const uint4* prow = reinterpret_cast<const uint4*>(lane_prof + uint32_t(cR[t]) * RS2);
                     uint32_t diag = diag_save;
                     diag_save = hl;
-                    uint32_t e = el, hleft = hl;
+                    uint32_t e = el, eg = hl, hleft = hl;
 #pragma unroll
                     for (int q = 0; q < (C2 + 3) / 4; ++q) {
                         const uint4 s4 = prow[q];
@@ -245,16 +252,22 @@ __global__ void __launch_bounds__(SplitClass<SCLS>::THREADS, SplitClass<SCLS>::M
                             const int c = 4 * q + k;
                             if (c < C2) {
                                 const uint32_t fc = __viaddmax_s16x2(f[c], kGE2, hg[c]);
-                                const uint32_t tf = __viaddmax_s16x2_relu(diag, sv[k], fc);
-                                e = __viaddmax_s16x2(e, kGE2, hleft);
+                                const uint32_t tf = __vimax3_s16x2(padd(diag, one, sv[k]), fc, kBIAS2);
+                                e = __viaddmax_s16x2(e, kGE2, eg);
+#if VTX_SW_EG
+                                eg = padd(tf, one, kGoeAdd);
+#endif
                                 const uint32_t h = __vmaxs2(tf, e);
                                 hh[k] = h;
                                 diag = hg[c];
-                                hleft = __vadd2(h, kGOE2);
+                                hleft = padd(h, one, kGoeAdd);
+#if !VTX_SW_EG
+                                eg = hleft;
+#endif
                                 hg[c] = hleft;
                                 f[c] = fc;
                             } else {
-                                hh[k] = 0;
+                                hh[k] = kBIAS2;
                             }
                         }
                         best = __vimax3_s16x2(best, hh[0], hh[1]);
@@ -265,7 +278,7 @@ __global__ void __launch_bounds__(SplitClass<SCLS>::THREADS, SplitClass<SCLS>::M
                 }
 #pragma unroll
                 for (int o = 2; o >= 1; o >>= 1) best = __vmaxs2(best, __shfl_xor_sync(0xffffffffu, best, o));
-                if (active && g == 0) call_and_scatter(a, pair, best);
+                if (active && g == 0) call_and_scatter(a, pair, best - kBIAS2);       // un-bias (no borrow: halves >= kBias)
             }
         }
     }
