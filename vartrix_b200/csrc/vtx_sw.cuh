@@ -4,10 +4,10 @@
 // (/root/reference/src/main.rs:898-901) and fuses evaluate_scores (main.rs:1019-1030) plus the
 // count-matrix increment as an epilogue.  Integer DP, no tensor cores:
 //
-//  * ref and alt haplotype scores travel in the two int16 lanes of one 32-bit word and every cell
-//    update is 5 native DPX/SIMD instructions: 2x VIADDMNMX.S16x2 (E, F), VIADD.16x2 (diag + s),
-//    VIMNMX3.S16x2.RELU (H) and VIADD.16x2 (H + gap_open + gap_extend), plus half a VIMNMX3 for the
-//    running maximum.
+//  * ref and alt haplotype scores travel in the two int16 lanes of one 32-bit word (biased by kBias, see
+//    below) and every cell update is 4.5 native DPX instructions -- 2x VIADDMNMX.S16x2 (E, F),
+//    VIMNMX3.S16x2 (max(diag + s, F, 0)), VIMNMX.S16x2 (H), half a VIMNMX3 (running maximum) -- plus two
+//    ordinary 32-bit adds (diag + s and H + gap_open + gap_extend).
 //  * LPP (=8) lanes cooperate on one pair: lane g owns C consecutive haplotype columns whose H/F
 //    state lives in registers; rows are skewed by one step per lane (anti-diagonal wavefront) and the
 //    boundary column travels to lane g+1 with two __shfl_up_sync per step.  A warp scores 32/LPP pairs
@@ -18,8 +18,8 @@
 //  * out-of-range rows/columns are all-mismatch sentinels, which can never raise a local maximum, so the
 //    inner loop carries no bounds predicates.
 //
-// Exactness: H <= read length < 32768 and E/F >= -16384 - (rows + cols), so int16 never saturates for
-// reads up to kFastMaxRead bases; longer reads, haplotypes wider than the largest tile class or with
+// Exactness: biased values stay inside [-300, 16384 + 1024 + 7] for reads up to kFastMaxRead bases, so int16
+// never saturates and the low half never borrows/carries other than the one constant carry; longer reads, haplotypes wider than the largest tile class or with
 // IUPAC/"=" bytes go to vtx_k_sw_generic (plain per-thread DP with byte equality).
 #pragma once
 #include <cstdint>

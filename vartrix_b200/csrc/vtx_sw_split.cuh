@@ -11,8 +11,8 @@
 //   phase 2  columns [96, n): halves are (ref, alt) of ONE read again.  8 reads x 4 lanes, C2 columns per
 //            lane; lane 0 of a read picks its half of the parked boundary and duplicates it (PRMT).
 //
-// Same recurrence, sentinels and exactness argument as vtx_sw.cuh; per pair it issues ~4 100 DPX
-// instructions instead of ~5 600 (prefix computed once per two reads, shorter pipeline drain).
+// Same recurrence, sentinels and exactness argument as vtx_sw.cuh; per pair it issues ~3 400 DPX
+// instructions instead of ~4 600 (prefix computed once per two reads, shorter pipeline drain).
 #pragma once
 #include "vtx_sw.cuh"
 
