@@ -267,13 +267,13 @@ def run_gpu(args):
     def step_e2e():
         for cb in hparts:
             rc = eng._L.vtx_submit(eng._h, C.byref(cb)); eng._ck(rc, "vtx_submit")
+        if world == 1:
+            return eng.finish(copy=False)    # vtx_finish streams the triplets into the library's pinned host arrays
         res = eng.finish_device()
-        if world > 1:
-            res = eng.gather()
-            if rank == 0:
-                return eng.fetch(res, copy=False)   # rank 0 writes the matrix: it alone needs the triplets on the host
-            return res
-        return eng.fetch(res, copy=False)    # triplets land in the library's pinned host arrays
+        res = eng.gather()
+        if rank == 0:
+            return eng.fetch(res, copy=False)   # rank 0 writes the matrix: it alone needs the triplets on the host
+        return res
 
     def barrier():
         if world > 1:

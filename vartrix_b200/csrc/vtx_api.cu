@@ -25,6 +25,8 @@ struct DBuf {
 
 enum { EV_START = 0, EV_H2D, EV_C0, EV_PREP, EV_SW, EV_POST, EV_COUNT };
 
+constexpr size_t kMaxCum = 4096;   // submits per finish that can stream their triplets out early
+
 struct TimeRec {   // CUDA events of one submit
     cudaEvent_t ev[EV_COUNT] = {};
     bool had_h2d = false;
@@ -73,6 +75,9 @@ struct vtx_ctx {
     uint64_t last_n = 0;
     vtx_metrics last_metrics{};
 
+    cudaStream_t fetch_stream = nullptr;                 // device->host copies of finished triplets
+    unsigned long long* h_cum = nullptr;                 // host-mapped running triplet count after each submit
+    unsigned long long* d_cum = nullptr;                 // device alias of h_cum
     std::vector<TimeRec> trecs;     // one per submit since the last finish (events are reused)
     size_t trec_used = 0;
     bool timing_valid = false;
@@ -278,7 +283,11 @@ int grow_results(vtx_ctx* ctx, size_t need)
         if (e != cudaSuccess) return set_err(ctx, VTX_E_NOMEM, "result cudaMalloc(%zu) failed: %s", ncap * esz[i], cudaGetErrorString(e));
         if (bufs[i]->p && ctx->res_ub && !ctx->finished)
             CK(cudaMemcpyAsync(np, bufs[i]->p, ctx->res_ub * esz[i], cudaMemcpyDeviceToDevice, ctx->stream));
-        if (bufs[i]->p) { CK(cudaStreamSynchronize(ctx->stream)); CK(cudaFree(bufs[i]->p)); }
+        if (bufs[i]->p) {
+            CK(cudaStreamSynchronize(ctx->stream));
+            if (ctx->fetch_stream) CK(cudaStreamSynchronize(ctx->fetch_stream));
+            CK(cudaFree(bufs[i]->p));
+        }
         bufs[i]->p = np; bufs[i]->cap = ncap * esz[i];
     }
     ctx->res_cap = ncap;
@@ -317,6 +326,8 @@ int process_batch(vtx_ctx* ctx, const DevBatch& b, TimeRec* tr)
     if (ctx->cfg.flags & VTX_F_KEEP_SCORES) { ENS(ctx->pair_scores, ncp * 4); pair_scores = P<uint32_t>(ctx->pair_scores); }
 
     if (nl == 0 || nc == 0) {
+        if (ctx->d_cum && ctx->trec_used - 1 < kMaxCum)     // an empty shard still publishes the running triplet count
+            vtx_k_bump<<<1, 32, 0, st>>>(P<unsigned long long>(ctx->d_res_n), nullptr, ctx->d_cum + (ctx->trec_used - 1));
         CK(cudaEventRecord(tr->ev[EV_PREP], st)); CK(cudaEventRecord(tr->ev[EV_SW], st)); CK(cudaEventRecord(tr->ev[EV_POST], st));
         ctx->timing_valid = true;
         return VTX_OK;
@@ -383,7 +394,9 @@ int process_batch(vtx_ctx* ctx, const DevBatch& b, TimeRec* tr)
     vtx_k_emit<<<blocks_for(nc, 256), 256, 0, st>>>(uint32_t(nc), ctx->cfg.mode, P<uint32_t>(ctx->keep2), P<uint32_t>(ctx->oidx),
                                                     P<unsigned long long>(ctx->d_res_n), P<uint32_t>(ctx->cslot_col),
                                                     P<uint32_t>(ctx->cslot_locus), b.locus_row, P<uint32_t>(ctx->ccnt), out);
-    vtx_k_bump<<<1, 32, 0, st>>>(P<unsigned long long>(ctx->d_res_n), P<uint32_t>(ctx->oidx) + nc);
+    const size_t sub_idx = ctx->trec_used - 1;       // this submit's slot
+    vtx_k_bump<<<1, 32, 0, st>>>(P<unsigned long long>(ctx->d_res_n), P<uint32_t>(ctx->oidx) + nc,
+                                 (ctx->d_cum && sub_idx < kMaxCum) ? ctx->d_cum + sub_idx : nullptr);
     launches += 2;
     CK(cudaGetLastError());
     CK(cudaEventRecord(tr->ev[EV_POST], st));
@@ -552,6 +565,10 @@ int vtx_create(const vtx_config* cfg, vtx_ctx** out)
     }
     pe = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     if (pe != cudaSuccess) { g_create_error = cudaGetErrorString(pe); vtx_destroy(ctx); return VTX_E_CUDA; }
+    cudaStreamCreateWithFlags(&ctx->fetch_stream, cudaStreamNonBlocking);
+    if (cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_cum), kMaxCum * 8, cudaHostAllocMapped) == cudaSuccess) {
+        if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx->d_cum), ctx->h_cum, 0) != cudaSuccess) ctx->d_cum = nullptr;
+    } else { ctx->h_cum = nullptr; cudaGetLastError(); }
     for (auto& sl : ctx->slot) {
         cudaEventCreateWithFlags(&sl.copy_done, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&sl.free_ev, cudaEventDisableTiming);
@@ -595,6 +612,8 @@ void vtx_destroy(vtx_ctx* ctx)
     if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
     for (auto& tr : ctx->trecs) for (auto& ev : tr.ev) if (ev) cudaEventDestroy(ev);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->fetch_stream) cudaStreamDestroy(ctx->fetch_stream);
+    if (ctx->h_cum) cudaFreeHost(ctx->h_cum);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -757,6 +776,8 @@ int vtx_finish_device(vtx_ctx* ctx, vtx_result* out)
     return VTX_OK;
 }
 
+static int ensure_host_results(vtx_ctx* ctx, size_t n);
+
 static int fetch_to(vtx_ctx* ctx, const vtx_result* dev, vtx_result* out, void** hbuf, size_t* hcap)
 {
     const size_t n = dev->n;
@@ -797,13 +818,65 @@ int vtx_fetch(vtx_ctx* ctx, const vtx_result* device_result, vtx_result* out)
                     : fetch_to(ctx, device_result, out, ctx->h_res, &ctx->h_res_cap);
 }
 
+// host pinned result arrays with room for `n` triplets
+static int ensure_host_results(vtx_ctx* ctx, size_t n)
+{
+    if (n <= ctx->h_res_cap) return VTX_OK;
+    const size_t esz[7] = { 4, 4, 4, 4, 4, 8, 8 };
+    const size_t ncap = n + n / 4 + 1024;
+    for (int i = 0; i < 7; ++i) {
+        if (ctx->h_res[i]) { cudaFreeHost(ctx->h_res[i]); ctx->h_res[i] = nullptr; }
+        cudaError_t e = cudaHostAlloc(&ctx->h_res[i], ncap * esz[i], cudaHostAllocDefault);
+        if (e != cudaSuccess) { ctx->h_res_cap = 0; return set_err(ctx, VTX_E_NOMEM, "pinned result alloc failed: %s", cudaGetErrorString(e)); }
+    }
+    ctx->h_res_cap = ncap;
+    return VTX_OK;
+}
+
 int vtx_finish(vtx_ctx* ctx, vtx_result* out)
 {
     if (!ctx || !out) return VTX_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    // Stream the triplets out submit by submit: the kernels of later submits are usually still running when the
+    // host gets here, so the device->host copy of everything but the last shard hides behind them.
+    const size_t esz[7] = { 4, 4, 4, 4, 4, 8, 8 };
+    DBuf* bufs[7] = { &ctx->r_row, &ctx->r_col, &ctx->r_ref, &ctx->r_alt, &ctx->r_unk, &ctx->r_val, &ctx->r_val2 };
+    const bool values_only = (ctx->cfg.flags & VTX_F_VALUES_ONLY) != 0;
+    const bool want[7] = { true, true, !values_only, !values_only, !values_only, true, !values_only || ctx->cfg.mode == VTX_MODE_COVERAGE };
+    size_t fetched = 0;
+    const bool streamed = !ctx->finished && ctx->h_cum && ctx->fetch_stream && ctx->trec_used > 0 && ctx->trec_used <= kMaxCum;
+    if (streamed) {
+        int rc = ensure_host_results(ctx, ctx->res_ub);
+        if (rc) return rc;
+        for (size_t i = 0; i < ctx->trec_used; ++i) {
+            CK(cudaEventSynchronize(ctx->trecs[i].ev[EV_POST]));
+            const size_t n_i = size_t(ctx->h_cum[i]);
+            if (n_i > fetched && n_i <= ctx->h_res_cap) {
+                for (int a = 0; a < 7; ++a)
+                    if (want[a]) CK(cudaMemcpyAsync(static_cast<uint8_t*>(ctx->h_res[a]) + fetched * esz[a], static_cast<uint8_t*>(bufs[a]->p) + fetched * esz[a],
+                                                    (n_i - fetched) * esz[a], cudaMemcpyDeviceToHost, ctx->fetch_stream));
+                fetched = n_i;
+            }
+        }
+    }
     vtx_result dev{};
     int rc = vtx_finish_device(ctx, &dev);
     if (rc) return rc;
-    return fetch_to(ctx, &dev, out, ctx->h_res, &ctx->h_res_cap);
+    const size_t n = dev.n;
+    rc = ensure_host_results(ctx, n);          // no-op when streamed (res_ub >= n)
+    if (rc) return rc;
+    if (n > fetched)
+        for (int a = 0; a < 7; ++a)
+            if (want[a]) CK(cudaMemcpyAsync(static_cast<uint8_t*>(ctx->h_res[a]) + fetched * esz[a], static_cast<uint8_t*>(bufs[a]->p) + fetched * esz[a],
+                                            (n - fetched) * esz[a], cudaMemcpyDeviceToHost, ctx->fetch_stream ? ctx->fetch_stream : ctx->stream));
+    CK(cudaStreamSynchronize(ctx->fetch_stream ? ctx->fetch_stream : ctx->stream));
+    out->n = n;
+    out->row = static_cast<uint32_t*>(ctx->h_res[0]); out->col = static_cast<uint32_t*>(ctx->h_res[1]);
+    out->ref_cnt = want[2] ? static_cast<uint32_t*>(ctx->h_res[2]) : nullptr; out->alt_cnt = want[3] ? static_cast<uint32_t*>(ctx->h_res[3]) : nullptr;
+    out->unk_cnt = want[4] ? static_cast<uint32_t*>(ctx->h_res[4]) : nullptr;
+    out->val = static_cast<double*>(ctx->h_res[5]); out->val2 = want[6] ? static_cast<double*>(ctx->h_res[6]) : nullptr;
+    out->metrics = dev.metrics;
+    return VTX_OK;
 }
 
 int vtx_last_timing(vtx_ctx* ctx, vtx_timing* t)

@@ -78,13 +78,20 @@ __global__ void vtx_k_cand_filter(uint64_t n_cand, const uint32_t* __restrict__ 
         else ok = true;
         keep[c] = ok ? 1u : 0u;
     }
+    // metric counters: warp ballots -> shared memory -> one atomic per counter per block (three hot addresses
+    // would otherwise serialise ~half a million warp-level atomics in L2)
+    __shared__ uint32_t s_cnt[3];
+    if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
     const uint32_t b0 = __ballot_sync(0xffffffffu, miss_cb), b1 = __ballot_sync(0xffffffffu, miss_umi),
                    b2 = __ballot_sync(0xffffffffu, ok);
     if ((threadIdx.x & 31) == 0) {
-        if (b0) atomicAdd(metrics + 0, (unsigned long long)__popc(b0));
-        if (b1) atomicAdd(metrics + 1, (unsigned long long)__popc(b1));
-        if (b2) atomicAdd(metrics + 2, (unsigned long long)__popc(b2));
+        if (b0) atomicAdd(&s_cnt[0], uint32_t(__popc(b0)));
+        if (b1) atomicAdd(&s_cnt[1], uint32_t(__popc(b1)));
+        if (b2) atomicAdd(&s_cnt[2], uint32_t(__popc(b2)));
     }
+    __syncthreads();
+    if (threadIdx.x < 3 && s_cnt[threadIdx.x]) atomicAdd(metrics + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]);
 }
 
 // largest l with cand_start[l] <= c
@@ -424,9 +431,15 @@ __global__ void vtx_k_emit(uint32_t n_slots_ub, int mode, const uint32_t* __rest
     out.val[o] = v; out.val2[o] = v2;
 }
 
-__global__ void vtx_k_bump(unsigned long long* res_n, const uint32_t* __restrict__ total)
+// res_n += total; the running count also goes to a host-mapped slot so that vtx_finish can start copying the
+// triplets of this submit while later submits are still computing
+__global__ void vtx_k_bump(unsigned long long* res_n, const uint32_t* __restrict__ total, unsigned long long* cum_host)
 {
-    if (threadIdx.x == 0 && blockIdx.x == 0) *res_n += *total;
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const unsigned long long n = *res_n + (total ? *total : 0u);
+        *res_n = n;
+        if (cum_host) *cum_host = n;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

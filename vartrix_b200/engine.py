@@ -245,11 +245,11 @@ class Engine:
                         _np_from(res.val2, n, np.float64, copy),
                         dict(num_not_cell_bc=int(m.num_not_cell_bc), num_non_umi=int(m.num_non_umi), num_scored=int(m.num_scored)))
 
-    def finish(self) -> Triplets:
+    def finish(self, copy: bool = True) -> Triplets:
         res = _capi.Result()
         self._ck(self._L.vtx_finish(self._h, C.byref(res)), "vtx_finish")
         self._keep.clear()
-        return self._triplets(res)
+        return self._triplets(res, copy)
 
     def finish_device(self) -> _capi.Result:
         res = _capi.Result()
