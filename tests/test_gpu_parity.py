@@ -294,3 +294,39 @@ def test_values_only_fetch_and_raw_score_side_channel(vb, oracle):
         got = eng.run(sb)
     assert np.array_equal(got.row, exp.row) and np.array_equal(got.col, exp.col)
     assert np.array_equal(got.val, exp.val) and np.array_equal(got.val2, exp.val2) and got.ref_cnt.size == 0
+
+
+def test_fuzz_whole_path_against_oracle(vb, oracle):
+    """Differential fuzz of the whole path: irregular shards (reads shared between loci, repeated candidates, missing
+    tags, tiny barcode lists so that cells collide, interned-style UMI keys, every mode) against the oracle."""
+    rng = np.random.default_rng(20240924)
+    for it in range(24):
+        n_loci = int(rng.integers(1, 30))
+        sb, pr, pl = _random_pairs_batch(vb, rng, n_loci=n_loci, reads_per_locus=int(rng.integers(1, 12)), m_lo=int(rng.integers(1, 60)),
+                                         m_hi=int(rng.integers(60, 200)), n_lo=int(rng.integers(40, 150)), n_hi=int(rng.integers(150, 260)))
+        n_reads = sb.n_reads
+        # candidates: every locus draws a random multiset of reads (reads are shared between loci, some repeated)
+        per = rng.integers(0, 40, size=n_loci)
+        cand_start = np.concatenate([[0], np.cumsum(per)]).astype(np.uint64)
+        cand_read = rng.integers(0, n_reads, size=int(per.sum())).astype(np.uint32)
+        n_bc = int(rng.integers(1, 7))
+        keys = [f"BC{k:02d}-1".encode() for k in range(n_bc)]
+        tags = keys + [b"UNLISTED-1", b"BC00-2"]
+        pick = rng.integers(0, len(tags), size=n_reads)
+        cb_bytes = np.frombuffer(b"".join(tags), np.uint8)
+        offs = np.concatenate([[0], np.cumsum([len(t) for t in tags])])
+        read_cb_off = offs[pick].astype(np.uint32); read_cb_len = np.array([len(tags[i]) for i in pick], np.uint16)
+        read_cb_off[rng.random(n_reads) < 0.1] = vb.engine.NO_CB
+        umi = rng.integers(0, 4, size=n_reads).astype(np.uint64) | (np.uint64(1) << np.uint64(61)) * (rng.random(n_reads) < 0.5).astype(np.uint64)
+        umi[rng.random(n_reads) < 0.1] = vb.engine.NO_UMI
+        shard = vb.StagedBatch(locus_row=np.cumsum(rng.integers(1, 4, size=n_loci)), hap_bytes=sb.hap_bytes, ref_off=sb.ref_off, ref_len=sb.ref_len,
+                               alt_off=sb.alt_off, alt_len=sb.alt_len, cand_start=cand_start, read_nib=sb.read_nib, read_off=sb.read_off,
+                               read_len=sb.read_len, cb_bytes=cb_bytes, read_cb_off=read_cb_off, read_cb_len=read_cb_len, read_umi_key=umi,
+                               cand_read=cand_read, n_rows=int(3 * n_loci + 4))
+        bcs = vb.Barcodes(keys)
+        mode = ("consensus", "coverage", "alt_frac")[it % 3]
+        use_umi = bool(it & 1)
+        got = _run_engine(vb, shard, bcs, mode, use_umi, no_split=bool(it & 2))
+        exp = _oracle_run(oracle, shard, bcs, mode, use_umi, threads=4)
+        assert_same_triplets(got, exp)
+        assert got.metrics == exp.metrics, it
