@@ -171,7 +171,9 @@ int launch_sw_class(vtx_ctx* ctx, SwArgs a, uint64_t* launches)
 {
     using TC = TileClass<CLS>;
     constexpr int PPW = 32 / TC::LPP, RS = TC::LPP * TC::CS;
-    const size_t warp_bytes = (size_t(5 * RS) * 4 + size_t(PPW) * (a.mcap + 2 * TC::LPP) * 2 + 15) & ~size_t(15);
+    const size_t codes_bytes = (size_t(PPW) * (a.mcap + 2 * TC::LPP) * 2 + 7) & ~size_t(7);
+    const size_t bnd_bytes = (CLS == kMultiClass && a.multi) ? size_t(PPW) * (a.mcap + 8) * 8 : 0;
+    const size_t warp_bytes = (size_t(5 * RS) * 4 + codes_bytes + bnd_bytes + 15) & ~size_t(15);
     constexpr int kSwThreads = TC::THREADS;
     const size_t smem = warp_bytes * (kSwThreads / 32);
     auto kern = vtx_k_sw_pairs<CLS>;
@@ -211,8 +213,9 @@ int run_sw(vtx_ctx* ctx, const DevBatch& b, uint32_t n_pairs_ub, const uint32_t*
     ENS(ctx->tile_counters, 64);
     const int force_slow = b.max_read_len > uint32_t(kFastMaxRead) ? 1 : 0;
     const int allow_split = (b.max_read_len <= uint32_t(kSplitMaxRead) && !(ctx->cfg.flags & VTX_F_NO_SPLIT)) ? 1 : 0;
+    const int allow_multi = (b.max_read_len <= uint32_t(kMultiMaxRead) && b.max_hap_len > uint32_t(class_max_n(kNumFastClasses - 1))) ? 1 : 0;
     vtx_k_locus_prep<<<blocks_for(uint64_t(nl) * 32, 256), 256, 0, ctx->stream>>>(
-        nl, b.hap, b.ref_off, b.ref_len, b.alt_off, b.alt_len, P<uint32_t>(ctx->pair_start), force_slow, allow_split,
+        nl, b.hap, b.ref_off, b.ref_len, b.alt_off, b.alt_len, P<uint32_t>(ctx->pair_start), force_slow, allow_split, allow_multi,
         P<uint32_t>(ctx->tcount));
     ++*launches;
     vtx_k_scan_rows<<<kNumClasses, kScanThreads, 0, ctx->stream>>>(P<uint32_t>(ctx->tcount), P<uint32_t>(ctx->tstart), nl, nl + 1);
@@ -232,6 +235,7 @@ int run_sw(vtx_ctx* ctx, const DevBatch& b, uint32_t n_pairs_ub, const uint32_t*
     a.mcap = mcap;
     a.k64k = 65536u;
     a.one = 1u;
+    a.multi = allow_multi;
     a.max_hap = b.max_hap_len;
 
     uint64_t before = *launches;

@@ -142,7 +142,7 @@ __global__ void vtx_k_pair_start_explicit(uint32_t n_loci, uint32_t n_pairs, con
 __global__ void vtx_k_locus_prep(uint32_t n_loci, const uint8_t* __restrict__ hap_bytes,
                                  const uint32_t* __restrict__ ref_off, const uint32_t* __restrict__ ref_len,
                                  const uint32_t* __restrict__ alt_off, const uint32_t* __restrict__ alt_len,
-                                 const uint32_t* __restrict__ pair_start, int force_slow, int allow_split,
+                                 const uint32_t* __restrict__ pair_start, int force_slow, int allow_split, int allow_multi,
                                  uint32_t* __restrict__ tcount /* [kNumClasses][n_loci + 1] */)
 {
     const uint32_t l = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -170,6 +170,7 @@ __global__ void vtx_k_locus_prep(uint32_t n_loci, const uint8_t* __restrict__ ha
     if (!exotic && !force_slow) {
 #pragma unroll
         for (int c = kNumFastClasses - 1; c >= 0; --c) if (nmax <= uint32_t(class_max_n(c))) cls = c;
+        if (cls == kSlowClass && allow_multi) cls = kMultiClass;        // wider than 320 columns: several passes
         if (same && allow_split) {
 #pragma unroll
             for (int c = kNumSplitClasses - 1; c >= 0; --c) if (nmax <= uint32_t(split_max_n(c))) cls = kSplitClass0 + c;

@@ -86,7 +86,11 @@ template <int CLS> struct TileClass;
 template <> struct TileClass<0> { static constexpr int LPP = 8, C = 26, CS = 28, THREADS = 320, MINB = 2; };   // n <= 208 (SNV, pad 100)
 template <> struct TileClass<1> { static constexpr int LPP = 8, C = 29, CS = 36, THREADS = 320, MINB = 2; };   // n <= 232 (indels <= 30)
 template <> struct TileClass<2> { static constexpr int LPP = 8, C = 32, CS = 36, THREADS = 256, MINB = 2; };   // n <= 256
-template <> struct TileClass<3> { static constexpr int LPP = 8, C = 40, CS = 44, THREADS = 384, MINB = 1; };   // n <= 320
+template <> struct TileClass<3> { static constexpr int LPP = 8, C = 40, CS = 44, THREADS = 384, MINB = 1; };   // n <= 320 per pass
+// Class 3 also takes windows wider than 320 columns (e.g. --padding 200) in several passes of 320 columns: the last
+// column (H + gap, E) of every row is parked in shared memory between passes, like the two-phase kernels do.
+constexpr int kMultiClass = 3;
+constexpr int kMultiMaxRead = 256;       // reads longer than this fall back to the generic kernel for wide windows
 __host__ __device__ constexpr int class_max_n(int cls)
 {
     return cls == 0 ? 208 : cls == 1 ? 232 : cls == 2 ? 256 : cls == 3 ? 320 : 0x7fffffff;
@@ -112,6 +116,7 @@ struct SwArgs {
     int32_t mcap;                   // row-code capacity (even, >= longest read in the batch)
     uint32_t k64k;                  // 65536 as a run-time value (keeps a shift-add on the FMA pipe, see vtx_sw_split.cuh)
     uint32_t one;                   // 1 as a run-time value (keeps the packed adds on the FMA pipe)
+    int32_t multi;                  // class 3 may run several column passes (boundary buffer present in smem)
     // generic kernel only
     uint32_t* scratch;              // [warps][max_hap + 1][32]
     uint32_t max_hap;
@@ -163,11 +168,15 @@ __global__ void __launch_bounds__(TileClass<CLS>::THREADS, TileClass<CLS>::MINB)
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane % LPP, grp = lane / LPP;
+    constexpr bool MULTI = (CLS == kMultiClass);
     const int code_stride = a.mcap + 2 * M;                      // u16 entries per group
-    const size_t warp_bytes = size_t(5 * RS) * 4 + size_t(PPW) * code_stride * 2;
+    const int bnd_stride = (MULTI && a.multi) ? a.mcap + 8 : 0;  // uint2 entries per group (multi-pass boundary column)
+    const size_t codes_bytes = (size_t(PPW) * code_stride * 2 + 7) & ~size_t(7);
+    const size_t warp_bytes = size_t(5 * RS) * 4 + codes_bytes + size_t(PPW) * bnd_stride * 8;
     uint8_t* wbase = smem_raw + warp * ((warp_bytes + 15) & ~size_t(15));
     uint32_t* prof = reinterpret_cast<uint32_t*>(wbase);
     uint16_t* codes = reinterpret_cast<uint16_t*>(wbase + size_t(5 * RS) * 4) + grp * code_stride;
+    uint2* bnd = reinterpret_cast<uint2*>(wbase + size_t(5 * RS) * 4 + codes_bytes) + grp * bnd_stride;
 
     const uint32_t n_tiles = __ldg(a.tile_start + a.n_loci);
     uint32_t cached_locus = 0xFFFFFFFFu;
@@ -190,15 +199,15 @@ __global__ void __launch_bounds__(TileClass<CLS>::THREADS, TileClass<CLS>::MINB)
             const uint32_t p_end = __ldg(a.pair_start + locus + 1);
 
             __syncwarp();
-            // ---- per-locus substitution profile (only when the locus changes) ----
-            if (locus != cached_locus) {
-                cached_locus = locus;
-                const uint8_t* rh = a.hap_bytes + __ldg(a.ref_off + locus);
-                const uint8_t* ah = a.hap_bytes + __ldg(a.alt_off + locus);
-                const int n_ref = int(__ldg(a.ref_len + locus)), n_alt = int(__ldg(a.alt_len + locus));
+            const uint8_t* rh = a.hap_bytes + __ldg(a.ref_off + locus);
+            const uint8_t* ah = a.hap_bytes + __ldg(a.alt_off + locus);
+            const int n_ref = int(__ldg(a.ref_len + locus)), n_alt = int(__ldg(a.alt_len + locus));
+            const int n_pass = MULTI ? max(1, (max(n_ref, n_alt) + LPP * C - 1) / (LPP * C)) : 1;
+            // per-locus substitution profile of columns [col0, col0 + LPP*C): rebuilt when the locus (or the pass) changes
+            auto build_profile = [&](int col0) {
                 for (int idx = lane; idx < RS; idx += 32) {
                     const int gg = idx / CS, k = idx - gg * CS;
-                    const int j = gg * C + k;
+                    const int j = col0 + gg * C + k;
                     uint32_t rb = 5, ab = 5;
                     if (k < C) {
                         if (j < n_ref) rb = hap_code(__ldg(rh + j));
@@ -208,7 +217,9 @@ __global__ void __launch_bounds__(TileClass<CLS>::THREADS, TileClass<CLS>::MINB)
                     for (uint32_t r = 0; r < 5; ++r)
                         prof[r * RS + idx] = pack2(r == rb ? kProfMatch : kProfMis, r == ab ? kProfMatch : kProfMis);
                 }
-            }
+            };
+            if (n_pass == 1 && locus != cached_locus) { cached_locus = locus; build_profile(0); }
+            if (n_pass > 1) cached_locus = 0xFFFFFFFFu;
             // ---- row codes of this group's read: byte offset of the profile row per read base ----
             const uint32_t pair = p0 + grp;
             const bool active = pair < p_end;
@@ -232,58 +243,65 @@ __global__ void __launch_bounds__(TileClass<CLS>::THREADS, TileClass<CLS>::MINB)
             __syncwarp();
 
             // ---- anti-diagonal wavefront: lane g works on row (t - g) of its C columns ----
-            uint32_t hg[C], f[C];
-#pragma unroll
-            for (int c = 0; c < C; ++c) { hg[c] = kGOE2; f[c] = kNEG2; }
-            uint32_t hg_last = kGOE2, e_last = kNEG2, diag_save = kGOE2, best = kBIAS2;
+            uint32_t best = kBIAS2;
             const uint8_t* lane_prof = reinterpret_cast<const uint8_t*>(prof) + g * CS * 4;
             const uint16_t* my_codes = codes + M - g;
             const int steps = mmax + LPP - 1;
             const uint32_t one = a.one;
-            for (int t = 0; t < steps; ++t) {
-                uint32_t hl = __shfl_up_sync(0xffffffffu, hg_last, 1, LPP);
-                uint32_t el = __shfl_up_sync(0xffffffffu, e_last, 1, LPP);
-                if (g == 0) { hl = kGOE2; el = kNEG2; }
-                const uint4* prow = reinterpret_cast<const uint4*>(lane_prof + my_codes[t]);
-                uint32_t diag = diag_save;
-                diag_save = hl;
-                // E[i][c] = max(E[i][c-1] + ge, H[i][c-1] + goe) = max(E[i][c-1] + ge, tf[i][c-1] + goe): `eg` carries
-                // the second operand, so the E chain is one instruction per cell
-                uint32_t e = el, eg = hl, hleft = hl;
+            for (int pass = 0; pass < n_pass; ++pass) {
+                if (MULTI && n_pass > 1) { __syncwarp(); build_profile(pass * LPP * C); __syncwarp(); }
+                uint32_t hg[C], f[C];
 #pragma unroll
-                for (int q = 0; q < (C + 3) / 4; ++q) {
-                    const uint4 s4 = prow[q];
-                    const uint32_t sv[4] = { s4.x, s4.y, s4.z, s4.w };
-                    uint32_t hh[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int c = 4 * q + k;
-                        if (c < C) {
-                            const uint32_t fc = __viaddmax_s16x2(f[c], kGE2, hg[c]);     // F[i][c]
-                            const uint32_t tt = padd(diag, one, sv[k]);                 // H[i-1][c-1] + s      (IMAD)
-                            const uint32_t tf = __vimax3_s16x2(tt, fc, kBIAS2);         // max(H[i-1][c-1] + s, F, 0)
-                            e = __viaddmax_s16x2(e, kGE2, eg);                          // E[i][c]
-#if VTX_SW_EG
-                            eg = padd(tf, one, kGoeAdd);                                // tf + goe             (IMAD)
-#endif
-                            const uint32_t h = __vmaxs2(tf, e);                         // H[i][c]
-                            hh[k] = h;
-                            diag = hg[c];
-                            hleft = padd(h, one, kGoeAdd);                              // H + goe              (IMAD)
-#if !VTX_SW_EG
-                            eg = hleft;
-#endif
-                            hg[c] = hleft;
-                            f[c] = fc;
-                        } else {
-                            hh[k] = kBIAS2;
-                        }
+                for (int c = 0; c < C; ++c) { hg[c] = kGOE2; f[c] = kNEG2; }
+                uint32_t hg_last = kGOE2, e_last = kNEG2, diag_save = kGOE2;
+                for (int t = 0; t < steps; ++t) {
+                    uint32_t hl = __shfl_up_sync(0xffffffffu, hg_last, 1, LPP);
+                    uint32_t el = __shfl_up_sync(0xffffffffu, e_last, 1, LPP);
+                    if (g == 0) {
+                        hl = kGOE2; el = kNEG2;
+                        if (MULTI && pass > 0 && t < mmax) { const uint2 b = bnd[t]; hl = b.x; el = b.y; }   // column col0 - 1 of row t
                     }
-                    best = __vimax3_s16x2(best, hh[0], hh[1]);
-                    if (4 * q + 2 < C) best = __vimax3_s16x2(best, hh[2], hh[3]);
+                    const uint4* prow = reinterpret_cast<const uint4*>(lane_prof + my_codes[t]);
+                    uint32_t diag = diag_save;
+                    diag_save = hl;
+                    // E[i][c] = max(E[i][c-1] + ge, H[i][c-1] + goe); with VTX_SW_EG the second operand is tf + goe
+                    uint32_t e = el, eg = hl, hleft = hl;
+#pragma unroll
+                    for (int q = 0; q < (C + 3) / 4; ++q) {
+                        const uint4 s4 = prow[q];
+                        const uint32_t sv[4] = { s4.x, s4.y, s4.z, s4.w };
+                        uint32_t hh[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int c = 4 * q + k;
+                            if (c < C) {
+                                const uint32_t fc = __viaddmax_s16x2(f[c], kGE2, hg[c]);     // F[i][c]
+                                const uint32_t tt = padd(diag, one, sv[k]);                 // H[i-1][c-1] + s
+                                const uint32_t tf = __vimax3_s16x2(tt, fc, kBIAS2);         // max(H[i-1][c-1] + s, F, 0)
+                                e = __viaddmax_s16x2(e, kGE2, eg);                          // E[i][c]
+#if VTX_SW_EG
+                                eg = padd(tf, one, kGoeAdd);                                // tf + goe
+#endif
+                                const uint32_t h = __vmaxs2(tf, e);                         // H[i][c]
+                                hh[k] = h;
+                                diag = hg[c];
+                                hleft = padd(h, one, kGoeAdd);                              // H + goe
+#if !VTX_SW_EG
+                                eg = hleft;
+#endif
+                                hg[c] = hleft;
+                                f[c] = fc;
+                            } else {
+                                hh[k] = kBIAS2;
+                            }
+                        }
+                        best = __vimax3_s16x2(best, hh[0], hh[1]);
+                        if (4 * q + 2 < C) best = __vimax3_s16x2(best, hh[2], hh[3]);
+                    }
+                    hg_last = hleft;
+                    e_last = e;
+                    if (MULTI && pass + 1 < n_pass && g == LPP - 1 && t >= LPP - 1) bnd[t - (LPP - 1)] = make_uint2(hleft, e);
                 }
-                hg_last = hleft;
-                e_last = e;
             }
             // ---- epilogue: group maximum, call, atomic scatter ----
 #pragma unroll
