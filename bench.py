@@ -76,7 +76,7 @@ def describe(args, cfg, world, info):
         "candidates_per_gpu": info["n_cand"], "scoring_method": cfg["scoring_method"], "umi": bool(cfg.get("umi")),
         "parallelism": f"loci sharded over {world} GPU(s), one allgatherv of triplets" if world > 1 else "1 GPU",
         "l2_policy": "inputs larger than L2 (staged shard >> 126 MB), no explicit flush",
-        "e2e_chunks": args.chunks, "e2e_first_chunk_frac": args.first_chunk,
+        "e2e_chunks": args.chunks, "e2e_first_chunk_frac": args.first_chunk, "host_cores_bound_to_gpu": len(os.sched_getaffinity(0)),
     }
 
 
@@ -213,6 +213,19 @@ def run_gpu(args):
     saved_stdout = os.dup(1)
     os.dup2(2, 1)
     torch.cuda.set_device(local)
+    # bind this rank to the CPU cores next to its GPU (NVML affinity) so that pinned staging buffers are allocated
+    # on the GPU-local NUMA node; the full affinity mask comes back before the CPU baseline is timed
+    full_affinity = os.sched_getaffinity(0)
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")[local]) if os.environ.get("CUDA_VISIBLE_DEVICES", "").replace(",", "").isdigit() else local)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cores = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1} & full_affinity
+        if cores:
+            os.sched_setaffinity(0, cores)
+    except Exception:
+        pass
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -369,6 +382,7 @@ def run_gpu(args):
             "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:
+            os.sched_setaffinity(0, full_affinity)
             line["cpu_baseline"] = cpu_baseline(sb, bcs, cfg, info, args.cpu_seconds)
     eng.close()
     if world > 1:
