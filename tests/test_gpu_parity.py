@@ -122,7 +122,9 @@ def _random_pairs_batch(vb, rng, n_loci, reads_per_locus, m_lo, m_hi, n_lo, n_hi
                                       alphabet=b"ACGTNRYKM=", read_codes=tuple(range(16)), related=False)),
     ("reads_with_N_and_iupac", dict(n_loci=20, reads_per_locus=8, m_lo=80, m_hi=150, n_lo=150, n_hi=208,
                                     read_codes=(1, 2, 4, 8, 15, 15, 3, 0), related=False)),
-    ("long_reads_generic", dict(n_loci=3, reads_per_locus=3, m_lo=1025, m_hi=1400, n_lo=180, n_hi=208)),
+    ("long_reads_row_blocks", dict(n_loci=3, reads_per_locus=3, m_lo=1025, m_hi=1400, n_lo=180, n_hi=208)),
+    ("very_long_reads_row_blocks", dict(n_loci=2, reads_per_locus=5, m_lo=2000, m_hi=6000, n_lo=150, n_hi=320)),
+    ("long_reads_wide_windows_generic", dict(n_loci=2, reads_per_locus=3, m_lo=300, m_hi=900, n_lo=330, n_hi=500)),
 ])
 def test_random_pairs_bit_exact(vb, oracle, name, kw):
     rng = np.random.default_rng(sum(map(ord, name)))

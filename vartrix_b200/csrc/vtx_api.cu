@@ -211,7 +211,7 @@ int run_sw(vtx_ctx* ctx, const DevBatch& b, uint32_t n_pairs_ub, const uint32_t*
     ENS(ctx->tcount, size_t(kNumClasses) * (nl + 1) * 4);
     ENS(ctx->tstart, size_t(kNumClasses) * (nl + 1) * 4);
     ENS(ctx->tile_counters, 64);
-    const int force_slow = b.max_read_len > uint32_t(kFastMaxRead) ? 1 : 0;
+    const int force_slow = 0;       // reads of any supported length run on the single-phase classes (row blocks)
     const int allow_split = (b.max_read_len <= uint32_t(kSplitMaxRead) && !(ctx->cfg.flags & VTX_F_NO_SPLIT)) ? 1 : 0;
     const int allow_multi = (b.max_read_len <= uint32_t(kMultiMaxRead) && b.max_hap_len > uint32_t(class_max_n(kNumFastClasses - 1))) ? 1 : 0;
     vtx_k_locus_prep<<<blocks_for(uint64_t(nl) * 32, 256), 256, 0, ctx->stream>>>(
@@ -487,7 +487,7 @@ int scan_host_batch(vtx_ctx* ctx, const vtx_batch* b, uint32_t* max_read, uint32
         default: break;
         }
     }
-    if (mr > 32000) return set_err(ctx, VTX_E_UNSUPPORTED, "reads longer than 32000 bases (int16 DP) are not supported (%u)", mr);
+    if (mr > uint32_t(kMaxRead)) return set_err(ctx, VTX_E_UNSUPPORTED, "reads longer than %d bases (biased int16 DP) are not supported (%u)", kMaxRead, mr);
     *max_read = mr; *max_hap = mh;
     if (max_depth) *max_depth = md;
     return VTX_OK;
@@ -713,7 +713,7 @@ int vtx_submit_device_ex(vtx_ctx* ctx, const vtx_batch* db, uint32_t max_read_le
     if (!ctx->have_barcodes) return set_err(ctx, VTX_E_STATE, "vtx_set_barcodes must be called before vtx_submit_device");
     int rc = validate_batch(ctx, db);
     if (rc) return rc;
-    if (max_read_len > 32000) return set_err(ctx, VTX_E_UNSUPPORTED, "reads longer than 32000 bases are not supported");
+    if (max_read_len > uint32_t(kMaxRead)) return set_err(ctx, VTX_E_UNSUPPORTED, "reads longer than %d bases are not supported", kMaxRead);
     CK(cudaSetDevice(ctx->device));
     DevBatch d{};
     d.n_loci = db->n_loci; d.n_reads = db->n_reads; d.n_cand = db->n_cand;

@@ -70,7 +70,8 @@ __device__ __forceinline__ uint32_t padd(uint32_t x, uint32_t one, uint32_t c)
 // profile entries are biased by -kGoe because the stored state is H + kGoe
 constexpr int kProfMatch = kMatch - kGoe, kProfMis = kMismatch - kGoe;     // 7, 1
 
-constexpr int kFastMaxRead = 1024;       // longest read the fast kernels take (smem row-code buffer)
+constexpr int kFastMaxRead = 1024;       // row-code buffer of the single-phase kernels; longer reads are scored in row blocks
+constexpr int kMaxRead = 16000;          // biased int16: H + 16384 must stay below 32768
 constexpr int kNumFastClasses = 4;                 // single-phase tile classes 0..3
 constexpr int kSlowClass = kNumFastClasses;        // 4: generic kernel
 constexpr int kNumSplitClasses = 2;                // 5, 6: two-phase kernels (vtx_sw_split.cuh)
@@ -230,17 +231,23 @@ __global__ void __launch_bounds__(TileClass<CLS>::THREADS, TileClass<CLS>::MINB)
                 m = int(__ldg(a.read_len + r));
                 nib = a.read_nib + __ldg(a.read_off + r);
             }
-            for (int e = g; e < code_stride; e += LPP)
-                if (e < M || e >= M + m) codes[e] = uint16_t(kSentinel);
-            for (int b = g; 2 * b < m; b += LPP) {
-                const uint32_t by = __ldg(nib + b);
-                codes[M + 2 * b] = uint16_t(nib_code(by >> 4) * (RS * 4));
-                if (2 * b + 1 < m) codes[M + 2 * b + 1] = uint16_t(nib_code(by & 0xF) * (RS * 4));
-            }
+            // row codes: byte offset of the profile row per read base, for the rows [t0 - M, t0 + R + M) of the current
+            // row block (reads longer than the buffer are scored block by block; the DP state stays in registers)
+            const int R = a.mcap;
+            auto fill_codes = [&](int t0) {
+                for (int e = g; e < code_stride; e += LPP) {
+                    const int row = t0 - M + e;
+                    uint32_t off = kSentinel;
+                    if (row >= 0 && row < m) {
+                        const uint32_t by = __ldg(nib + (row >> 1));
+                        off = nib_code((row & 1) ? (by & 0xF) : (by >> 4)) * (RS * 4);
+                    }
+                    codes[e] = uint16_t(off);
+                }
+            };
             int mmax = m;
 #pragma unroll
             for (int o = 16; o >= 1; o >>= 1) mmax = max(mmax, __shfl_xor_sync(0xffffffffu, mmax, o));
-            __syncwarp();
 
             // ---- anti-diagonal wavefront: lane g works on row (t - g) of its C columns ----
             uint32_t best = kBIAS2;
@@ -254,14 +261,19 @@ __global__ void __launch_bounds__(TileClass<CLS>::THREADS, TileClass<CLS>::MINB)
 #pragma unroll
                 for (int c = 0; c < C; ++c) { hg[c] = kGOE2; f[c] = kNEG2; }
                 uint32_t hg_last = kGOE2, e_last = kNEG2, diag_save = kGOE2;
-                for (int t = 0; t < steps; ++t) {
+                for (int t0 = 0; t0 < steps; t0 += R) {
+                __syncwarp();
+                fill_codes(t0);
+                __syncwarp();
+                const int t_hi = min(steps, t0 + R);
+                for (int t = t0; t < t_hi; ++t) {
                     uint32_t hl = __shfl_up_sync(0xffffffffu, hg_last, 1, LPP);
                     uint32_t el = __shfl_up_sync(0xffffffffu, e_last, 1, LPP);
                     if (g == 0) {
                         hl = kGOE2; el = kNEG2;
                         if (MULTI && pass > 0 && t < mmax) { const uint2 b = bnd[t]; hl = b.x; el = b.y; }   // column col0 - 1 of row t
                     }
-                    const uint4* prow = reinterpret_cast<const uint4*>(lane_prof + my_codes[t]);
+                    const uint4* prow = reinterpret_cast<const uint4*>(lane_prof + my_codes[t - t0]);
                     uint32_t diag = diag_save;
                     diag_save = hl;
                     // E[i][c] = max(E[i][c-1] + ge, H[i][c-1] + goe); with VTX_SW_EG the second operand is tf + goe
@@ -301,6 +313,7 @@ __global__ void __launch_bounds__(TileClass<CLS>::THREADS, TileClass<CLS>::MINB)
                     hg_last = hleft;
                     e_last = e;
                     if (MULTI && pass + 1 < n_pass && g == LPP - 1 && t >= LPP - 1) bnd[t - (LPP - 1)] = make_uint2(hleft, e);
+                }
                 }
             }
             // ---- epilogue: group maximum, call, atomic scatter ----
