@@ -74,7 +74,8 @@ def describe(args, cfg, world, info):
                     + (", --umi" if cfg.get("umi") else ""),
         "loci_per_gpu": cfg["n_loci"], "barcodes": cfg["n_barcodes"], "pairs_per_gpu": info["n_pairs"],
         "candidates_per_gpu": info["n_cand"], "scoring_method": cfg["scoring_method"], "umi": bool(cfg.get("umi")),
-        "parallelism": f"loci sharded over {world} GPU(s), one allgatherv of triplets" if world > 1 else "1 GPU",
+        "parallelism": (f"loci sharded over {world} GPU(s), one NCCL allgatherv of triplets per step; on the e2e path every rank copies its own "
+                        f"row range to its host (h2d/d2h bytes are job totals)") if world > 1 else "1 GPU",
         "l2_policy": "inputs larger than L2 (staged shard >> 126 MB), no explicit flush",
         "e2e_chunks": args.chunks, "e2e_first_chunk_frac": args.first_chunk, "host_cores_bound_to_gpu": len(os.sched_getaffinity(0)),
     }
@@ -280,13 +281,13 @@ def run_gpu(args):
     def step_e2e():
         for cb in hparts:
             rc = eng._L.vtx_submit(eng._h, C.byref(cb)); eng._ck(rc, "vtx_submit")
-        if world == 1:
-            return eng.finish(copy=False)    # vtx_finish streams the triplets into the library's pinned host arrays
-        res = eng.finish_device()
-        res = eng.gather()
-        if rank == 0:
-            return eng.fetch(res, copy=False)   # rank 0 writes the matrix: it alone needs the triplets on the host
-        return res
+        # vtx_finish streams this rank's triplets into the library's pinned host arrays while later shards compute.
+        # With several ranks every rank ends up with its own contiguous row range on its host (rank r writes block r
+        # of the .mtx at its offset), and the NCCL allgatherv still assembles the whole matrix on every GPU.
+        out = eng.finish(copy=False)
+        if world > 1:
+            eng.gather()
+        return out
 
     def barrier():
         if world > 1:
@@ -331,8 +332,10 @@ def run_gpu(args):
     ms_e, _, _, last_e, _ = timed(step_e2e, args.steps)
     t_e = eng.timing()
     e2e_value = total_pairs * args.steps / (ms_e / 1e3)
-    n_out = int(last_e.n) if hasattr(last_e, "n") else len(last_e.row)
-    d2h_bytes = n_out * 16 + 32        # row, col (u32) + val (f64) per triplet (VTX_F_VALUES_ONLY) + counters
+    n_out = len(last_e.row)
+    if world > 1:
+        tn = torch.tensor([n_out], device="cuda", dtype=torch.int64); dist.all_reduce(tn); n_out = int(tn.item())
+    d2h_bytes = n_out * 16 + 32 * world    # row, col (u32) + val (f64) per triplet (VTX_F_VALUES_ONLY) + counters, all ranks
 
     line = None
     if rank == 0:
@@ -365,7 +368,7 @@ def run_gpu(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int16x2", "data": "synthetic", "config": describe(args, cfg, world, info),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes * world, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": ms_e / args.steps,
                     "last_step_device_ms": {k: round(t_e[k], 3) for k in ("h2d_ms", "prep_ms", "sw_ms", "post_ms")}},
             "gpu_launches": launches,
