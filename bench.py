@@ -110,9 +110,11 @@ def cpu_baseline(sb, bcs, cfg, info, target_s):
     rate = pairs / max(dt, 1e-9)
     n_loci = int(min(sb.n_loci, max(probe_loci, target_s * rate / max(info["n_pairs"] / sb.n_loci, 1))))
     pairs, dt = cpu_sample_run(sb, bcs, cfg, n_loci, threads)
-    return {"value": pairs / dt, "unit": UNIT, "cores": threads, "kind": "port",
+    p1, d1 = cpu_sample_run(sb, bcs, cfg, min(sb.n_loci, 160), 1)          # the reference's default is --threads 1 (main.rs:107-111)
+    return {"value": pairs / dt, "unit": UNIT, "cores": threads, "kind": "port", "value_1thread": p1 / d1,
             "sample": f"first {n_loci} loci of the shard ({pairs} pairs, {dt:.1f} s); full-matrix SW C port of the reference "
-                      f"algorithm (oracle/vtx_oracle.c), static locus chunks like main.rs:250-254, {threads} threads"}
+                      f"algorithm (oracle/vtx_oracle.c), static locus chunks like main.rs:250-254, {threads} threads; "
+                      f"value_1thread from {p1} pairs in {d1:.1f} s"}
 
 
 def run_reference(args):
