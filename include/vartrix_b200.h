@@ -67,9 +67,10 @@ typedef struct vtx_config {
 } vtx_config;
 
 #define VTX_F_KEEP_SCORES 1u    /* also keep per-pair raw scores on the device (debug / parity) */
-#define VTX_F_NO_SPLIT    2u    /* do not use the two-phase (shared-prefix) Smith-Waterman kernels */
+#define VTX_F_NO_SPLIT    2u    /* use only the single-phase Smith-Waterman kernels (neither shared-prefix nor folded) */
 #define VTX_F_VALUES_ONLY 4u    /* vtx_finish / vtx_fetch copy only row, col, val (and val2 in coverage mode) to the host;
                                    ref_cnt / alt_cnt / unk_cnt come back NULL (halves the device->host traffic) */
+#define VTX_F_NO_FOLD     8u    /* do not use the folded (shared prefix AND suffix) Smith-Waterman kernel */
 
 /*
  * One staged shard of loci.  SoA; for vtx_submit the pointers are HOST pointers (ideally pinned, see
@@ -194,6 +195,10 @@ typedef struct vtx_timing {
     uint64_t total_launches;
 } vtx_timing;
 int         vtx_last_timing(vtx_ctx* ctx, vtx_timing* out);
+/* Warp tiles each Smith-Waterman kernel class got in the most recent submit / vtx_score_pairs (diagnostic: which
+ * kernels took the work).  out[c] for c < n_out: 0..3 single-phase tile classes (4 pairs per tile), 4 generic
+ * (16 pairs), 5..6 shared-prefix kernels (8 pairs), 7 folded kernel (4 pairs).  Returns the number of classes. */
+int         vtx_last_tile_counts(vtx_ctx* ctx, uint32_t* out, uint32_t n_out);
 
 /* ---- multi-GPU: loci are sharded across ranks; one allgatherv of finished triplets ------------- */
 /* Every rank calls vtx_comm_init with the same 128-byte id (made by vtx_comm_unique_id on one rank

@@ -82,6 +82,8 @@ def lib():
         L = ctypes.CDLL(path)
         L.vtxo_sw_full.restype = ctypes.c_int32
         L.vtxo_sw_full.argtypes = [ctypes.c_char_p, ctypes.c_int32, ctypes.c_char_p, ctypes.c_int32]
+        L.vtxo_sw_fold.restype = ctypes.c_int32
+        L.vtxo_sw_fold.argtypes = [ctypes.c_char_p, ctypes.c_int32, ctypes.c_char_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]
         L.vtxo_sw_band_model.restype = ctypes.c_int32
         L.vtxo_sw_band_model.argtypes = [ctypes.c_char_p, ctypes.c_int32, ctypes.c_char_p, ctypes.c_int32,
                                          ctypes.c_int32, ctypes.c_int32]
@@ -255,6 +257,11 @@ def score_pairs(batch: Batch, pair_read: np.ndarray, pair_locus: np.ndarray, n_t
 
 def sw_full(x: bytes, y: bytes) -> int:
     return lib().vtxo_sw_full(x, len(x), y, len(y))
+
+
+def sw_fold(x: bytes, y: bytes, p: int, s: int) -> int:
+    """The same score through the prefix / reversed-suffix / middle / junction decomposition (vtxo_sw_fold)."""
+    return lib().vtxo_sw_fold(x, len(x), y, len(y), p, s)
 
 
 def sw_band_model(x: bytes, y: bytes, k: int = 6, w: int = 20) -> int:

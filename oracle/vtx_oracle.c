@@ -15,6 +15,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
+#include <stddef.h>
 
 #define NEG_INF (-(1 << 28))
 
@@ -59,6 +60,58 @@ int32_t vtxo_sw_full(const uint8_t* x, int32_t m, const uint8_t* y, int32_t n)
         }
     }
     if (S != stack_s) { free(S); free(I); }
+    return best;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * "Fold" decomposition of the same score (CHECKER for the GPU kernel vtx_k_sw_fold, which relies on
+ * it; the decomposition itself is proven in DESIGN.md and pinned numerically by tests/test_fold_math_cpu.py):
+ *   columns [0, P)      forward DP            -> last column (H, D) per row + maximum
+ *   columns [n - S, n)  DP of the REVERSED read against the reversed columns -> (Hr, Dr) per row + maximum
+ *   columns [P, n - S)  forward DP continued from the forward boundary
+ *   junction            max_i  max( H(i, last) + Hr(i + 1),  D(i, last) + Dr(i + 1) - go )
+ * (D = horizontal-gap state; "- go" because a gap running across the junction was opened on both sides).
+ * Any P + S <= n gives vtxo_sw_full(x, m, y, n).
+ * ------------------------------------------------------------------------------------------ */
+static int32_t fold_pass(const uint8_t* x, int32_t m, int32_t xstep, const uint8_t* y, int32_t ncol, int32_t ystep,
+                         int32_t* H, int32_t* D /* in: boundary left of the first column; out: last column; [m + 1] */)
+{
+    /* x[i * xstep], y[j * ystep]: a pass over ncol columns continuing from the boundary column (H, D) */
+    const int32_t go = VTXO_GAP_OPEN, ge = VTXO_GAP_EXTEND;
+    int32_t best = 0;
+    for (int32_t j = 0; j < ncol; ++j) {
+        const uint8_t yj = y[(ptrdiff_t)j * ystep];
+        int32_t diag = H[0], ins = NEG_INF;           /* row 0: H = 0 */
+        for (int32_t i = 1; i <= m; ++i) {
+            const int32_t left = H[i];
+            const int32_t d = imax(D[i] + ge, left + go + ge);
+            ins = imax(ins + ge, H[i - 1] + go + ge);  /* H[i-1] already holds this column */
+            int32_t s = diag + (x[(ptrdiff_t)(i - 1) * xstep] == yj ? VTXO_MATCH : VTXO_MISMATCH);
+            s = imax(imax(s, ins), imax(d, 0));
+            diag = left;
+            H[i] = s; D[i] = d;
+            if (s > best) best = s;
+        }
+    }
+    return best;
+}
+
+int32_t vtxo_sw_fold(const uint8_t* x, int32_t m, const uint8_t* y, int32_t n, int32_t P, int32_t S)
+{
+    if (m <= 0 || n <= 0) return 0;
+    if (P < 0 || S < 0 || P + S > n) return -1;
+    int32_t* buf = (int32_t*)malloc(sizeof(int32_t) * 4 * (size_t)(m + 2));
+    int32_t *Hf = buf, *Df = Hf + (m + 2), *Hr = Df + (m + 2), *Dr = Hr + (m + 2);
+    for (int32_t i = 0; i <= m + 1; ++i) { Hf[i] = 0; Df[i] = NEG_INF; Hr[i] = 0; Dr[i] = NEG_INF; }
+    int32_t best = fold_pass(x, m, 1, y, P, 1, Hf, Df);                                   /* prefix */
+    if (S > 0) best = imax(best, fold_pass(x + (m - 1), m, -1, y + (n - 1), S, -1, Hr, Dr)); /* reversed suffix */
+    best = imax(best, fold_pass(x, m, 1, y + P, n - S - P, 1, Hf, Df));                   /* middle, from the boundary */
+    /* junction: forward row i (1-based) meets reversed row m - i */
+    for (int32_t i = 1; i <= m - 1; ++i) {
+        best = imax(best, Hf[i] + Hr[m - i]);
+        if (Df[i] > NEG_INF / 2 && Dr[m - i] > NEG_INF / 2) best = imax(best, Df[i] + Dr[m - i] - VTXO_GAP_OPEN);
+    }
+    free(buf);
     return best;
 }
 

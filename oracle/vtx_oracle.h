@@ -72,6 +72,10 @@ typedef struct vtxo_metrics {      /* main.rs:449-459 (device-side subset) */
 /* Affine local Smith-Waterman score, byte equality, full matrix (see header comment). */
 int32_t vtxo_sw_full(const uint8_t* x, int32_t m, const uint8_t* y, int32_t n);
 
+/* The same score through the prefix / reversed-suffix / middle / junction decomposition the GPU fold kernel uses
+ * (any P + S <= n); exists so that the decomposition is pinned on the CPU against vtxo_sw_full. */
+int32_t vtxo_sw_fold(const uint8_t* x, int32_t m, const uint8_t* y, int32_t n, int32_t P, int32_t S);
+
 /* Best-effort model of bio 0.30.0's band (k-mer seeds, sparse chain, +-w band, lazy ends);
  * DIAGNOSTIC ONLY -- used to count pairs whose banded score could differ from the full one. */
 int32_t vtxo_sw_band_model(const uint8_t* x, int32_t m, const uint8_t* y, int32_t n, int32_t k, int32_t w);

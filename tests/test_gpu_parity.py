@@ -131,11 +131,123 @@ def test_random_pairs_bit_exact(vb, oracle, name, kw):
     sb, pr, pl = _random_pairs_batch(vb, rng, **kw)
     perm = rng.permutation(len(pr))                 # arbitrary pair order is allowed
     ors, oas = oracle.score_pairs(to_oracle_batch(oracle, sb), pr[perm], pl[perm], n_threads=8)
-    for no_split in (False, True):                  # two-phase (shared-prefix) kernels and the single-phase classes
-        with vb.Engine("coverage", no_split=no_split) as eng:
+    # folded + shared-prefix kernels where the windows allow, shared-prefix only, single-phase classes only
+    for kw_eng in (dict(), dict(no_fold=True), dict(no_split=True)):
+        with vb.Engine("coverage", **kw_eng) as eng:
             rs, as_ = eng.score_pairs(sb, pr[perm], pl[perm])
         bad = np.nonzero((rs.astype(np.int32) != ors) | (as_.astype(np.int32) != oas))[0]
-        assert bad.size == 0, (name, no_split, bad[:5], rs[bad[:5]], ors[bad[:5]], as_[bad[:5]], oas[bad[:5]])
+        assert bad.size == 0, (name, kw_eng, bad[:5], rs[bad[:5]], ors[bad[:5]], as_[bad[:5]], oas[bad[:5]])
+
+
+# ------------------------------------------------------------------------------------------------
+# windows the folded kernel takes: both flanks (>= 96 columns) common to ref and alt, 1..40 allele columns
+# ------------------------------------------------------------------------------------------------
+def _edited(rng, src, alpha, sub, indel):
+    out = []
+    for b in src:
+        u = rng.random()
+        if u < sub:
+            out.append(alpha[rng.integers(0, len(alpha))])
+        elif u < sub + indel:
+            continue
+        elif u < sub + 2 * indel:
+            out.append(b); out.extend(alpha[rng.integers(0, len(alpha), int(rng.integers(1, 6)))])
+        else:
+            out.append(b)
+    return np.array(out, np.uint8)
+
+
+def _fold_pairs_batch(vb, rng, n_loci, reads_per_locus, m_lo, m_hi, mid_lo, mid_hi, flank_lo=96, flank_hi=96, alphabet=b"ACGT",
+                      same_mid_len=False, sub=0.01, indel=0.004, related_mid=True):
+    haps, ref_off, ref_len, alt_off, alt_len = bytearray(), [], [], [], []
+    nibs, read_off, read_len = bytearray(), [], []
+    alpha = np.frombuffer(alphabet, np.uint8)
+    enc = {ord("A"): 1, ord("C"): 2, ord("G"): 4, ord("T"): 8, ord("N"): 15}
+    for l in range(n_loci):
+        left = alpha[rng.integers(0, len(alpha), int(rng.integers(flank_lo, flank_hi + 1)))]
+        right = alpha[rng.integers(0, len(alpha), int(rng.integers(flank_lo, flank_hi + 1)))]
+        lr = int(rng.integers(mid_lo, mid_hi + 1)); la = lr if same_mid_len else int(rng.integers(mid_lo, mid_hi + 1))
+        mr = alpha[rng.integers(0, len(alpha), lr)]
+        if related_mid:                                  # SNV / indel like: the alt allele is an edit of the ref allele
+            ma = np.resize(mr, la).copy()
+            ma[int(rng.integers(0, la))] = alpha[rng.integers(0, len(alpha))]
+        else:
+            ma = alpha[rng.integers(0, len(alpha), la)]
+        ref = np.concatenate([left, mr, right]); alt = np.concatenate([left, ma, right])
+        for h, offs, lens in ((ref, ref_off, ref_len), (alt, alt_off, alt_len)):
+            while len(haps) % 16: haps.append(0)
+            offs.append(len(haps)); lens.append(len(h)); haps.extend(h.tobytes())
+        for _ in range(reads_per_locus):
+            m = int(rng.integers(m_lo, m_hi + 1))
+            src = ref if rng.random() < 0.5 else alt
+            u = rng.random()
+            if u < 0.1:
+                seq = alpha[rng.integers(0, len(alpha), m)]
+            else:                                        # a stretch of a haplotype (possibly hanging over an end) with edits
+                s0 = int(rng.integers(-20, len(src) - 10))
+                seq = np.array([src[j] if 0 <= j < len(src) else alpha[rng.integers(0, len(alpha))] for j in range(s0, s0 + m + 8)], np.uint8)
+                seq = _edited(rng, seq, alpha, sub, indel)[:m]
+            if u > 0.97 and len(seq):
+                seq = seq.copy(); seq[int(rng.integers(0, len(seq)))] = ord("N")
+            m = len(seq)
+            codes = np.array([enc[int(c)] for c in seq], np.uint8)
+            if m & 1: codes = np.concatenate([codes, np.zeros(1, np.uint8)])
+            while len(nibs) % 16: nibs.append(0)
+            read_off.append(len(nibs)); read_len.append(m)
+            nibs.extend(((codes[0::2] << 4) | codes[1::2]).astype(np.uint8).tobytes())
+    while len(nibs) % 16: nibs.append(0)
+    n_reads = len(read_len)
+    sb = vb.StagedBatch(
+        locus_row=np.arange(n_loci), hap_bytes=np.frombuffer(bytes(haps), np.uint8), ref_off=ref_off, ref_len=ref_len,
+        alt_off=alt_off, alt_len=alt_len, cand_start=np.arange(n_loci + 1, dtype=np.uint64) * reads_per_locus,
+        read_nib=np.frombuffer(bytes(nibs), np.uint8), read_off=read_off, read_len=read_len, cb_bytes=np.zeros(0, np.uint8),
+        read_cb_off=np.full(n_reads, vb.engine.NO_CB), read_cb_len=np.zeros(n_reads),
+        read_umi_key=np.full(n_reads, vb.engine.NO_UMI, np.uint64), cand_read=np.arange(n_reads), n_rows=n_loci)
+    pr = np.arange(n_reads, dtype=np.uint32); pl = np.repeat(np.arange(n_loci), reads_per_locus).astype(np.uint32)
+    return sb, pr, pl
+
+
+@pytest.mark.parametrize("name,kw,all_fold", [
+    ("snv_pad100", dict(n_loci=60, reads_per_locus=13, m_lo=140, m_hi=151, mid_lo=9, mid_hi=9, same_mid_len=True), True),
+    ("indel_pad100", dict(n_loci=60, reads_per_locus=9, m_lo=100, m_hi=152, mid_lo=9, mid_hi=40), True),
+    ("complex_alleles", dict(n_loci=60, reads_per_locus=7, m_lo=30, m_hi=152, mid_lo=1, mid_hi=40, related_mid=False), True),
+    ("shortest_middle", dict(n_loci=40, reads_per_locus=6, m_lo=1, m_hi=152, mid_lo=1, mid_hi=2), True),
+    ("noisy_reads_gaps_across_the_junctions", dict(n_loci=50, reads_per_locus=9, m_lo=80, m_hi=152, mid_lo=1, mid_hi=40,
+                                                   sub=0.03, indel=0.03), True),
+    ("low_complexity", dict(n_loci=40, reads_per_locus=9, m_lo=60, m_hi=152, mid_lo=1, mid_hi=30, alphabet=b"AC",
+                            sub=0.02, indel=0.02), True),
+    ("homopolymer", dict(n_loci=20, reads_per_locus=6, m_lo=60, m_hi=152, mid_lo=1, mid_hi=30, alphabet=b"A"), True),
+    ("wider_flanks_and_too_wide", dict(n_loci=60, reads_per_locus=6, m_lo=100, m_hi=152, mid_lo=1, mid_hi=30, flank_lo=96,
+                                       flank_hi=110), False),
+])
+def test_fold_windows_bit_exact(vb, oracle, name, kw, all_fold):
+    rng = np.random.default_rng(sum(map(ord, name)) + 7)
+    sb, pr, pl = _fold_pairs_batch(vb, rng, **kw)
+    perm = rng.permutation(len(pr))
+    ors, oas = oracle.score_pairs(to_oracle_batch(oracle, sb), pr[perm], pl[perm], n_threads=8)
+    for kw_eng in (dict(), dict(no_fold=True)):
+        with vb.Engine("coverage", **kw_eng) as eng:
+            rs, as_ = eng.score_pairs(sb, pr[perm], pl[perm])
+            tiles = eng.tile_counts()
+        bad = np.nonzero((rs.astype(np.int32) != ors) | (as_.astype(np.int32) != oas))[0]
+        assert bad.size == 0, (name, kw_eng, bad[:5], rs[bad[:5]], ors[bad[:5]], as_[bad[:5]], oas[bad[:5]])
+        if kw_eng:
+            assert tiles[7] == 0 and sum(tiles) > 0
+        elif all_fold:                                  # every locus of these families must take the folded kernel
+            assert tiles[7] > 0 and sum(tiles) == tiles[7], tiles
+        else:
+            assert tiles[7] > 0 and sum(tiles) > tiles[7], tiles
+
+
+def test_fold_falls_back_for_long_reads(vb, oracle):
+    rng = np.random.default_rng(99)
+    sb, pr, pl = _fold_pairs_batch(vb, rng, n_loci=10, reads_per_locus=5, m_lo=150, m_hi=200, mid_lo=9, mid_hi=9, same_mid_len=True)
+    assert int(sb.read_len.max()) > 152
+    ors, oas = oracle.score_pairs(to_oracle_batch(oracle, sb), pr, pl, n_threads=8)
+    with vb.Engine("coverage") as eng:
+        rs, as_ = eng.score_pairs(sb, pr, pl)
+        assert eng.tile_counts()[7] == 0
+    assert np.array_equal(rs.astype(np.int32), ors) and np.array_equal(as_.astype(np.int32), oas)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -149,6 +261,7 @@ def test_synthetic_shard_matches_oracle(vb, oracle, mode, kind, umi):
     exp = _oracle_run(oracle, sb, bcs, mode, umi)
     assert_same_triplets(got, exp)
     assert_same_triplets(_run_engine(vb, sb, bcs, mode, umi, no_split=True), exp)
+    assert_same_triplets(_run_engine(vb, sb, bcs, mode, umi, no_fold=True), exp)
     assert got.metrics == exp.metrics and got.metrics["num_scored"] == info["n_pairs"]
     # text output is byte-identical to the oracle's writer as well
     assert vb.mtx.mtx_text(sb.n_rows, len(bcs), got.row, got.col, got.val) == oracle.mtx_text(sb.n_rows, len(bcs), exp.row, exp.col, exp.val)
@@ -328,7 +441,7 @@ def test_fuzz_whole_path_against_oracle(vb, oracle):
         bcs = vb.Barcodes(keys)
         mode = ("consensus", "coverage", "alt_frac")[it % 3]
         use_umi = bool(it & 1)
-        got = _run_engine(vb, shard, bcs, mode, use_umi, no_split=bool(it & 2))
+        got = _run_engine(vb, shard, bcs, mode, use_umi, no_split=bool(it & 2), no_fold=bool(it & 4))
         exp = _oracle_run(oracle, shard, bcs, mode, use_umi, threads=4)
         assert_same_triplets(got, exp)
         assert got.metrics == exp.metrics, it

@@ -21,7 +21,7 @@ def child(npz, steps):
     sb = vb.StagedBatch(n_rows=int(z["n_rows"]), **{f: z[f] for f in vb.StagedBatch.FIELDS})
     bcs = vb.Barcodes([bytes(k) for k in z["keys"]])
     stream = torch.cuda.Stream()
-    eng = vb.Engine(str(z["mode"]), umi=bool(z["umi"]), stream=stream.cuda_stream, no_split=bool(os.environ.get("VTX_NO_SPLIT")))
+    eng = vb.Engine(str(z["mode"]), umi=bool(z["umi"]), stream=stream.cuda_stream, no_split=bool(os.environ.get("VTX_NO_SPLIT")), no_fold=bool(os.environ.get("VTX_NO_FOLD")))
     eng.set_barcodes(bcs)
     dev = {}
     db = sb.to_c()
@@ -40,7 +40,7 @@ def child(npz, steps):
         tot.append((time.perf_counter() - t0) * 1e3)
         sw.append(eng.timing()["sw_ms"])
     n = int(r.metrics.num_scored)
-    print(json.dumps(dict(lib=os.environ.get("VTX_LIB", "default"), no_split=bool(os.environ.get("VTX_NO_SPLIT")), pairs=n, sw_ms=float(np.median(sw)), step_ms=float(np.median(tot)),
+    print(json.dumps(dict(lib=os.environ.get("VTX_LIB", "default"), no_split=bool(os.environ.get("VTX_NO_SPLIT")), no_fold=bool(os.environ.get("VTX_NO_FOLD")), pairs=n, sw_ms=float(np.median(sw)), step_ms=float(np.median(tot)),
                           mpairs_s_kernel=n / np.median(sw) / 1e3, checksum=int(r.n))))
 
 

@@ -21,12 +21,13 @@ NO_UMI = 0xFFFFFFFFFFFFFFFF
 F_KEEP_SCORES = 1
 F_NO_SPLIT = 2
 F_VALUES_ONLY = 4
+F_NO_FOLD = 8
 
 # every symbol include/vartrix_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "vtx_abi_version", "vtx_create", "vtx_destroy", "vtx_last_error", "vtx_host_alloc", "vtx_host_free",
     "vtx_set_barcodes", "vtx_submit", "vtx_submit_device", "vtx_submit_device_ex", "vtx_finish",
-    "vtx_finish_device", "vtx_fetch", "vtx_sync", "vtx_wait_copies", "vtx_score_pairs", "vtx_pack_umi", "vtx_last_timing",
+    "vtx_finish_device", "vtx_fetch", "vtx_sync", "vtx_wait_copies", "vtx_score_pairs", "vtx_pack_umi", "vtx_last_timing", "vtx_last_tile_counts",
     "vtx_comm_unique_id", "vtx_comm_init", "vtx_gather",
 ]
 
@@ -109,6 +110,8 @@ def load():
     L.vtx_pack_umi.argtypes = [C.c_char_p, C.c_uint32]
     L.vtx_last_timing.restype = C.c_int
     L.vtx_last_timing.argtypes = [C.c_void_p, C.POINTER(Timing)]
+    L.vtx_last_tile_counts.restype = C.c_int
+    L.vtx_last_tile_counts.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.c_uint32]
     L.vtx_comm_unique_id.restype = C.c_int
     L.vtx_comm_unique_id.argtypes = [C.c_void_p]
     L.vtx_comm_init.restype = C.c_int

@@ -81,6 +81,8 @@ struct vtx_ctx {
     std::vector<TimeRec> trecs;     // one per submit since the last finish (events are reused)
     size_t trec_used = 0;
     bool timing_valid = false;
+    uint32_t last_tiles_nl = 0;       // loci of the most recent run_sw (vtx_last_tile_counts)
+    bool last_tiles_valid = false;
     uint64_t t_pairs = 0;
 
     // multi-GPU (vtx_comm.cpp)
@@ -203,6 +205,20 @@ int launch_sw_split(vtx_ctx* ctx, SwArgs a, uint64_t* launches)
     return VTX_OK;
 }
 
+int launch_sw_fold(vtx_ctx* ctx, SwArgs a, uint64_t* launches)
+{
+    const size_t smem = fold_warp_bytes() * (kFoldThreads / 32);
+    auto kern = vtx_k_sw_fold;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kFoldThreads, smem));
+    if (per_sm < 1) return set_err(ctx, VTX_E_CUDA, "folded SW kernel does not fit on an SM (smem %zu)", smem);
+    kern<<<ctx->n_sm * per_sm, kFoldThreads, smem, ctx->stream>>>(a);
+    CK(cudaGetLastError());
+    ++*launches;
+    return VTX_OK;
+}
+
 // classes + tiles + SW kernels, shared by submit and score_pairs.  pair_start must be ready.
 int run_sw(vtx_ctx* ctx, const DevBatch& b, uint32_t n_pairs_ub, const uint32_t* pair_slot, uint32_t* counters,
            uint32_t* pair_scores, uint64_t* launches, uint64_t* sw_launches, TimeRec* tr)
@@ -214,14 +230,17 @@ int run_sw(vtx_ctx* ctx, const DevBatch& b, uint32_t n_pairs_ub, const uint32_t*
     const int force_slow = 0;       // reads of any supported length run on the single-phase classes (row blocks)
     const int allow_split = (b.max_read_len <= uint32_t(kSplitMaxRead) && !(ctx->cfg.flags & VTX_F_NO_SPLIT)) ? 1 : 0;
     const int allow_multi = (b.max_read_len <= uint32_t(kMultiMaxRead) && b.max_hap_len > uint32_t(class_max_n(kNumFastClasses - 1))) ? 1 : 0;
+    const int allow_fold = (b.max_read_len <= uint32_t(kFoldMaxRead) && !(ctx->cfg.flags & (VTX_F_NO_SPLIT | VTX_F_NO_FOLD))) ? 1 : 0;
     vtx_k_locus_prep<<<blocks_for(uint64_t(nl) * 32, 256), 256, 0, ctx->stream>>>(
         nl, b.hap, b.ref_off, b.ref_len, b.alt_off, b.alt_len, P<uint32_t>(ctx->pair_start), force_slow, allow_split, allow_multi,
-        P<uint32_t>(ctx->tcount));
+        allow_fold, P<uint32_t>(ctx->tcount));
     ++*launches;
     vtx_k_scan_rows<<<kNumClasses, kScanThreads, 0, ctx->stream>>>(P<uint32_t>(ctx->tcount), P<uint32_t>(ctx->tstart), nl, nl + 1);
     ++*launches;
     CK(cudaGetLastError());
     CK(cudaMemsetAsync(ctx->tile_counters.p, 0, 64, ctx->stream));
+    ctx->last_tiles_nl = nl;
+    ctx->last_tiles_valid = true;
     if (tr) CK(cudaEventRecord(tr->ev[EV_PREP], ctx->stream));
 
     SwArgs a{};
@@ -258,6 +277,12 @@ int run_sw(vtx_ctx* ctx, const DevBatch& b, uint32_t n_pairs_ub, const uint32_t*
             int rc = c == 0 ? launch_sw_split<0>(ctx, a, launches) : launch_sw_split<1>(ctx, a, launches);
             if (rc) return rc;
         }
+    }
+    if (allow_fold) {
+        a.tile_start = P<uint32_t>(ctx->tstart) + size_t(kFoldClass) * (nl + 1);
+        a.tile_counter = P<uint32_t>(ctx->tile_counters) + kFoldClass;
+        int rc = launch_sw_fold(ctx, a, launches);
+        if (rc) return rc;
     }
     {   // generic class (rare)
         const unsigned blocks = unsigned(ctx->n_sm) * 4, threads = 128;
@@ -881,6 +906,21 @@ int vtx_finish(vtx_ctx* ctx, vtx_result* out)
     out->val = static_cast<double*>(ctx->h_res[5]); out->val2 = want[6] ? static_cast<double*>(ctx->h_res[6]) : nullptr;
     out->metrics = dev.metrics;
     return VTX_OK;
+}
+
+int vtx_last_tile_counts(vtx_ctx* ctx, uint32_t* out, uint32_t n_out)
+{
+    if (!ctx || !out) return VTX_E_INVALID;
+    if (!ctx->last_tiles_valid) return set_err(ctx, VTX_E_STATE, "no Smith-Waterman pass has run yet");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const uint32_t nl = ctx->last_tiles_nl;
+    for (uint32_t c = 0; c < n_out; ++c) {
+        out[c] = 0;
+        if (c < uint32_t(kNumClasses))
+            CK(cudaMemcpy(out + c, P<uint32_t>(ctx->tstart) + size_t(c) * (nl + 1) + nl, 4, cudaMemcpyDeviceToHost));
+    }
+    return kNumClasses;
 }
 
 int vtx_last_timing(vtx_ctx* ctx, vtx_timing* t)

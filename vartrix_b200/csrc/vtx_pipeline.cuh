@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 #include "vtx_sw.cuh"
 #include "vtx_sw_split.cuh"
+#include "vtx_sw_fold.cuh"
 
 namespace vtx {
 
@@ -142,7 +143,7 @@ __global__ void vtx_k_pair_start_explicit(uint32_t n_loci, uint32_t n_pairs, con
 __global__ void vtx_k_locus_prep(uint32_t n_loci, const uint8_t* __restrict__ hap_bytes,
                                  const uint32_t* __restrict__ ref_off, const uint32_t* __restrict__ ref_len,
                                  const uint32_t* __restrict__ alt_off, const uint32_t* __restrict__ alt_len,
-                                 const uint32_t* __restrict__ pair_start, int force_slow, int allow_split, int allow_multi,
+                                 const uint32_t* __restrict__ pair_start, int force_slow, int allow_split, int allow_multi, int allow_fold,
                                  uint32_t* __restrict__ tcount /* [kNumClasses][n_loci + 1] */)
 {
     const uint32_t l = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -164,6 +165,10 @@ __global__ void vtx_k_locus_prep(uint32_t n_loci, const uint8_t* __restrict__ ha
     bool same = nr >= uint32_t(kSplitP) && na >= uint32_t(kSplitP);
     if (same) for (uint32_t j = lane; j < uint32_t(kSplitP); j += 32) same &= (rh[j] == ah[j]);
     same = __all_sync(0xffffffffu, same);
+    // ... and the last kFoldP columns (same right flank)?  Then neither flank needs a per-haplotype DP (vtx_sw_fold.cuh).
+    bool fold = same && allow_fold && min(nr, na) > uint32_t(2 * kFoldP) && max(nr, na) <= uint32_t(2 * kFoldP + kFoldMaxMid);
+    if (fold) for (uint32_t j = lane; j < uint32_t(kFoldP); j += 32) fold &= (rh[nr - 1 - j] == ah[na - 1 - j]);
+    fold = __all_sync(0xffffffffu, fold);
     if (lane != 0) return;
     const uint32_t nmax = max(nr, na);
     int cls = kSlowClass;
@@ -175,11 +180,12 @@ __global__ void vtx_k_locus_prep(uint32_t n_loci, const uint8_t* __restrict__ ha
 #pragma unroll
             for (int c = kNumSplitClasses - 1; c >= 0; --c) if (nmax <= uint32_t(split_max_n(c))) cls = kSplitClass0 + c;
         }
+        if (fold) cls = kFoldClass;
     }
     const uint32_t np = pair_start[l + 1] - pair_start[l];
 #pragma unroll
     for (int c = 0; c < kNumClasses; ++c) {
-        const uint32_t ppw = (c == kSlowClass) ? uint32_t(kSlowPairsPerWarp) : (c > kSlowClass ? uint32_t(kSplitPPW) : 4u);
+        const uint32_t ppw = (c == kSlowClass) ? uint32_t(kSlowPairsPerWarp) : (c == kFoldClass ? uint32_t(kFoldPPW) : (c > kSlowClass ? uint32_t(kSplitPPW) : 4u));
         tcount[size_t(c) * (n_loci + 1) + l] = (c == cls) ? (np + ppw - 1) / ppw : 0u;
     }
 }

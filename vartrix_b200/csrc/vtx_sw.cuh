@@ -76,7 +76,8 @@ constexpr int kNumFastClasses = 4;                 // single-phase tile classes 
 constexpr int kSlowClass = kNumFastClasses;        // 4: generic kernel
 constexpr int kNumSplitClasses = 2;                // 5, 6: two-phase kernels (vtx_sw_split.cuh)
 constexpr int kSplitClass0 = kSlowClass + 1;
-constexpr int kNumClasses = kSplitClass0 + kNumSplitClasses;
+constexpr int kFoldClass = kSplitClass0 + kNumSplitClasses;   // 7: folded kernel (vtx_sw_fold.cuh)
+constexpr int kNumClasses = kFoldClass + 1;
 constexpr int kTileChunk = 8;            // most tiles grabbed per atomic
 
 // fast tile classes: lanes per pair, columns per lane, storage stride (words; CS % 4 == 0, (CS/4) odd

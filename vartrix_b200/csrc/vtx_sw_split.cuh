@@ -36,6 +36,9 @@ template <int SCLS> struct SplitClass;
 #ifndef VTX_SPLIT1_COPIES
 #define VTX_SPLIT1_COPIES 1
 #endif
+#ifndef VTX_SPLIT_ONLY
+#define VTX_SPLIT_ONLY 0         // 1 / 2: run only phase 1 / phase 2 (timing experiments; results are wrong)
+#endif
 #ifndef VTX_SPLIT1_THREADS
 #define VTX_SPLIT1_THREADS 256
 #endif
@@ -165,7 +168,11 @@ __global__ void __launch_bounds__(SplitClass<SCLS>::THREADS, SplitClass<SCLS>::M
                 const uint8_t* cB = codes + (2 * u + 1) * code_stride + M - g;
                 const uint32_t* lane_prof = prof1 + g * C1;
                 uint2* my_bnd = bnd + u * bnd_stride;
+#if VTX_SPLIT_ONLY == 2
+                const int steps = 0;                                         // timing experiment: phase 2 alone
+#else
                 const int steps = mmax + 7;
+#endif
                 for (int t = 0; t < steps; ++t) {
                     uint32_t hl = __shfl_up_sync(0xffffffffu, hg_last, 1, 8);
                     uint32_t el = __shfl_up_sync(0xffffffffu, e_last, 1, 8);
@@ -227,7 +234,11 @@ __global__ void __launch_bounds__(SplitClass<SCLS>::THREADS, SplitClass<SCLS>::M
                 const uint8_t* cR = codes + r * code_stride + M - g;
                 const uint32_t* lane_prof = prof2 + (w ? COPY2 : 0) + g * CS2;
                 const uint2* my_bnd = bnd + u * bnd_stride;
+#if VTX_SPLIT_ONLY == 1
+                const int steps = 0;                                         // timing experiment: phase 1 alone
+#else
                 const int steps = mmax + 3;
+#endif
                 for (int t = 0; t < steps; ++t) {
                     uint32_t hl = __shfl_up_sync(0xffffffffu, hg_last, 1, 4);
                     uint32_t el = __shfl_up_sync(0xffffffffu, e_last, 1, 4);

@@ -193,12 +193,12 @@ class Engine:
 
     def __init__(self, scoring_method: str = "consensus", umi: bool = False, device: int = 0, stream: int = 0,
                  keep_scores: bool = False, min_score: int = 25, no_split: bool = False,
-                 values_only: bool = False):
+                 values_only: bool = False, no_fold: bool = False):
         self._L = _capi.load()
         cfg = _capi.Config(device=device, mode=MODES[scoring_method], use_umi=int(bool(umi)), match=1, mismatch=-5,
                            gap_open=-5, gap_extend=-1, min_score=min_score, stream=stream or None,
                            flags=(_capi.F_KEEP_SCORES if keep_scores else 0) | (_capi.F_NO_SPLIT if no_split else 0) |
-                           (_capi.F_VALUES_ONLY if values_only else 0))
+                           (_capi.F_VALUES_ONLY if values_only else 0) | (_capi.F_NO_FOLD if no_fold else 0))
         h = C.c_void_p()
         rc = self._L.vtx_create(C.byref(cfg), C.byref(h))
         if rc != 0:
@@ -265,6 +265,14 @@ class Engine:
         self._ck(self._L.vtx_last_timing(self._h, C.byref(t)), "vtx_last_timing")
         return dict(h2d_ms=t.h2d_ms, prep_ms=t.prep_ms, sw_ms=t.sw_ms, post_ms=t.post_ms, n_pairs=int(t.n_pairs),
                     sw_launches=int(t.sw_launches), total_launches=int(t.total_launches))
+
+    def tile_counts(self) -> list:
+        """Warp tiles per SW kernel class of the last submit / score_pairs (classes: see vtx_last_tile_counts)."""
+        out = (C.c_uint32 * 16)()
+        n = self._L.vtx_last_tile_counts(self._h, out, 16)
+        if n < 0:
+            self._ck(n, "vtx_last_tile_counts")
+        return [int(out[i]) for i in range(n)]
 
     def run(self, batch: StagedBatch) -> Triplets:
         self.submit(batch)
