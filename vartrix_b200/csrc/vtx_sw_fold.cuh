@@ -39,10 +39,13 @@ constexpr int kFoldPPW = 4;            // pairs per warp tile
 constexpr int kFoldR = 19;             // read rows per lane in the middle (8 x 19 = 152)
 constexpr int kFoldMaxRead = 8 * kFoldR;
 constexpr int kFoldMaxMid = 40;        // allele columns: n <= 2 * 96 + 40 = 232
-constexpr int kFoldRows = kFoldMaxRead + 8;          // boundary rows kept per read
+constexpr int kFoldRows = kFoldMaxRead;              // boundary rows kept per read
 constexpr int kFoldCodeStride = kFoldMaxRead + 16;   // row codes per read and direction (8 sentinels either side)
+// 320 threads x 2 CTAs = 20 warps/SM (96 registers, a few spills in the tile prologue only): 9.32 ms vs 9.82 ms at
+// 256 x 2 on the config-3 shape; merging the profile rows with one IADD3 instead of IMAD + add, or unrolling the
+// row loop, does not pay at that occupancy (profiles/r01_fold_variants.txt)
 #ifndef VTX_FOLD_THREADS
-#define VTX_FOLD_THREADS 256
+#define VTX_FOLD_THREADS 320
 #endif
 constexpr int kFoldThreads = VTX_FOLD_THREADS;
 
@@ -176,6 +179,7 @@ __global__ void __launch_bounds__(kFoldThreads, 2) vtx_k_sw_fold(const SwArgs a)
 #pragma unroll
                     for (int q = 0; q < C1 / 4; ++q) {
                         const uint4 a4 = pa[q], b4 = pb[q];
+                        // {s_fwd, s_rev} = s_fwd + (s_rev << 16) as an IMAD (FMA pipe), like vtx_k_sw_split's phase 1
                         const uint32_t sv[4] = { b4.x * k64k + a4.x, b4.y * k64k + a4.y, b4.z * k64k + a4.z, b4.w * k64k + a4.w };
                         uint32_t hh[4];
 #pragma unroll
@@ -270,10 +274,10 @@ __global__ void __launch_bounds__(kFoldThreads, 2) vtx_k_sw_fold(const SwArgs a)
                         if (R & 1) best = __vmaxs2(best, hh[0]);
                         hup_last = hdown;
                         f_last = f;
-                        if (k == lmin - 1 && lmin != lmax) junction(short_mask);
-                        if (k == lmax - 1) junction(lmin != lmax ? ~short_mask : 0xFFFFFFFFu);
+                        if (k == lmin - 1 && lmin != lmax) junction(short_mask);    // the shorter allele ends here (indels only)
                     }
                 }
+                junction(lmin != lmax ? ~short_mask : 0xFFFFFFFFu);                   // every lane has finished column lmax - 1
 #pragma unroll
                 for (int o = 4; o >= 1; o >>= 1) best = __vmaxs2(best, __shfl_xor_sync(0xffffffffu, best, o));
                 if (active && g == 0) call_and_scatter(a, pair, best - kBIAS2);
