@@ -348,7 +348,7 @@ def run_gpu(args):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0)); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6.65 TB/s"
         b_alg = vb.synth.algorithmic_bytes_per_pair(info)
-        traffic, traffic_src, alu_pct, tj_kernel = None, None, None, "vtx_k_sw_split<0>"
+        traffic, traffic_src, alu_pct, tj_kernel = None, None, None, "vtx_k_sw_fold"
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "sw_kernel_traffic.json")))
             traffic = tj["dram_bytes_per_pair"] * n_pairs; traffic_src = tj["source"]; alu_pct = tj.get("alu_pipe_active_pct")
@@ -358,11 +358,24 @@ def run_gpu(args):
         sw_avg_ms = float(np.mean(sw_ms))
         achieved = n_pairs * b_alg / (sw_avg_ms / 1e3) / 1e9
         cells = info["read_len"] * 2 * (2 * 100 + 1)
-        # the bound that actually binds: the ALU pipe.  DPX s16x2 instructions occupy it for 2 cycles per warp and SMSP,
-        # 32-bit VIADD for 1 (profiles/r01_dpx_microbench.txt).  SASS of the two-phase SNV tile (8 pairs): a phase-1
-        # warp-step (12 columns) = 54 DPX + 12 adds, a phase-2 warp-step (27 columns) = 122 DPX + 28 VIADD.
+        # the bound that actually binds: the ALU pipe.  DPX s16x2 instructions (and PRMT) occupy it for 2 cycles per warp
+        # and SMSP, 32-bit VIADD / IADD3 / LOP3 / SEL / ISETP for 1 (profiles/r01_dpx_microbench.txt).  Counted from the SASS
+        # of the kernel that took the work:
+        #   folded kernel, tile = 4 pairs: main-pass warp-step (12 columns, forward | reverse halves) = 54 DPX + 21 -> 129
+        #     cycles, (m + 7) steps; allele-column warp-step (19 rows) = 86 DPX + 28 -> 200 cycles, (L + 7) steps for L allele
+        #     columns; boundary unpack 135; junction 199 (8 more, divergent, when the alleles differ in length)
+        #   two-phase kernel, tile = 8 pairs: phase-1 warp-step 128 cycles x (m + 7), phase-2 warp-step (27 columns) 280 x (m + 3)
         m = info["read_len"]
-        alu_cycles_per_pair = ((m + 7) * (54 * 2 + 12) + (m + 3) * (122 * 2 + 28)) / 8.0
+        tiles = eng.tile_counts()
+        folded = tiles[7] * 4 >= sum(tiles[:4]) * 4 + sum(tiles[5:7]) * 8
+        if folded:
+            lmax = np.maximum(sb.ref_len, sb.alt_len).astype(np.float64) - 192.0
+            uneq = float(np.mean(sb.ref_len != sb.alt_len))
+            alu_cycles_per_pair = ((m + 7) * 129.0 + (float(lmax.mean()) + 7) * 200.0 + 135 + 199 + uneq * 8 * 199) / 4.0
+            model_kernel = "folded SW kernel vtx_k_sw_fold"
+        else:
+            alu_cycles_per_pair = ((m + 7) * 128.0 + (m + 3) * 280.0) / 8.0
+            model_kernel = "two-phase SW kernel vtx_k_sw_split<0>"
         sm_mhz = (clocks or {}).get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
         dpx_peak = torch.cuda.get_device_properties(local).multi_processor_count * 4.0 * sm_mhz * 1e6
         dpx_ach = n_pairs * alu_cycles_per_pair / (sw_avg_ms / 1e3)
@@ -379,7 +392,8 @@ def run_gpu(args):
                          "peak_source": peak_src, "kernel": tj_kernel,
                          "kernel_ms": sw_avg_ms, "algorithmic_bytes_per_pair": b_alg, "pairs_per_launch": n_pairs,
                          "gcups": n_pairs * cells / (sw_avg_ms / 1e3) / 1e9,
-                         "issue_bound": {"what": "ALU-pipe busy cycles/s of the two-phase SW kernel (SASS model: %.0f SMSP-cycles per pair)" % alu_cycles_per_pair,
+                         "issue_bound": {"what": "ALU-pipe busy cycles/s of the %s (SASS model: %.0f SMSP-cycles per pair)" % (model_kernel, alu_cycles_per_pair),
+                                         "tiles_per_kernel_class": tiles,
                                          "achieved": dpx_ach, "peak": dpx_peak, "frac": dpx_ach / dpx_peak,
                                          "peak_source": "n_SM x 4 SMSPs x sampled SM clock; DPX = 2 cycles, VIADD = 1 (measured, profiles/r01_dpx_microbench.txt)"},
                          "note": "integer DP: ~540 cell updates per algorithmic byte, so the kernel is DPX-issue bound, not HBM "
