@@ -47,7 +47,8 @@ def parse_args():
     ap.add_argument("--loci", type=int, default=0, help="override loci per GPU (0 = the config's)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--chunks", type=int, default=8, help="staged shards per step on the e2e path (copy/compute overlap)")
+    ap.add_argument("--chunks", type=int, default=8, help="staged shards per step on the e2e path (copy/compute overlap); with --growth: largest shard = 1/chunks of the step")
+    ap.add_argument("--growth", type=float, default=1.4, help="e2e shards grow geometrically from --first-chunk by this factor (0: equal shards after the first)")
     ap.add_argument("--first-chunk", type=float, default=0.02, help="fraction of the candidates in the first (priming) shard")
     return ap.parse_args()
 
@@ -77,7 +78,7 @@ def describe(args, cfg, world, info):
         "parallelism": (f"loci sharded over {world} GPU(s), one NCCL allgatherv of triplets per step; on the e2e path every rank copies its own "
                         f"row range to its host (h2d/d2h bytes are job totals)") if world > 1 else "1 GPU",
         "l2_policy": "inputs larger than L2 (staged shard >> 126 MB), no explicit flush",
-        "e2e_chunks": args.chunks, "e2e_first_chunk_frac": args.first_chunk, "host_cores_bound_to_gpu": len(os.sched_getaffinity(0)),
+        "e2e_chunks": args.chunks, "e2e_first_chunk_frac": args.first_chunk, "e2e_chunk_growth": args.growth, "host_cores_bound_to_gpu": len(os.sched_getaffinity(0)),
     }
 
 
@@ -258,7 +259,7 @@ def run_gpu(args):
     # double-buffers them so the copy of shard k+1 overlaps the kernels of shard k
     del pinned
     hparts, hkeep, h2d_bytes = [], [], 0
-    for lo, hi in vb.shard_bounds(sb.cand_start, max(1, args.chunks), first_frac=args.first_chunk):
+    for lo, hi in vb.shard_bounds(sb.cand_start, max(1, args.chunks), first_frac=args.first_chunk, growth=args.growth):
         if hi <= lo:
             continue
         part = sb.shard(lo, hi)

@@ -30,6 +30,7 @@ def main(names):
             for p in parts:
                 eng.submit(p)
             got = eng.finish()
+            tiles = eng.tile_counts()
         t_gpu = time.time() - t0
         t0 = time.time()
         ob = P.Batch(**{f: getattr(sb, f) for f in P.Batch.FIELDS}, n_rows=sb.n_rows)
@@ -42,7 +43,7 @@ def main(names):
             h.update(np.ascontiguousarray(getattr(got, f)).tobytes())
         report.append(dict(config=name, loci=cfg["n_loci"], barcodes=cfg["n_barcodes"], mode=cfg["scoring_method"], umi=umi,
                            pairs=got.metrics["num_scored"], triplets=int(len(got.row)), bit_exact_vs_oracle=bool(same),
-                           metrics_equal=bool(got.metrics == exp.metrics), triplets_sha256=h.hexdigest()[:16],
+                           metrics_equal=bool(got.metrics == exp.metrics), triplets_sha256=h.hexdigest()[:16], sw_tiles_per_kernel_class_last_submit=tiles,
                            gpu_wall_s=round(t_gpu, 2), oracle_wall_s=round(t_cpu, 1), oracle_threads=threads))
     print(json.dumps(report, indent=1))
 

@@ -317,21 +317,31 @@ def pack_umi(s: bytes) -> int:
     return int(_capi.load().vtx_pack_umi(s, len(s)))
 
 
-def shard_bounds(cand_start: np.ndarray, n_shards: int, first_frac: float = 0.0):
+def shard_bounds(cand_start: np.ndarray, n_shards: int, first_frac: float = 0.0, growth: float = 0.0):
     """Contiguous locus ranges balanced by candidate count: -> list of (lo, hi).
     first_frac > 0 makes the first shard that small a fraction of the candidates (a staging producer primes the
-    copy/compute pipeline with a small shard so the kernels start early) and balances the rest."""
+    copy/compute pipeline with a small shard so the kernels start early) and balances the rest.
+    growth > 1 (with first_frac > 0) sizes the shards geometrically instead -- first_frac, first_frac * growth, ... --
+    so that the host->device copy of every shard hides behind the kernels of the one before it (copy time per
+    candidate is ~0.7x kernel time, so growth <= 1.4); shards stop growing at 1/n_shards of the total and the number
+    of shards follows from that."""
     n_loci = len(cand_start) - 1
     total = int(cand_start[-1])
-    cuts = [0]
-    for s in range(1, n_shards):
-        if first_frac > 0 and n_shards > 1:
-            target = int(total * (first_frac + (1.0 - first_frac) * (s - 1) / (n_shards - 1)))
-        else:
-            target = total * s // n_shards
-        cuts.append(int(np.searchsorted(cand_start, target, side="left")))
-    cuts.append(n_loci)
+    targets = []
+    if first_frac > 0 and growth > 1.0 and n_shards > 1:
+        acc, f, cap = 0.0, first_frac, 1.0 / n_shards
+        while acc + f < 1.0 - 1e-9:
+            acc += f
+            targets.append(int(total * acc))
+            f = min(f * growth, cap)
+    else:
+        for s in range(1, n_shards):
+            if first_frac > 0 and n_shards > 1:
+                targets.append(int(total * (first_frac + (1.0 - first_frac) * (s - 1) / (n_shards - 1))))
+            else:
+                targets.append(total * s // n_shards)
+    cuts = [0] + [int(np.searchsorted(cand_start, t, side="left")) for t in targets] + [n_loci]
     cuts = [min(max(c, 0), n_loci) for c in cuts]
     for i in range(1, len(cuts)):
         cuts[i] = max(cuts[i], cuts[i - 1])
-    return [(cuts[i], cuts[i + 1]) for i in range(n_shards)]
+    return [(cuts[i], cuts[i + 1]) for i in range(len(cuts) - 1)]
