@@ -47,9 +47,9 @@ def parse_args():
     ap.add_argument("--loci", type=int, default=0, help="override loci per GPU (0 = the config's)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--chunks", type=int, default=8, help="staged shards per step on the e2e path (copy/compute overlap); with --growth: largest shard = 1/chunks of the step")
+    ap.add_argument("--chunks", type=int, default=6, help="staged shards per step on the e2e path (copy/compute overlap); with --growth: largest shard = 1/chunks of the step")
     ap.add_argument("--growth", type=float, default=1.4, help="e2e shards grow geometrically from --first-chunk by this factor (0: equal shards after the first)")
-    ap.add_argument("--first-chunk", type=float, default=0.02, help="fraction of the candidates in the first (priming) shard")
+    ap.add_argument("--first-chunk", type=float, default=0.01, help="fraction of the candidates in the first (priming) shard")
     return ap.parse_args()
 
 
