@@ -149,6 +149,22 @@ def test_synth_shapes_and_shard_invariance(oracle):
     assert vb.shard_bounds(sb.cand_start, 3)[0][0] == 0 and vb.shard_bounds(sb.cand_start, 3)[-1][1] == 30
 
 
+def test_shard_schedules_cover_every_locus_once():
+    import vartrix_b200 as vb
+    rng = np.random.default_rng(4)
+    cs = np.concatenate([[0], np.cumsum(rng.integers(0, 90, size=5000))]).astype(np.uint64)
+    for kw in (dict(n_shards=1), dict(n_shards=7), dict(n_shards=8, first_frac=0.02), dict(n_shards=6, first_frac=0.01, growth=1.4),
+               dict(n_shards=6, first_frac=0.01, growth=1.1), dict(n_shards=3, first_frac=0.5, growth=1.4)):
+        b = vb.shard_bounds(cs, **kw)
+        assert b[0][0] == 0 and b[-1][1] == 5000 and all(b[i][1] == b[i + 1][0] for i in range(len(b) - 1)), kw
+        assert all(hi >= lo for lo, hi in b), kw
+    geo = vb.shard_bounds(cs, 6, first_frac=0.01, growth=1.4)
+    sizes = [int(cs[hi] - cs[lo]) for lo, hi in geo]
+    total = int(cs[-1])
+    assert sizes[0] <= 0.012 * total + 90 and max(sizes) <= total / 6 + 180          # primer, then capped at 1/6 of the step
+    assert all(sizes[i + 1] <= 1.4 * sizes[i] + 180 for i in range(len(sizes) - 2))   # each copy hides behind the shard before it
+
+
 def test_band_model_equals_full_on_synthetic_shards(oracle):
     """on the synthetic workloads (random context, SNVs and <= 30 bp indels) the best-effort model of
     rust-bio's k=6 / w=20 band never clips the optimal path, so full-matrix scores are the banded scores."""
