@@ -1,5 +1,5 @@
-// bam_reader.hpp -- BGZF + BAM + BAI region reader for the staging host (zlib only; htslib is not in
-// this image).  Replaces what rust-htslib 0.36 / C htslib give the reference at
+// bam_reader.hpp -- BGZF + BAM + BAI region reader for the staging host (own DEFLATE decoder, zlib as the
+// fallback; htslib is not in this image).  Replaces what rust-htslib 0.36 / C htslib give the reference at
 // /root/reference/src/main.rs:262, 470 (IndexedReader::from_path), 822-829 (fetch + records),
 // 742/753 (Record::aux), 793-796 (cigar), 896 (seq).  Region semantics = the htslib iterator: every
 // record of the contig with pos < end and bam_endpos > beg, in file order.
@@ -15,6 +15,8 @@
 #include <sys/stat.h>
 #include <unistd.h>
 #include <vector>
+
+#include "inflate_fast.hpp"
 
 namespace vtxhost {
 
@@ -37,8 +39,9 @@ public:
         memset(&zs_, 0, sizeof(zs_));
         if (inflateInit2(&zs_, -15) != Z_OK) { *err = "inflateInit2 failed"; return false; }
         zinit_ = true;
-        cbuf_.resize(1 << 16); ubuf_.resize(1 << 16);
-        block_coff_ = 0; block_len_ = 0; block_pos_ = 0; next_coff_ = 0; have_block_ = false;
+        cbuf_.resize((1 << 16) + kInflateInPad);
+        for (Slot& c : slots_) { c.coff = ~0ull; c.len = 0; }
+        cur_ = nullptr; block_pos_ = 0; eof_ = false; clock_ = 0;
         return true;
     }
     void close()
@@ -49,51 +52,64 @@ public:
     bool seek(uint64_t voff)
     {
         const uint64_t coff = voff >> 16; const uint32_t uoff = uint32_t(voff & 0xFFFF);
-        if (!have_block_ || coff != block_coff_) { if (!load(coff)) return false; }
-        if (uoff > block_len_) return false;
+        if (!cur_ || coff != cur_->coff) { if (!load(coff)) return false; }
+        if (uoff > cur_->len) return false;
         block_pos_ = uoff;
         return true;
     }
     uint64_t tell()
     {   // htslib convention: at the end of a block the position is the start of the next one
-        if (have_block_ && block_pos_ == block_len_ && block_len_ > 0) return next_coff_ << 16;
-        return (block_coff_ << 16) | block_pos_;
+        if (!cur_) return 0;
+        if (block_pos_ == cur_->len && cur_->len > 0) return cur_->next << 16;
+        return (cur_->coff << 16) | block_pos_;
     }
     // read exactly n bytes; false at EOF / error
     bool read(void* dst, size_t n)
     {
         uint8_t* d = static_cast<uint8_t*>(dst);
         while (n) {
-            if (!have_block_ || block_pos_ == block_len_) {
-                if (!load(have_block_ ? next_coff_ : 0)) return false;
-                if (block_len_ == 0) { if (eof_) return false; continue; }   // empty (EOF marker) block
+            if (!cur_ || block_pos_ == cur_->len) {
+                if (!load(cur_ ? cur_->next : 0)) return false;
+                if (cur_->len == 0) { if (eof_) return false; continue; }   // empty (EOF marker) block
             }
-            const size_t k = std::min<size_t>(n, block_len_ - block_pos_);
-            memcpy(d, ubuf_.data() + block_pos_, k);
+            const size_t k = std::min<size_t>(n, cur_->len - block_pos_);
+            memcpy(d, cur_->data.data() + block_pos_, k);
             d += k; n -= k; block_pos_ += uint32_t(k);
         }
         return true;
     }
+    // the next n bytes in place when they lie inside the current block (no copy, position unchanged), else nullptr
+    const uint8_t* peek(size_t n)
+    {
+        if (cur_ && block_pos_ == cur_->len && cur_->len > 0 && !load(cur_->next)) return nullptr;
+        if (!cur_ || size_t(cur_->len - block_pos_) < n) return nullptr;
+        return cur_->data.data() + block_pos_;
+    }
+    void skip(size_t n) { block_pos_ += uint32_t(n); }     // only after a successful peek(>= n)
     bool at_eof() const { return eof_; }
 
 private:
-    // neighbouring loci fetch overlapping file ranges: keep the last few inflated blocks
-    struct Cached { uint64_t coff = ~0ull, next = 0; std::vector<uint8_t> data; };
-    static constexpr int kCache = 6;
-    Cached cache_[kCache];
-    int cache_rr_ = 0;
+    // Neighbouring loci fetch overlapping file ranges (every fetch restarts at its 16 kb index window): inflated
+    // blocks stay in a small cache and are used in place.  48 x 64 KiB covers the ~10 blocks of a 16 kb window of
+    // a deep BAM several times over, so the cyclic re-scan pattern of consecutive loci always hits.
+    struct Slot { uint64_t coff = ~0ull, next = 0; uint32_t len = 0; std::vector<uint8_t> data; };
+    static constexpr int kSlots = 48;
+    Slot slots_[kSlots];
+    Slot end_slot_;
+    Slot* cur_ = nullptr;
+    int clock_ = 0;
 
     bool load(uint64_t coff)
     {
         eof_ = false;
-        for (Cached& c : cache_)
-            if (c.coff == coff) {
-                if (ubuf_.size() < c.data.size()) ubuf_.resize(c.data.size());
-                memcpy(ubuf_.data(), c.data.data(), c.data.size());
-                block_coff_ = coff; block_len_ = uint32_t(c.data.size()); block_pos_ = 0; next_coff_ = c.next; have_block_ = true;
-                return true;
-            }
-        if (coff >= size_) { eof_ = true; have_block_ = true; block_coff_ = coff; block_len_ = 0; block_pos_ = 0; next_coff_ = coff; return false; }
+        for (Slot& c : slots_)
+            if (c.coff == coff) { cur_ = &c; block_pos_ = 0; return true; }
+        if (coff >= size_) {            // past the last block: an empty pseudo-block that the cache never serves
+            eof_ = true; end_slot_.coff = coff; end_slot_.next = coff; end_slot_.len = 0; cur_ = &end_slot_; block_pos_ = 0;
+            return false;
+        }
+        Slot* v = &slots_[clock_]; clock_ = (clock_ + 1) % kSlots;      // round robin; the outgoing current block is not needed again
+        v->coff = ~0ull;
         uint8_t hdr[18];
         if (pread(fd_, hdr, 18, off_t(coff)) != 18) { eof_ = true; return false; }
         if (hdr[0] != 31 || hdr[1] != 139) return false;
@@ -113,28 +129,27 @@ private:
         const uint32_t total = bsize + 1;
         if (total < 12 + xlen + 8) return false;
         const uint32_t clen = total - 12 - xlen - 8;
-        if (cbuf_.size() < total) cbuf_.resize(total);
+        if (cbuf_.size() < total + kInflateInPad) cbuf_.resize(total + kInflateInPad);
         if (pread(fd_, cbuf_.data(), clen + 8, off_t(coff + 12 + xlen)) != ssize_t(clen + 8)) return false;
         const uint32_t isize = rd32(cbuf_.data() + clen + 4);
-        if (isize > ubuf_.size()) ubuf_.resize(isize);
-        if (isize) {
+        if (v->data.size() < isize + kInflateOutPad) v->data.resize(std::max<size_t>(isize, size_t(1) << 16) + kInflateOutPad);
+        if (isize && !vtx_inflate_raw(cbuf_.data(), clen, v->data.data(), isize)) {
+            // the single-pass decoder refused the member: let zlib have the last word before calling the file corrupt
             inflateReset(&zs_);
             zs_.next_in = cbuf_.data(); zs_.avail_in = clen;
-            zs_.next_out = ubuf_.data(); zs_.avail_out = isize;
+            zs_.next_out = v->data.data(); zs_.avail_out = isize;
             if (inflate(&zs_, Z_FINISH) != Z_STREAM_END) return false;
         }
-        block_coff_ = coff; block_len_ = isize; block_pos_ = 0; next_coff_ = coff + total; have_block_ = true;
-        Cached& c = cache_[cache_rr_]; cache_rr_ = (cache_rr_ + 1) % kCache;
-        c.coff = coff; c.next = next_coff_; c.data.assign(ubuf_.begin(), ubuf_.begin() + isize);
+        v->coff = coff; v->next = coff + total; v->len = isize;
+        cur_ = v; block_pos_ = 0;
         return true;
     }
     int fd_ = -1;
     uint64_t size_ = 0;
     z_stream zs_;
-    bool zinit_ = false, have_block_ = false, eof_ = false;
-    std::vector<uint8_t> cbuf_, ubuf_;
-    uint64_t block_coff_ = 0, next_coff_ = 0;
-    uint32_t block_len_ = 0, block_pos_ = 0;
+    bool zinit_ = false, eof_ = false;
+    std::vector<uint8_t> cbuf_;
+    uint32_t block_pos_ = 0;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -155,17 +170,19 @@ struct BamRecord {
     const uint8_t* aux() const { return seq() + (l_seq() + 1) / 2 + l_seq(); }
     const uint8_t* end() const { return data.data() + data.size(); }
     // htslib bam_endpos: pos + reference length of the CIGAR; pos + 1 when unmapped / no CIGAR / zero length
-    int64_t endpos() const
+    int64_t endpos() const { return endpos_of(data.data()); }
+    static int64_t endpos_of(const uint8_t* d)      // d = the record without its block_size prefix
     {
         int64_t rlen = 0;
-        if (!(flag() & 4)) {
-            const uint8_t* c = cigar();
-            for (uint32_t i = 0; i < n_cigar(); ++i) {
+        if (!(rd16(d + 14) & 4)) {
+            const uint8_t* c = d + 32 + d[8];
+            const uint32_t nc = rd16(d + 12);
+            for (uint32_t i = 0; i < nc; ++i) {
                 const uint32_t v = rd32(c + 4 * i), op = v & 0xF;
                 if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) rlen += v >> 4;
             }
         }
-        return int64_t(pos()) + (rlen > 0 ? rlen : 1);
+        return int64_t(int32_t(rd32(d + 4))) + (rlen > 0 ? rlen : 1);
     }
     // first aux field named `tag`: value bytes when its type is 'Z' (Record::aux -> Aux::String), else nullptr
     const uint8_t* aux_z(const char tag[2], uint32_t* len) const
@@ -244,6 +261,14 @@ public:
     bool fetch(int tid, int64_t beg, int64_t end)
     {
         chunks_.clear(); cur_ = 0; positioned_ = false; tid_ = tid; beg_ = beg; end_ = end; done_ = false;
+        // Resume point of the previous region, valid for this one if it is on the same contig and does not start
+        // earlier: the file is coordinate-sorted, so every record before the first record that overlapped
+        // [prev_beg, prev_end) (or, if none did, before the record that ended that scan) ends at or before prev_beg
+        // <= beg and cannot overlap the new region either.  Sorted VCFs therefore scan each stretch of the file once
+        // instead of once per locus from the start of its 16 kb index window.
+        const bool resume = hint_valid_ && tid == hint_tid_ && beg >= hint_beg_;
+        const uint64_t resume_off = hint_voff_;
+        hint_valid_ = false; hint_set_ = false; hint_tid_ = tid; hint_beg_ = beg;
         if (tid < 0 || size_t(tid) >= refs_.size()) { done_ = true; return false; }
         if (beg < 0) beg = 0;
         if (end <= beg) { done_ = true; return true; }
@@ -255,6 +280,8 @@ public:
             min_off = r.linear[w];
             // htslib walks back over empty windows; offsets are monotone so the entry itself is a safe lower bound
         }
+        if (resume && resume_off > min_off) min_off = resume_off;
+        start_off_ = min_off;
         const int64_t e1 = end - 1;
         auto add_bin = [&](uint32_t bin) {
             auto it = std::lower_bound(r.bin_ids.begin(), r.bin_ids.end(), bin);
@@ -282,20 +309,42 @@ public:
         while (!done_) {
             if (!positioned_) {
                 if (cur_ >= chunks_.size()) { done_ = true; break; }
-                if (!bg_.seek(chunks_[cur_].beg)) { done_ = true; break; }
+                if (!bg_.seek(std::max(chunks_[cur_].beg, start_off_))) { done_ = true; break; }   // start_off_ is a record boundary
                 positioned_ = true;
             }
             if (bg_.tell() >= chunks_[cur_].end) { ++cur_; positioned_ = false; continue; }
             const uint64_t voff = bg_.tell();
-            uint8_t b4[4];
-            if (!bg_.read(b4, 4)) { done_ = true; break; }
-            const uint32_t bs = rd32(b4);
-            rec->data.resize(bs);
-            if (bs < 32 || !bg_.read(rec->data.data(), bs)) { done_ = true; break; }
-            rec->voff = voff;
-            if (rec->refid() != tid_ || int64_t(rec->pos()) >= end_) { done_ = true; break; }   // sorted file: nothing further can overlap
-            if (rec->endpos() > beg_) return true;
+            // records that lie inside one BGZF block are examined in place; only those handed out are copied
+            const uint8_t* p = bg_.peek(4);
+            uint32_t bs = 0;
+            const uint8_t* body = nullptr;
+            if (p) { bs = rd32(p); if (bs >= 32) { const uint8_t* q = bg_.peek(4 + size_t(bs)); if (q) body = q + 4; } }
+            if (body) {
+                bg_.skip(4 + size_t(bs));
+            } else {                                   // straddles a block boundary: assemble a copy
+                uint8_t b4[4];
+                if (!bg_.read(b4, 4)) { done_ = true; break; }
+                bs = rd32(b4);
+                rec->data.resize(bs);
+                if (bs < 32 || !bg_.read(rec->data.data(), bs)) { done_ = true; break; }
+                body = rec->data.data();
+            }
+            if (int32_t(rd32(body)) != tid_ || int64_t(int32_t(rd32(body + 4))) >= end_) {          // sorted file: nothing further can overlap
+                if (!hint_set_) { hint_voff_ = voff; hint_set_ = true; }
+                hint_valid_ = true;
+                done_ = true;
+                break;
+            }
+            if (BamRecord::endpos_of(body) > beg_) {
+                if (!hint_set_) { hint_voff_ = voff; hint_set_ = true; }
+                if (body != rec->data.data()) rec->data.assign(body, body + bs);
+                rec->voff = voff;
+                return true;
+            }
         }
+        // the scan ran off the chunks (or the file) without meeting a record at or beyond `end`: the next region may
+        // still resume at the first overlapping record, if there was one
+        if (hint_set_) hint_valid_ = true;
         return false;
     }
 
@@ -348,6 +397,11 @@ private:
     bool positioned_ = false, done_ = true;
     int tid_ = -1;
     int64_t beg_ = 0, end_ = 0;
+    uint64_t start_off_ = 0;          // lower bound of this region's scan (linear index or resume point)
+    bool hint_valid_ = false, hint_set_ = false;
+    int hint_tid_ = -1;
+    int64_t hint_beg_ = 0;
+    uint64_t hint_voff_ = 0;
 };
 
 }  // namespace vtxhost
