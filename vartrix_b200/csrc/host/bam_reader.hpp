@@ -156,21 +156,25 @@ private:
 // BAM record view + BAI index
 // ---------------------------------------------------------------------------------------------
 struct BamRecord {
-    std::vector<uint8_t> data;    // the record without its block_size prefix
+    // A view: `p` points at the record (without its block_size prefix) inside the reader's inflated block, or into `own`
+    // when the record straddles two blocks.  Valid until the next BamFile::next / fetch on the reader that produced it.
+    const uint8_t* p = nullptr;
+    uint32_t len = 0;
+    std::vector<uint8_t> own;
     uint64_t voff = 0;            // virtual offset of the record (identity of the record inside the file)
-    int32_t refid() const { return int32_t(rd32(data.data())); }
-    int32_t pos() const { return int32_t(rd32(data.data() + 4)); }
-    uint32_t l_read_name() const { return data[8]; }
-    uint32_t mapq() const { return data[9]; }
-    uint32_t n_cigar() const { return rd16(data.data() + 12); }
-    uint32_t flag() const { return rd16(data.data() + 14); }
-    int32_t l_seq() const { return int32_t(rd32(data.data() + 16)); }
-    const uint8_t* cigar() const { return data.data() + 32 + l_read_name(); }
+    int32_t refid() const { return int32_t(rd32(p)); }
+    int32_t pos() const { return int32_t(rd32(p + 4)); }
+    uint32_t l_read_name() const { return p[8]; }
+    uint32_t mapq() const { return p[9]; }
+    uint32_t n_cigar() const { return rd16(p + 12); }
+    uint32_t flag() const { return rd16(p + 14); }
+    int32_t l_seq() const { return int32_t(rd32(p + 16)); }
+    const uint8_t* cigar() const { return p + 32 + l_read_name(); }
     const uint8_t* seq() const { return cigar() + 4 * n_cigar(); }
     const uint8_t* aux() const { return seq() + (l_seq() + 1) / 2 + l_seq(); }
-    const uint8_t* end() const { return data.data() + data.size(); }
+    const uint8_t* end() const { return p + len; }
     // htslib bam_endpos: pos + reference length of the CIGAR; pos + 1 when unmapped / no CIGAR / zero length
-    int64_t endpos() const { return endpos_of(data.data()); }
+    int64_t endpos() const { return endpos_of(p); }
     static int64_t endpos_of(const uint8_t* d)      // d = the record without its block_size prefix
     {
         int64_t rlen = 0;
@@ -325,9 +329,9 @@ public:
                 uint8_t b4[4];
                 if (!bg_.read(b4, 4)) { done_ = true; break; }
                 bs = rd32(b4);
-                rec->data.resize(bs);
-                if (bs < 32 || !bg_.read(rec->data.data(), bs)) { done_ = true; break; }
-                body = rec->data.data();
+                rec->own.resize(bs);
+                if (bs < 32 || !bg_.read(rec->own.data(), bs)) { done_ = true; break; }
+                body = rec->own.data();
             }
             if (int32_t(rd32(body)) != tid_ || int64_t(int32_t(rd32(body + 4))) >= end_) {          // sorted file: nothing further can overlap
                 if (!hint_set_) { hint_voff_ = voff; hint_set_ = true; }
@@ -337,7 +341,7 @@ public:
             }
             if (BamRecord::endpos_of(body) > beg_) {
                 if (!hint_set_) { hint_voff_ = voff; hint_set_ = true; }
-                if (body != rec->data.data()) rec->data.assign(body, body + bs);
+                rec->p = body; rec->len = bs;
                 rec->voff = voff;
                 return true;
             }

@@ -3,6 +3,7 @@
 // four record filters and stage the survivors as one `vtx_batch` shard.  Alignment, barcode lookup, UMI
 // gate and aggregation happen on the GPU behind include/vartrix_b200.h.
 #pragma once
+#include <algorithm>
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -128,11 +129,51 @@ inline bool useful_alignment(const BamRecord& rec, int64_t start, int64_t end)
 
 inline void pad16(std::vector<uint8_t>& v) { while (v.size() & 15) v.push_back(0); }
 
+// record virtual offset -> staged read id of the current shard: open addressing, linear probing, grows at 50 % load.
+// (One lookup per candidate; a node-based std::unordered_map spends more time allocating than hashing here.)
+class ReadIndex {
+public:
+    ReadIndex() { keys_.assign(1 << 12, kEmpty); vals_.resize(1 << 12); }
+    void clear() { std::fill(keys_.begin(), keys_.end(), kEmpty); n_ = 0; }
+    // id of `voff`; `fresh` tells whether it was inserted now (with id = next_id)
+    uint32_t find_or_insert(uint64_t voff, uint32_t next_id, bool* fresh)
+    {
+        if ((n_ + 1) * 2 > keys_.size()) grow();
+        size_t i = slot(voff);
+        while (keys_[i] != kEmpty) {
+            if (keys_[i] == voff) { *fresh = false; return vals_[i]; }
+            i = (i + 1) & (keys_.size() - 1);
+        }
+        keys_[i] = voff; vals_[i] = next_id; ++n_;
+        *fresh = true;
+        return next_id;
+    }
+private:
+    static constexpr uint64_t kEmpty = ~0ull;          // no BAM record lives at virtual offset 2^64 - 1
+    size_t slot(uint64_t k) const { return size_t((k * 0x9E3779B97F4A7C15ull) >> 20) & (keys_.size() - 1); }
+    void grow()
+    {
+        std::vector<uint64_t> ok; std::vector<uint32_t> ov;
+        ok.swap(keys_); ov.swap(vals_);
+        keys_.assign(ok.size() * 2, kEmpty); vals_.resize(ok.size() * 2);
+        for (size_t j = 0; j < ok.size(); ++j)
+            if (ok[j] != kEmpty) {
+                size_t i = slot(ok[j]);
+                while (keys_[i] != kEmpty) i = (i + 1) & (keys_.size() - 1);
+                keys_[i] = ok[j]; vals_[i] = ov[j];
+            }
+    }
+    std::vector<uint64_t> keys_;
+    std::vector<uint32_t> vals_;
+    size_t n_ = 0;
+};
+
 // Records [lo, hi) of the VCF -> one shard.  Mirrors evaluate_rec + the head of evaluate_alns.
 inline bool stage_loci(const std::vector<VcfRecord>& recs, size_t lo, size_t hi, const Fasta& fa, BamFile& bam,
                        const StageArgs& a, UmiInterner& umis, StagedShard* out, std::string* err)
 {
-    std::unordered_map<uint64_t, uint32_t> read_index;      // record virtual offset -> staged read id
+    static thread_local ReadIndex read_index;               // record virtual offset -> staged read id (table reused across shards)
+    read_index.clear();
     BamRecord rec;
     std::string left, right, ref_hap, alt_hap;
     out->cand_start.push_back(0);
@@ -169,8 +210,9 @@ inline bool stage_loci(const std::vector<VcfRecord>& recs, size_t lo, size_t hi,
                 if (a.primary_only && (fl & 0x100 || fl & 0x800)) { out->met.num_non_primary++; continue; }   // 841
                 if (a.no_duplicates && (fl & 0x400)) { out->met.num_duplicates++; continue; }                 // 849
                 if (!useful_alignment(rec, start, end)) { out->met.num_not_useful++; continue; }              // 857
-                auto ins = read_index.emplace(rec.voff, uint32_t(out->read_len.size()));
-                if (ins.second) {
+                bool fresh = false;
+                const uint32_t rid = read_index.find_or_insert(rec.voff, uint32_t(out->read_len.size()), &fresh);
+                if (fresh) {
                     const int32_t ls = rec.l_seq() < 0 ? 0 : rec.l_seq();
                     pad16(out->read_nib);
                     out->read_off.push_back(out->read_nib.size());
@@ -183,7 +225,7 @@ inline bool stage_loci(const std::vector<VcfRecord>& recs, size_t lo, size_t hi,
                     const uint8_t* ub = rec.aux_z("UB", &n);                                                  // main.rs:752-757
                     out->read_umi_key.push_back(ub ? umis.key(ub, n) : VTX_NO_UMI);
                 }
-                out->cand_read.push_back(ins.first->second);
+                out->cand_read.push_back(rid);
             }
         }
         out->cand_start.push_back(out->cand_read.size());
