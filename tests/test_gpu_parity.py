@@ -158,7 +158,7 @@ def _edited(rng, src, alpha, sub, indel):
 
 
 def _fold_pairs_batch(vb, rng, n_loci, reads_per_locus, m_lo, m_hi, mid_lo, mid_hi, flank_lo=96, flank_hi=96, alphabet=b"ACGT",
-                      same_mid_len=False, sub=0.01, indel=0.004, related_mid=True):
+                      same_mid_len=False, sub=0.01, indel=0.004, related_mid=True, long_loci=0):
     haps, ref_off, ref_len, alt_off, alt_len = bytearray(), [], [], [], []
     nibs, read_off, read_len = bytearray(), [], []
     alpha = np.frombuffer(alphabet, np.uint8)
@@ -177,8 +177,10 @@ def _fold_pairs_batch(vb, rng, n_loci, reads_per_locus, m_lo, m_hi, mid_lo, mid_
         for h, offs, lens in ((ref, ref_off, ref_len), (alt, alt_off, alt_len)):
             while len(haps) % 16: haps.append(0)
             offs.append(len(haps)); lens.append(len(h)); haps.extend(h.tobytes())
-        for _ in range(reads_per_locus):
+        for ri in range(reads_per_locus):
             m = int(rng.integers(m_lo, m_hi + 1))
+            if l < long_loci and ri == 1:
+                m = int(rng.integers(153, 257))            # one read of this locus is too long for the folded kernel
             src = ref if rng.random() < 0.5 else alt
             u = rng.random()
             if u < 0.1:
@@ -239,14 +241,17 @@ def test_fold_windows_bit_exact(vb, oracle, name, kw, all_fold):
             assert tiles[7] > 0 and sum(tiles) > tiles[7], tiles
 
 
-def test_fold_falls_back_for_long_reads(vb, oracle):
+def test_fold_is_decided_per_locus_by_its_longest_read(vb, oracle):
     rng = np.random.default_rng(99)
-    sb, pr, pl = _fold_pairs_batch(vb, rng, n_loci=10, reads_per_locus=5, m_lo=150, m_hi=200, mid_lo=9, mid_hi=9, same_mid_len=True)
-    assert int(sb.read_len.max()) > 152
+    sb, pr, pl = _fold_pairs_batch(vb, rng, n_loci=12, reads_per_locus=5, m_lo=120, m_hi=152, mid_lo=9, mid_hi=9, same_mid_len=True,
+                                   long_loci=4)
+    lens = sb.read_len.reshape(12, 5)
+    assert (lens[:4].max(axis=1) > 152).all() and (lens[4:] <= 152).all()
     ors, oas = oracle.score_pairs(to_oracle_batch(oracle, sb), pr, pl, n_threads=8)
     with vb.Engine("coverage") as eng:
         rs, as_ = eng.score_pairs(sb, pr, pl)
-        assert eng.tile_counts()[7] == 0
+        tiles = eng.tile_counts()
+    assert tiles[7] == 8 * 2 and tiles[5] == 4        # 8 loci x ceil(5/4) folded tiles; 4 loci x ceil(5/8) two-phase tiles
     assert np.array_equal(rs.astype(np.int32), ors) and np.array_equal(as_.astype(np.int32), oas)
 
 

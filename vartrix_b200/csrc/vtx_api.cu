@@ -231,10 +231,10 @@ int run_sw(vtx_ctx* ctx, const DevBatch& b, uint32_t n_pairs_ub, const uint32_t*
     const int force_slow = 0;       // reads of any supported length run on the single-phase classes (row blocks)
     const int allow_split = (b.max_read_len <= uint32_t(kSplitMaxRead) && !(ctx->cfg.flags & VTX_F_NO_SPLIT)) ? 1 : 0;
     const int allow_multi = (b.max_read_len <= uint32_t(kMultiMaxRead) && b.max_hap_len > uint32_t(class_max_n(kNumFastClasses - 1))) ? 1 : 0;
-    const int allow_fold = (b.max_read_len <= uint32_t(kFoldMaxRead) && !(ctx->cfg.flags & (VTX_F_NO_SPLIT | VTX_F_NO_FOLD))) ? 1 : 0;
+    const int allow_fold = (ctx->cfg.flags & (VTX_F_NO_SPLIT | VTX_F_NO_FOLD)) ? 0 : 1;      // per locus: windows and read lengths decide
     vtx_k_locus_prep<<<blocks_for(uint64_t(nl) * 32, 256), 256, 0, ctx->stream>>>(
-        nl, b.hap, b.ref_off, b.ref_len, b.alt_off, b.alt_len, P<uint32_t>(ctx->pair_start), force_slow, allow_split, allow_multi,
-        allow_fold, P<uint32_t>(ctx->tcount));
+        nl, b.hap, b.ref_off, b.ref_len, b.alt_off, b.alt_len, P<uint32_t>(ctx->pair_start), P<uint32_t>(ctx->pair_read), b.read_len,
+        force_slow, allow_split, allow_multi, allow_fold, P<uint32_t>(ctx->tcount));
     ++*launches;
     vtx_k_scan_rows<<<kNumClasses, kScanThreads, 0, ctx->stream>>>(P<uint32_t>(ctx->tcount), P<uint32_t>(ctx->tstart), nl, nl + 1);
     ++*launches;

@@ -143,7 +143,8 @@ __global__ void vtx_k_pair_start_explicit(uint32_t n_loci, uint32_t n_pairs, con
 __global__ void vtx_k_locus_prep(uint32_t n_loci, const uint8_t* __restrict__ hap_bytes,
                                  const uint32_t* __restrict__ ref_off, const uint32_t* __restrict__ ref_len,
                                  const uint32_t* __restrict__ alt_off, const uint32_t* __restrict__ alt_len,
-                                 const uint32_t* __restrict__ pair_start, int force_slow, int allow_split, int allow_multi, int allow_fold,
+                                 const uint32_t* __restrict__ pair_start, const uint32_t* __restrict__ pair_read,
+                                 const uint32_t* __restrict__ read_len, int force_slow, int allow_split, int allow_multi, int allow_fold,
                                  uint32_t* __restrict__ tcount /* [kNumClasses][n_loci + 1] */)
 {
     const uint32_t l = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -169,6 +170,11 @@ __global__ void vtx_k_locus_prep(uint32_t n_loci, const uint8_t* __restrict__ ha
     bool fold = same && allow_fold && min(nr, na) > uint32_t(2 * kFoldP) && max(nr, na) <= uint32_t(2 * kFoldP + kFoldMaxMid);
     if (fold) for (uint32_t j = lane; j < uint32_t(kFoldP); j += 32) fold &= (rh[nr - 1 - j] == ah[na - 1 - j]);
     fold = __all_sync(0xffffffffu, fold);
+    if (fold) {                       // the folded kernel keeps 8 x 19 read rows in registers: every read of the locus must fit
+        uint32_t longest = 0;
+        for (uint32_t p = pair_start[l] + lane; p < pair_start[l + 1]; p += 32) longest = max(longest, read_len[pair_read[p]]);
+        fold = __reduce_max_sync(0xffffffffu, longest) <= uint32_t(kFoldMaxRead);
+    }
     if (lane != 0) return;
     const uint32_t nmax = max(nr, na);
     int cls = kSlowClass;
