@@ -154,3 +154,60 @@ def test_cpp_staging_with_dense_overlapping_loci(oracle, dataset, tmp_path):
     _same_staging(sb, ob)
     assert met == {m: ob.host_metrics[m] for m in met}
     assert sb.n_cand > 1.5 * len(sb.read_len)        # reads are shared between neighbouring loci
+
+
+def test_cpp_staging_with_long_spliced_records_across_index_bins(oracle, tmp_path):
+    """Spliced records of up to 150 kb live in high-level BAI bins, far ahead (in file order) of the short reads around the
+    loci they cover: the region iterator (chunk merging, linear-index lower bound, resumed scans) must still hand out
+    exactly the records htslib would, in file order."""
+    from vartrix_b200.synth_files import BamWriter
+    rng = np.random.default_rng(11)
+    contigs = [("chrA", 400_000), ("chrB", 120_000)]
+    genome = [rng.integers(0, 4, size=L, dtype=np.uint8) for _, L in contigs]
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    fa = tmp_path / "g.fa"
+    with open(fa, "wb") as f, open(str(fa) + ".fai", "w") as fai:
+        for (name, L), g in zip(contigs, genome):
+            f.write(f">{name}\n".encode()); off = f.tell()
+            seq = acgt[g]
+            for s0 in range(0, L, 70):
+                f.write(seq[s0:s0 + 70].tobytes() + b"\n")
+            fai.write(f"{name}\t{L}\t{off}\t70\t71\n")
+    reads = []
+    for ci, (_, L) in enumerate(contigs):
+        for _ in range(2500 if ci == 0 else 600):                      # short reads
+            p0 = int(rng.integers(0, L - 120))
+            reads.append((ci, p0, [("M", 100)], acgt[genome[ci][p0:p0 + 100]].tobytes()))
+        for _ in range(160 if ci == 0 else 30):                        # spliced: 50M <1..150 kb>N 50M
+            gap = int(rng.choice([900, 5000, 17000, 70000, 150000]))
+            p0 = int(rng.integers(0, max(1, L - gap - 120)))
+            if p0 + gap + 100 >= L:
+                continue
+            seq = np.concatenate([genome[ci][p0:p0 + 50], genome[ci][p0 + 50 + gap:p0 + 100 + gap]])
+            reads.append((ci, p0, [("M", 50), ("N", gap), ("M", 50)], acgt[seq].tobytes()))
+    reads.sort(key=lambda r: (r[0], r[1]))
+    bam = tmp_path / "r.bam"
+    bw = BamWriter(str(bam), contigs)
+    for i, (ci, p0, cig, seq) in enumerate(reads):
+        bw.add(ci, p0, 60, 0, cig, seq, f"q{i}".encode(), b"CBZ" + b"ACGTACGTACGTACGT-1\0" + b"UBZ" + b"ACGTACGTAC\0")
+    bw.close()
+    vcf = tmp_path / "v.vcf"
+    with open(vcf, "w") as f:
+        f.write("##fileformat=VCFv4.2\n" + "".join(f"##contig=<ID={n},length={L}>\n" for n, L in contigs))
+        f.write("#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\n")
+        for ci, (name, L) in enumerate(contigs):
+            for p0 in np.sort(rng.integers(200, L - 200, size=220 if ci == 0 else 60)):
+                ref = "ACGT"[genome[ci][p0]]
+                f.write(f"{name}\t{p0 + 1}\t.\t{ref}\t{'ACGT'[(genome[ci][p0] + 1) % 4]}\t.\t.\t.\n")
+    bcs = tmp_path / "b.tsv"; bcs.write_text("ACGTACGTACGTACGT-1\n")
+    for threads, shard in ((1, 1000000), (3, 41)):
+        out = tmp_path / f"s{threads}.staged"
+        subprocess.run([CLI, "-v", str(vcf), "-b", str(bam), "-f", str(fa), "-c", str(bcs), "--dump-staged", str(out),
+                        "--shard-loci", str(shard), "--threads", str(threads)], check=True, cwd=str(tmp_path))
+        from vartrix_b200.staged_io import read_dump
+        _, _, shards = read_dump(str(out))
+        for k, (sb, met) in enumerate(shards):
+            ob = oracle.stage_from_files(str(vcf), str(bam), str(fa), rec_lo=shard * k, rec_hi=min(280, shard * k + shard))
+            _same_staging(sb, ob)
+            assert met == {m: ob.host_metrics[m] for m in met}, (threads, k)
+        assert sum(int(m["num_not_useful"]) for _, m in shards) > 0        # spliced records that skip their locus
