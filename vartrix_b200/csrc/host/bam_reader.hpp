@@ -329,8 +329,9 @@ public:
                 uint8_t b4[4];
                 if (!bg_.read(b4, 4)) { done_ = true; break; }
                 bs = rd32(b4);
+                if (bs < 32 || bs > (1u << 28)) { done_ = true; break; }        // not a BAM record: stop instead of allocating gigabytes
                 rec->own.resize(bs);
-                if (bs < 32 || !bg_.read(rec->own.data(), bs)) { done_ = true; break; }
+                if (!bg_.read(rec->own.data(), bs)) { done_ = true; break; }
                 body = rec->own.data();
             }
             if (int32_t(rd32(body)) != tid_ || int64_t(int32_t(rd32(body + 4))) >= end_) {          // sorted file: nothing further can overlap
