@@ -159,8 +159,9 @@ int         vtx_set_barcodes(vtx_ctx* ctx, const uint8_t* bytes, const uint32_t*
 /* Enqueue one shard (asynchronous on the ctx stream).  Shards must arrive in ascending row order. */
 int         vtx_submit(vtx_ctx* ctx, const vtx_batch* host_batch);
 int         vtx_submit_device(vtx_ctx* ctx, const vtx_batch* device_batch);
-/* Device batches cannot be scanned by the host: state the longest read and the widest haplotype window
- * (plain vtx_submit_device assumes reads <= 1024 bases and windows <= 320 bytes). */
+/* Device batches cannot be scanned by the host: state the longest read and the widest haplotype window (upper
+ * bounds; buffers are sized and kernels selected from them, so a batch that exceeds them is undefined behaviour;
+ * plain vtx_submit_device assumes reads <= 1024 bases and windows <= 320 bytes). */
 int         vtx_submit_device_ex(vtx_ctx* ctx, const vtx_batch* device_batch, uint32_t max_read_len, uint32_t max_hap_len);
 /* Wait for everything submitted since the last finish and hand back the triplets (host arrays). */
 int         vtx_finish(vtx_ctx* ctx, vtx_result* out);

@@ -272,6 +272,28 @@ def test_synthetic_shard_matches_oracle(vb, oracle, mode, kind, umi):
     assert vb.mtx.mtx_text(sb.n_rows, len(bcs), got.row, got.col, got.val) == oracle.mtx_text(sb.n_rows, len(bcs), exp.row, exp.col, exp.val)
 
 
+def test_device_resident_submit_equals_host_submit(vb):
+    """vtx_submit_device_ex (what bench.py's `value` times): same triplets as the host-buffer path, for SNV and indel shards."""
+    import torch
+    for kind, umi in (("snv", False), ("indel", True)):
+        sb, bcs, info = vb.synth.make_shard(400, 150, depth=40, seed=21, kind=kind, umi=umi)
+        exp = _run_engine(vb, sb, bcs, "coverage", umi)
+        keep, db = [], sb.to_c()
+        for f in vb.StagedBatch.FIELDS:
+            a = getattr(sb, f)
+            t = torch.from_numpy(a.view(np.uint8).reshape(-1) if a.dtype.itemsize > 1 else a.reshape(-1)).cuda()
+            keep.append(t)
+            setattr(db, f, t.data_ptr() if t.numel() else None)
+        with vb.Engine("coverage", umi=umi) as eng:
+            eng.set_barcodes(bcs)
+            for _ in range(2):                         # resubmitting the same resident shard gives the same answer
+                eng.submit_device(db, int(sb.read_len.max()), int(max(sb.ref_len.max(), sb.alt_len.max())))
+                dev = eng.finish_device()
+                got = eng.fetch(dev)
+                assert_same_triplets(got, exp)
+                assert got.metrics == exp.metrics
+
+
 def test_edge_cases(vb, oracle):
     sb, bcs, info = vb.synth.make_shard(40, 10, depth=30, seed=3, umi=True, unlisted_frac=0.3)
     # reads without CB / without UB, loci without candidates

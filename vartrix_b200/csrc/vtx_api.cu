@@ -165,7 +165,6 @@ struct DevBatch {   // device pointers
     const uint8_t* cb_bytes; const uint32_t* read_cb_off; const uint16_t* read_cb_len; const uint64_t* read_umi;
     const uint32_t* cand_read;
     uint32_t max_read_len = 0, max_hap_len = 0;
-    bool bounds_exact = false;       // the two maxima were computed by the library (host batches), not declared by the caller
     uint64_t max_depth = ~0ull;      // most candidates of one locus (unknown for device batches: assume deep)
 };
 
@@ -261,7 +260,8 @@ int run_sw(vtx_ctx* ctx, const DevBatch& b, uint32_t n_pairs_ub, const uint32_t*
     uint64_t before = *launches;
     for (int c = 0; c < kNumFastClasses; ++c) {
         // a class whose narrowest window is wider than every window of this batch has no tiles: skip the empty launch
-        if (c > 0 && b.bounds_exact && b.max_hap_len <= uint32_t(class_max_n(c - 1))) continue;
+        // (max_hap_len is exact for host batches and a promised upper bound for device batches)
+        if (c > 0 && b.max_hap_len <= uint32_t(class_max_n(c - 1))) continue;
         a.tile_start = P<uint32_t>(ctx->tstart) + size_t(c) * (nl + 1);
         a.tile_counter = P<uint32_t>(ctx->tile_counters) + c;
         int rc = VTX_OK;
@@ -275,7 +275,7 @@ int run_sw(vtx_ctx* ctx, const DevBatch& b, uint32_t n_pairs_ub, const uint32_t*
     }
     if (allow_split) {
         for (int c = 0; c < kNumSplitClasses; ++c) {
-            if (c > 0 && b.bounds_exact && b.max_hap_len <= uint32_t(split_max_n(c - 1))) continue;
+            if (c > 0 && b.max_hap_len <= uint32_t(split_max_n(c - 1))) continue;
             a.tile_start = P<uint32_t>(ctx->tstart) + size_t(kSplitClass0 + c) * (nl + 1);
             a.tile_counter = P<uint32_t>(ctx->tile_counters) + kSplitClass0 + c;
             int rc = c == 0 ? launch_sw_split<0>(ctx, a, launches) : launch_sw_split<1>(ctx, a, launches);
@@ -724,7 +724,6 @@ int vtx_submit(vtx_ctx* ctx, const vtx_batch* hb)
     d.read_umi = P<uint64_t>(sl->read_umi); d.cand_read = P<uint32_t>(sl->cand_read);
     // 2. ... validate the host arrays meanwhile; nothing has been launched on them yet
     rc = scan_host_batch(ctx, hb, &d.max_read_len, &d.max_hap_len, true, &d.max_depth);
-    d.bounds_exact = true;
     if (rc) { cudaStreamSynchronize(ctx->copy_stream); --ctx->trec_used; return rc; }
     // 3. kernels wait for the copy, and release the slot when done
     CK(cudaStreamWaitEvent(ctx->stream, sl->copy_done, 0));
@@ -958,7 +957,6 @@ int vtx_score_pairs(vtx_ctx* ctx, const vtx_batch* hb, uint64_t n_pairs, const u
     if (n_pairs && (!pair_read || !pair_locus || !ref_score || !alt_score)) return set_err(ctx, VTX_E_INVALID, "NULL pair arrays");
     DevBatch d{};
     rc = scan_host_batch(ctx, hb, &d.max_read_len, &d.max_hap_len, false);
-    d.bounds_exact = true;
     if (rc) return rc;
     if (n_pairs == 0) return VTX_OK;
     const uint32_t nl = hb->n_loci;
