@@ -175,7 +175,7 @@ inline bool stage_loci(const std::vector<VcfRecord>& recs, size_t lo, size_t hi,
     static thread_local ReadIndex read_index;               // record virtual offset -> staged read id (table reused across shards)
     read_index.clear();
     BamRecord rec;
-    std::string left, right, ref_hap, alt_hap;
+    std::string ref_hap, alt_hap;
     out->cand_start.push_back(0);
     for (size_t i = lo; i < hi; ++i) {
         const VcfRecord& v = recs[i];
@@ -185,13 +185,15 @@ inline bool stage_loci(const std::vector<VcfRecord>& recs, size_t lo, size_t hi,
         const int64_t L = fa.length(v.chrom);
         if (L < 0) { *err = "Requested chromosome " + v.chrom + " was not found in fasta"; return false; }
         // construct_haplotypes, main.rs:958-994
-        if (!fa.fetch_upper(v.chrom, std::max<int64_t>(start - a.padding, 0), start, &left) ||
-            !fa.fetch_upper(v.chrom, end, std::min(end + a.padding, L), &right) ||
-            !fa.fetch_upper(v.chrom, std::max<int64_t>(0, start - a.padding), std::min(end + a.padding, L), &ref_hap)) {
+        // one read of the reference window; its two flanks are the alt haplotype's flanks (same FASTA bytes)
+        const int64_t w0 = std::max<int64_t>(start - a.padding, 0), w1 = std::min(end + a.padding, L);
+        if (end > L || !fa.fetch_upper(v.chrom, w0, w1, &ref_hap)) {
             *err = "FASTA fetch failed at " + v.chrom + ":" + std::to_string(v.pos0);
             return false;
         }
-        alt_hap = left + alt + right;
+        alt_hap.assign(ref_hap, 0, size_t(start - w0));            // FASTA[max(start - pad, 0), start)
+        alt_hap += alt;
+        alt_hap.append(ref_hap, size_t(end - w0), std::string::npos);   // FASTA[end, min(end + pad, L))
         bool ok = true;
         for (unsigned char c : alt_hap) if (!a.valid[c]) { ok = false; break; }         // main.rs:675-684
         if (!ok) { out->met.num_invalid_recs++; continue; }
