@@ -14,8 +14,12 @@ allgatherv over NCCL inside the timed region.
 `value`  : pairs/s with the staged shard already resident in HBM (vtx_submit_device + vtx_finish_device).
 `e2e`    : pairs/s through the host-facing C ABI from pinned HOST buffers (vtx_submit + vtx_finish), i.e.
            with the host->device copy of the shard and the device->host copy of the triplets in the timed region.
-`roofline`: the dominant kernel (vtx_k_sw_pairs) against the measured HBM peak, from CUDA events recorded on
-           the engine's stream inside the library (vtx_last_timing), averaged over the timed steps.
+           The step's shard is handed over the way a staging producer would: a 1 % shard first, then shards growing
+           by up to 1.4x (less when the measured copy/kernel ratio of this rank asks for it) up to 1/6 of the step,
+           so that every copy hides behind the previous shard's kernels.
+`roofline`: the dominant kernel (vtx_k_sw_fold for windows built with --padding >= 96) against the measured HBM
+           peak, from CUDA events recorded on the engine's stream inside the library (vtx_last_timing), averaged over
+           the timed steps; `roofline.issue_bound` is the same kernel against the ALU-pipe bound that actually binds.
 `cpu_baseline`: the oracle's C port of the reference algorithm timed on this box's host cores (bounded sample).
 """
 from __future__ import annotations
