@@ -118,6 +118,22 @@ def test_header_symbols_are_exported():
     assert lib.vtx_abi_version() == 1
 
 
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: the header must compile as C99 (no C++-isms, no torch / CUDA types) and link against
+    the library from a C translation unit."""
+    import subprocess
+    from vartrix_b200 import _capi
+    src = tmp_path / "abi.c"
+    src.write_text('#include "vartrix_b200.h"\n'
+                   'int main(void) { vtx_config c; vtx_batch b; vtx_result r; vtx_timing t; (void)c; (void)b; (void)r; (void)t;\n'
+                   '  return vtx_abi_version() == 1 && vtx_pack_umi((const unsigned char*)"ACGT", 4) != VTX_NO_UMI ? 0 : 1; }\n')
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(_capi.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-lvartrix_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    assert subprocess.run([str(exe)]).returncode == 0
+
+
 def test_engine_fails_loudly_without_gpu():
     import vartrix_b200 as vb
     from conftest import HAS_GPU
