@@ -356,6 +356,8 @@ def run_gpu(args):
     if args.growth > 1.0:
         tw = eng.timing()
         g_new = pick_growth(tw["h2d_ms"], tw["prep_ms"] + tw["sw_ms"] + tw["post_ms"], args.growth)
+        if world > 1:      # every rank must take the same branch (the extra warm-up steps below contain a collective)
+            tg = torch.tensor([g_new], device="cuda", dtype=torch.float64); dist.all_reduce(tg, op=dist.ReduceOp.MIN); g_new = float(tg.item())
         if abs(g_new - e2e_growth) > 0.05:
             del hparts[:], hkeep[:]
             e2e_growth = g_new
