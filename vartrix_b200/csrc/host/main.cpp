@@ -46,7 +46,7 @@ bool exists(const std::string& p) { struct stat st; return stat(p.c_str(), &st) 
 struct Opts {
     std::string vcf, bam, fasta, barcodes, out_matrix = "out_matrix.mtx", ref_matrix = "ref_matrix.mtx", out_variants, out_barcodes;
     std::string scoring = "consensus", bam_tag = "CB", valid_chars = "ATGCatgc", dump_staged;
-    long padding = 100, threads = 1, mapq = 0, device = 0, shard_loci = 2048;
+    long padding = 100, threads = 1, mapq = 0, device = 0, shard_loci = 0;      // 0: chosen from the number of loci and threads
     bool primary = false, no_dups = false, umi = false, ref_matrix_given = false;
 };
 
@@ -73,7 +73,7 @@ void usage()
          "      --bam-tag TAG           BAM tag marking cells [CB]\n"
          "      --valid-chars CHARS     Valid characters in an alternative haplotype [ATGCatgc]\n"
          "      --device INT            CUDA device ordinal [0]\n"
-         "      --shard-loci INT        VCF records per staged shard [2048]\n"
+         "      --shard-loci INT        VCF records per staged shard [up to 2048, fewer for short VCFs]\n"
          "      --dump-staged FILE      Stage only, write the shards to FILE (no GPU)");
 }
 
@@ -114,7 +114,7 @@ bool parse(int argc, char** argv, Opts* o)
     if (o->scoring != "consensus" && o->scoring != "coverage" && o->scoring != "alt_frac") { fprintf(stderr, "error: invalid --scoring-method\n"); return false; }
     if (o->bam_tag.size() != 2) { fprintf(stderr, "error: --bam-tag must have two characters\n"); return false; }
     if (o->threads < 1) o->threads = 1;
-    if (o->shard_loci < 1) o->shard_loci = 1;
+    if (o->shard_loci < 0) o->shard_loci = 0;
     return true;
 }
 
@@ -270,6 +270,9 @@ int main(int argc, char** argv)
     for (unsigned char c : o.valid_chars) sa.valid[c] = true;
 
     // ---- staging: worker threads produce shards of `shard_loci` records; the main thread consumes them in order ----
+    // default shard size: 2048 loci (~100 k candidates at 50x, enough to fill the GPU), smaller when the VCF is short so that
+    // every staging thread still gets several shards
+    if (o.shard_loci == 0) o.shard_loci = long(std::min<size_t>(2048, std::max<size_t>(128, recs.size() / (size_t(o.threads) * 4 + 1))));
     const size_t n_shards = (recs.size() + size_t(o.shard_loci) - 1) / size_t(o.shard_loci);
     std::vector<std::unique_ptr<StagedShard>> ready(n_shards);
     std::mutex mu; std::condition_variable cv;
