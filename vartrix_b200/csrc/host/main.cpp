@@ -271,8 +271,8 @@ int main(int argc, char** argv)
 
     // ---- staging: worker threads produce shards of `shard_loci` records; the main thread consumes them in order ----
     // default shard size: 2048 loci (~100 k candidates at 50x, enough to fill the GPU), smaller when the VCF is short so that
-    // every staging thread still gets several shards
-    if (o.shard_loci == 0) o.shard_loci = long(std::min<size_t>(2048, std::max<size_t>(128, recs.size() / (size_t(o.threads) * 4 + 1))));
+    // every staging thread still gets ~10 shards (load balance; the GPU is idle most of the time anyway)
+    if (o.shard_loci == 0) o.shard_loci = long(std::min<size_t>(2048, std::max<size_t>(128, recs.size() / (size_t(o.threads) * 10 + 1))));
     const size_t n_shards = (recs.size() + size_t(o.shard_loci) - 1) / size_t(o.shard_loci);
     std::vector<std::unique_ptr<StagedShard>> ready(n_shards);
     std::mutex mu; std::condition_variable cv;
