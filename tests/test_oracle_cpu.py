@@ -191,3 +191,17 @@ def test_band_model_equals_full_on_synthetic_shards(oracle):
         full = oracle.run_batch(ob, obc, oracle.MODE_COVERAGE, False, n_threads=4)
         band = oracle.run_batch(ob, obc, oracle.MODE_COVERAGE, False, n_threads=4, band_model=True)
         assert np.array_equal(full.val, band.val) and np.array_equal(full.val2, band.val2) and np.array_equal(full.unk_cnt, band.unk_cnt), kind
+
+
+def test_bench_arguments_and_shard_growth_policy():
+    """bench.py parses on a CPU-only box, and its shard-growth policy stays inside [1.1, cap]."""
+    import importlib.util
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--help"], capture_output=True, text=True)
+    assert r.returncode == 0 and "--impl" in r.stdout and "--growth" in r.stdout
+    spec = importlib.util.spec_from_file_location("vtx_bench", os.path.join(ROOT, "bench.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    assert mod.pick_growth(16.6, 35.3, 1.4) == 1.4            # one GPU: copies are twice as fast as the kernels
+    assert 1.15 < mod.pick_growth(27.0, 36.6, 1.4) < 1.3      # eight ranks sharing the host's PCIe paths
+    assert mod.pick_growth(80.0, 36.0, 1.4) == 1.1 and mod.pick_growth(0.0, 1.0, 1.4) == 1.4
