@@ -9,7 +9,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-REF_TEST_DIR = "/root/reference/test"       # present only in the build container
+# the reference's own regression inputs and golden matrices (/root/reference/test, committed verbatim as test data)
+REF_TEST_DIR = os.path.join(GOLDEN, "ref_inputs")
 
 
 def pytest_configure(config):

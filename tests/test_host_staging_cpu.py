@@ -1,5 +1,5 @@
 """The C++ staging host (csrc/host: BGZF/BAM/BAI, .fai FASTA, VCF, filters) against the oracle's independent
-pure-Python decode, on the reference's own fixtures (present in the build container only)."""
+pure-Python decode, on the reference's own fixtures (committed under tests/golden/ref_inputs)."""
 import os
 import subprocess
 
@@ -9,7 +9,7 @@ import pytest
 from conftest import REF_TEST_DIR, ROOT
 
 CLI = os.path.join(ROOT, "vartrix_b200", "bin", "vartrix_b200")
-needs_ref = pytest.mark.skipif(not os.path.isdir(REF_TEST_DIR), reason="reference fixtures only exist in the build container")
+needs_ref = pytest.mark.skipif(not os.path.isdir(REF_TEST_DIR), reason="tests/golden/ref_inputs missing")
 
 
 def _labels(keys):

@@ -23,13 +23,13 @@ def test_oracle_reproduces_goldens_from_committed_fixtures(oracle, goldens, gold
             assert same_entries(triplet_dict(res.row, res.col, res.val2), golden_dict(g2)), case["name"]
 
 
-@pytest.mark.skipif(not os.path.isdir(REF_TEST_DIR), reason="reference fixtures only exist in the build container")
+@pytest.mark.skipif(not os.path.isdir(REF_TEST_DIR), reason="tests/golden/ref_inputs missing")
 def test_oracle_reproduces_goldens_from_reference_files(oracle):
     from oracle import check_goldens
     assert check_goldens.main(REF_TEST_DIR) == 0
 
 
-@pytest.mark.skipif(not os.path.isdir(REF_TEST_DIR), reason="reference fixtures only exist in the build container")
+@pytest.mark.skipif(not os.path.isdir(REF_TEST_DIR), reason="tests/golden/ref_inputs missing")
 def test_committed_fixtures_are_current(oracle, golden_batches):
     b = oracle.stage_from_files(f"{REF_TEST_DIR}/test_dna.vcf", f"{REF_TEST_DIR}/test_dna.bam", f"{REF_TEST_DIR}/test_dna.fa")
     g = golden_batches["dna_batch.npz"]

@@ -41,7 +41,7 @@ public:
         zinit_ = true;
         cbuf_.resize((1 << 16) + kInflateInPad);
         for (Slot& c : slots_) { c.coff = ~0ull; c.len = 0; }
-        cur_ = nullptr; block_pos_ = 0; eof_ = false; clock_ = 0;
+        cur_ = nullptr; block_pos_ = 0; eof_ = false; clock_ = 0; err_.clear();
         return true;
     }
     void close()
@@ -87,6 +87,10 @@ public:
     }
     void skip(size_t n) { block_pos_ += uint32_t(n); }     // only after a successful peek(>= n)
     bool at_eof() const { return eof_; }
+    // Anything but a clean end of file (bad magic, truncated member, inflate or CRC failure, short read) is an ERROR, not
+    // an end of region: the reference aborts on it (`let rec = _rec?`, main.rs:830), so the staging host must too.
+    bool bad() const { return !err_.empty(); }
+    const std::string& error() const { return err_; }
 
 private:
     // Neighbouring loci fetch overlapping file ranges (every fetch restarts at its 16 kb index window): inflated
@@ -99,9 +103,15 @@ private:
     Slot* cur_ = nullptr;
     int clock_ = 0;
 
+    bool fail(uint64_t coff, const char* what)
+    {
+        if (err_.empty()) err_ = std::string("BGZF block at file offset ") + std::to_string(coff) + ": " + what;
+        return false;
+    }
     bool load(uint64_t coff)
     {
         eof_ = false;
+        if (!err_.empty()) return false;
         for (Slot& c : slots_)
             if (c.coff == coff) { cur_ = &c; block_pos_ = 0; return true; }
         if (coff >= size_) {            // past the last block: an empty pseudo-block that the cache never serves
@@ -110,40 +120,49 @@ private:
         }
         Slot* v = &slots_[clock_]; clock_ = (clock_ + 1) % kSlots;      // round robin; the outgoing current block is not needed again
         v->coff = ~0ull;
+        if (cur_ == v) cur_ = nullptr;
         uint8_t hdr[18];
-        if (pread(fd_, hdr, 18, off_t(coff)) != 18) { eof_ = true; return false; }
-        if (hdr[0] != 31 || hdr[1] != 139) return false;
+        if (pread(fd_, hdr, 18, off_t(coff)) != 18) return fail(coff, "truncated file (short read of the member header)");
+        if (hdr[0] != 31 || hdr[1] != 139 || hdr[2] != 8 || !(hdr[3] & 4)) return fail(coff, "not a BGZF member (bad gzip magic)");
         const uint32_t xlen = rd16(hdr + 10);
         // locate the BC subfield (normally the first and only one)
-        uint32_t bsize = 0;
-        if (xlen == 6 && hdr[12] == 66 && hdr[13] == 67) bsize = rd16(hdr + 16);
+        uint32_t bsize = 0; bool have_bc = false;
+        if (xlen == 6 && hdr[12] == 66 && hdr[13] == 67) { bsize = rd16(hdr + 16); have_bc = true; }
         else {
             std::vector<uint8_t> x(xlen);
-            if (pread(fd_, x.data(), xlen, off_t(coff + 12)) != ssize_t(xlen)) return false;
+            if (pread(fd_, x.data(), xlen, off_t(coff + 12)) != ssize_t(xlen)) return fail(coff, "truncated file (extra field)");
             for (uint32_t q = 0; q + 4 <= xlen;) {
                 const uint32_t slen = rd16(x.data() + q + 2);
-                if (x[q] == 66 && x[q + 1] == 67) bsize = rd16(x.data() + q + 4);
+                if (x[q] == 66 && x[q + 1] == 67 && slen == 2 && q + 6 <= xlen) { bsize = rd16(x.data() + q + 4); have_bc = true; }
                 q += 4 + slen;
             }
         }
+        if (!have_bc) return fail(coff, "gzip member without the BGZF 'BC' field");
         const uint32_t total = bsize + 1;
-        if (total < 12 + xlen + 8) return false;
+        if (total < 12 + xlen + 8) return fail(coff, "BSIZE smaller than the member header");
         const uint32_t clen = total - 12 - xlen - 8;
         if (cbuf_.size() < total + kInflateInPad) cbuf_.resize(total + kInflateInPad);
-        if (pread(fd_, cbuf_.data(), clen + 8, off_t(coff + 12 + xlen)) != ssize_t(clen + 8)) return false;
-        const uint32_t isize = rd32(cbuf_.data() + clen + 4);
-        if (v->data.size() < isize + kInflateOutPad) v->data.resize(std::max<size_t>(isize, size_t(1) << 16) + kInflateOutPad);
+        if (pread(fd_, cbuf_.data(), clen + 8, off_t(coff + 12 + xlen)) != ssize_t(clen + 8)) return fail(coff, "truncated file (short read of the member body)");
+        const uint32_t crc = rd32(cbuf_.data() + clen), isize = rd32(cbuf_.data() + clen + 4);
+        if (isize > (1u << 16)) return fail(coff, "ISIZE above 64 KiB");
+        if (v->data.size() < (size_t(1) << 16) + kInflateOutPad) v->data.resize((size_t(1) << 16) + kInflateOutPad);
         if (isize && !vtx_inflate_raw(cbuf_.data(), clen, v->data.data(), isize)) {
             // the single-pass decoder refused the member: let zlib have the last word before calling the file corrupt
             inflateReset(&zs_);
             zs_.next_in = cbuf_.data(); zs_.avail_in = clen;
             zs_.next_out = v->data.data(); zs_.avail_out = isize;
-            if (inflate(&zs_, Z_FINISH) != Z_STREAM_END) return false;
+            if (inflate(&zs_, Z_FINISH) != Z_STREAM_END || zs_.total_out != isize) return fail(coff, "inflate failed (corrupt data)");
         }
+        if (check_crc_ && uint32_t(crc32(crc32(0L, Z_NULL, 0), v->data.data(), isize)) != crc) return fail(coff, "CRC32 mismatch (corrupt data)");
         v->coff = coff; v->next = coff + total; v->len = isize;
         cur_ = v; block_pos_ = 0;
         return true;
     }
+public:
+    void set_check_crc(bool on) { check_crc_ = on; }
+private:
+    std::string err_;
+    bool check_crc_ = true;
     int fd_ = -1;
     uint64_t size_ = 0;
     z_stream zs_;
@@ -308,12 +327,18 @@ public:
         if (chunks_.empty()) done_ = true;
         return true;
     }
+    // false = end of the region OR an error: check bad() afterwards (a corrupt or truncated file must abort the run
+    // like the reference's `let rec = _rec?` does, main.rs:830, never shorten it silently)
     bool next(BamRecord* rec)
     {
         while (!done_) {
             if (!positioned_) {
                 if (cur_ >= chunks_.size()) { done_ = true; break; }
-                if (!bg_.seek(std::max(chunks_[cur_].beg, start_off_))) { done_ = true; break; }   // start_off_ is a record boundary
+                if (!bg_.seek(std::max(chunks_[cur_].beg, start_off_))) {          // start_off_ is a record boundary
+                    if (bg_.bad()) return fail(bg_.error());
+                    if (!bg_.at_eof()) return fail("BAM index points outside a BGZF block (index and file do not match)");
+                    done_ = true; break;
+                }
                 positioned_ = true;
             }
             if (bg_.tell() >= chunks_[cur_].end) { ++cur_; positioned_ = false; continue; }
@@ -323,16 +348,26 @@ public:
             uint32_t bs = 0;
             const uint8_t* body = nullptr;
             if (p) { bs = rd32(p); if (bs >= 32) { const uint8_t* q = bg_.peek(4 + size_t(bs)); if (q) body = q + 4; } }
+            if (bg_.bad()) return fail(bg_.error());
             if (body) {
                 bg_.skip(4 + size_t(bs));
-            } else {                                   // straddles a block boundary: assemble a copy
+            } else {                                   // straddles a block boundary (or the file ends here): assemble a copy
                 uint8_t b4[4];
-                if (!bg_.read(b4, 4)) { done_ = true; break; }
+                if (!bg_.read(b4, 1)) {                // not even one byte: a clean end of file between two records
+                    if (bg_.bad()) return fail(bg_.error());
+                    done_ = true; break;
+                }
+                if (!bg_.read(b4 + 1, 3)) return fail(bg_.bad() ? bg_.error() : "truncated BAM record (file ends inside a record)");
                 bs = rd32(b4);
-                if (bs < 32 || bs > (1u << 28)) { done_ = true; break; }        // not a BAM record: stop instead of allocating gigabytes
+                if (bs < 32 || bs > (1u << 28)) return fail("corrupt BAM record (block_size " + std::to_string(bs) + ")");
                 rec->own.resize(bs);
-                if (!bg_.read(rec->own.data(), bs)) { done_ = true; break; }
+                if (!bg_.read(rec->own.data(), bs)) return fail(bg_.bad() ? bg_.error() : "truncated BAM record (file ends inside a record)");
                 body = rec->own.data();
+            }
+            {   // the variable-length fields must lie inside the record: stager and endpos_of index them unchecked
+                const int64_t l_seq = int32_t(rd32(body + 16));
+                const uint64_t need = 32ull + body[8] + 4ull * rd16(body + 12) + (l_seq < 0 ? 0 : uint64_t(l_seq + 1) / 2 + uint64_t(l_seq));
+                if (l_seq < 0 || need > bs) return fail("corrupt BAM record at virtual offset " + std::to_string(voff) + " (fields exceed block_size)");
             }
             if (int32_t(rd32(body)) != tid_ || int64_t(int32_t(rd32(body + 4))) >= end_) {          // sorted file: nothing further can overlap
                 if (!hint_set_) { hint_voff_ = voff; hint_set_ = true; }
@@ -352,8 +387,18 @@ public:
         if (hint_set_) hint_valid_ = true;
         return false;
     }
+    bool bad() const { return !err_.empty(); }
+    const std::string& error() const { return err_; }
+    void set_check_crc(bool on) { bg_.set_check_crc(on); }
 
 private:
+    bool fail(const std::string& what)
+    {
+        if (err_.empty()) err_ = path_ + ": " + what;
+        done_ = true; hint_valid_ = false;
+        return false;
+    }
+    std::string err_;
     bool load_index(std::string* err)
     {
         std::string p = path_ + ".bai";

@@ -136,7 +136,9 @@ void check_inputs_exist(const Opts& o)
     const size_t dot = o.bam.find_last_of('.');
     const std::string ext = dot == std::string::npos ? "" : o.bam.substr(dot + 1);
     if (ext == "bam") {
-        if (!exists(o.bam + ".bai") && !exists(o.bam + ".csi")) { LOG_ERR("BAM index does not exist. Expecting %s.bai or %s.csi", o.bam.c_str(), o.bam.c_str()); exit(1); }
+        const bool bai = exists(o.bam + ".bai") || exists(o.bam.substr(0, dot) + ".bai");
+        if (!bai && exists(o.bam + ".csi")) { LOG_ERR("%s.csi: CSI indices are not supported by this build (no htslib); create a BAI index (samtools index -b)", o.bam.c_str()); exit(1); }
+        if (!bai) { LOG_ERR("BAM index does not exist. Expecting %s.bai", o.bam.c_str()); exit(1); }
     } else if (ext == "cram") {
         LOG_ERR("CRAM input is not supported by this build (no htslib); convert to BAM"); exit(1);
     } else { LOG_ERR("BAM file did not end in .bam or .cram. Unable to validate"); exit(1); }
@@ -298,18 +300,19 @@ int main(int argc, char** argv)
             cv.notify_all();
         }
     };
-    std::vector<std::thread> pool;
-    for (long t = 0; t < o.threads; ++t) pool.emplace_back(worker);
-
     HostMetrics hm;
     FILE* dump = nullptr;
     Arena arenas[3];
-    if (!o.dump_staged.empty()) {
+    if (!o.dump_staged.empty()) {            // before the pool starts: an early return must not leave joinable threads behind
         dump = fopen(o.dump_staged.c_str(), "wb");
         if (!dump) { LOG_ERR("cannot write %s", o.dump_staged.c_str()); return 1; }
         uint64_t hdr[2] = { recs.size(), bcs.keys.size() };
         fwrite(hdr, 8, 2, dump);
-    } else if (engine_ready.get() != 0) {
+    }
+    std::vector<std::thread> pool;
+    for (long t = 0; t < o.threads; ++t) pool.emplace_back(worker);
+
+    if (!dump && engine_ready.get() != 0) {
         printf("Vartrix error.\nError: %s\n", engine_err.c_str());
         { std::lock_guard<std::mutex> g(mu); failed = true; }
         cv.notify_all();
@@ -363,9 +366,9 @@ int main(int argc, char** argv)
     LOG_INFO("Number of VCF records skipped due to being multi-allelic: %llu", (unsigned long long)hm.num_multiallelic_recs);
     LOG_INFO("Number of (read, locus) pairs scored on the GPU: %llu", (unsigned long long)res.metrics.num_scored);
 
-    if (!write_mtx(o.out_matrix, recs.size(), bcs.keys.size(), res.n, res.row, res.col, res.val, &err)) { printf("Vartrix error.\nError: Error writing out-matrix\n"); rc = 1; }
+    if (!write_mtx(o.out_matrix, recs.size(), bcs.keys.size(), res.n, res.row, res.col, res.val, &err, unsigned(o.threads))) { printf("Vartrix error.\nError: Error writing out-matrix\n"); rc = 1; }
     if (o.scoring == "coverage")        // clap-2 default_value counts as present (main.rs:100, 385)
-        if (!write_mtx(o.ref_matrix, recs.size(), bcs.keys.size(), res.n, res.row, res.col, res.val2, &err)) { printf("Vartrix error.\nError: Error writing ref-matrix\n"); rc = 1; }
+        if (!write_mtx(o.ref_matrix, recs.size(), bcs.keys.size(), res.n, res.row, res.col, res.val2, &err, unsigned(o.threads))) { printf("Vartrix error.\nError: Error writing ref-matrix\n"); rc = 1; }
 
     if (!o.out_variants.empty()) {      // write_variants (main.rs:1166-1179): chrom_pos0
         validate_output_path(o.out_variants);

@@ -229,6 +229,7 @@ inline bool stage_loci(const std::vector<VcfRecord>& recs, size_t lo, size_t hi,
                 }
                 out->cand_read.push_back(rid);
             }
+            if (bam.bad()) { *err = bam.error(); return false; }            // corrupt / truncated BAM: abort (main.rs:830)
         }
         out->cand_start.push_back(out->cand_read.size());
     }

@@ -45,26 +45,37 @@ constexpr uint32_t kBIAS2 = pack2(kBias, kBias);                    // biased 0 
 constexpr uint32_t kGOE2 = pack2(kBias + kGoe, kBias + kGoe);       // biased (0 + gap): H = 0 seen through H + go + ge
 constexpr uint32_t kNEG2 = pack2(0, 0);                             // biased -16384 ("minus infinity")
 constexpr uint32_t kGoeAdd = (uint32_t(uint16_t(int16_t(kGoe - 1))) << 16) | uint32_t(uint16_t(int16_t(kGoe)));   // + (gap, gap) incl. the carry
-// measured (profiles/r01_add_variants.txt): letting ptxas split the packed adds between VIADD (ALU) and IMAD.IADD
-// (FMA) and chaining E through H + goe beats forcing full IMADs (those run on the half-width "FMA heavy" pipe)
-#ifndef VTX_SW_PADD
-#define VTX_SW_PADD 1        // 0: force IMAD (x * one + c); 1: plain add, ptxas balances VIADD / IMAD.IADD; 2: mad.lo with literal 1
-#endif
-#ifndef VTX_SW_EG
-#define VTX_SW_EG 0          // 1: E chain through tf + goe (one instruction per cell, one more add); 0: through H + goe
+// The remaining plain add of a cell, H + gap.  ptxas places a plain `x + c` on the ALU pipe (VIADD), which the DPX
+// instructions already saturate; written as x * one + c with a run-time `one` it is an IMAD on the FMA pipe instead.
+// VTX_SW_HADD: 0 = plain add everywhere, 1 = IMAD everywhere, 2 = IMAD on even columns (splits the adds between the pipes).
+#ifndef VTX_SW_HADD
+#define VTX_SW_HADD 0
 #endif
 __device__ __forceinline__ uint32_t padd(uint32_t x, uint32_t one, uint32_t c)
 {
-#if VTX_SW_PADD == 0
-    return x * one + c;
-#elif VTX_SW_PADD == 2
-    (void)one;
-    uint32_t d;
-    asm("mad.lo.u32 %0, %1, 1, %2;" : "=r"(d) : "r"(x), "r"(c));
-    return d;
-#else
     (void)one;
     return x + c;
+}
+__device__ __forceinline__ uint32_t hadd(uint32_t h, uint32_t one, int col)
+{
+#if VTX_SW_HADD == 1
+    (void)col;
+    return h * one + kGoeAdd;
+#elif VTX_SW_HADD == 2
+    return (col & 1) ? h + kGoeAdd : h * one + kGoeAdd;
+#else
+    (void)one; (void)col;
+    return h + kGoeAdd;
+#endif
+}
+// H = max(diag + s, F, E, 0) of one cell (biased halves; `diag` is stored as H + goe and `s` as s - goe)
+__device__ __forceinline__ uint32_t sw_h(uint32_t diag, uint32_t one, uint32_t s, uint32_t f, uint32_t e)
+{
+#if VTX_SW_FUSE
+    (void)one;
+    return __vimax3_s16x2(__viaddmax_s16x2(diag, s, f), e, kBIAS2);
+#else
+    return __vmaxs2(__vimax3_s16x2(padd(diag, one, s), f, kBIAS2), e);
 #endif
 }
 // profile entries are biased by -kGoe because the stored state is H + kGoe
@@ -277,7 +288,7 @@ __global__ void __launch_bounds__(TileClass<CLS>::THREADS, TileClass<CLS>::MINB)
                     const uint4* prow = reinterpret_cast<const uint4*>(lane_prof + my_codes[t - t0]);
                     uint32_t diag = diag_save;
                     diag_save = hl;
-                    // E[i][c] = max(E[i][c-1] + ge, H[i][c-1] + goe); with VTX_SW_EG the second operand is tf + goe
+                    // E[i][c] = max(E[i][c-1] + ge, H[i][c-1] + goe)
                     uint32_t e = el, eg = hl, hleft = hl;
 #pragma unroll
                     for (int q = 0; q < (C + 3) / 4; ++q) {
@@ -289,19 +300,12 @@ __global__ void __launch_bounds__(TileClass<CLS>::THREADS, TileClass<CLS>::MINB)
                             const int c = 4 * q + k;
                             if (c < C) {
                                 const uint32_t fc = __viaddmax_s16x2(f[c], kGE2, hg[c]);     // F[i][c]
-                                const uint32_t tt = padd(diag, one, sv[k]);                 // H[i-1][c-1] + s
-                                const uint32_t tf = __vimax3_s16x2(tt, fc, kBIAS2);         // max(H[i-1][c-1] + s, F, 0)
                                 e = __viaddmax_s16x2(e, kGE2, eg);                          // E[i][c]
-#if VTX_SW_EG
-                                eg = padd(tf, one, kGoeAdd);                                // tf + goe
-#endif
-                                const uint32_t h = __vmaxs2(tf, e);                         // H[i][c]
+                                const uint32_t h = sw_h(diag, one, sv[k], fc, e);           // H[i][c]
                                 hh[k] = h;
                                 diag = hg[c];
-                                hleft = padd(h, one, kGoeAdd);                              // H + goe
-#if !VTX_SW_EG
+                                hleft = hadd(h, one, c);                                    // H + goe
                                 eg = hleft;
-#endif
                                 hg[c] = hleft;
                                 f[c] = fc;
                             } else {

@@ -39,21 +39,32 @@ constexpr int kFoldPPW = 4;            // pairs per warp tile
 constexpr int kFoldR = 19;             // read rows per lane in the middle (8 x 19 = 152)
 constexpr int kFoldMaxRead = 8 * kFoldR;
 constexpr int kFoldMaxMid = 40;        // allele columns: n <= 2 * 96 + 40 = 232
-constexpr int kFoldRows = kFoldMaxRead;              // boundary rows kept per read
+// boundary rows kept per read; 156 (not 152) so that the four reads of a tile start 8, 16 and 24 banks apart
+// (152 rows x 8 bytes put reads 0/2 and 1/3 on the same banks: a 2-way conflict on every boundary store and load)
+constexpr int kFoldRows = kFoldMaxRead + 4;
 constexpr int kFoldCodeStride = kFoldMaxRead + 16;   // row codes per read and direction (8 sentinels either side)
 // 320 threads x 2 CTAs = 20 warps/SM (96 registers, a few spills in the tile prologue only): 9.32 ms vs 9.82 ms at
 // 256 x 2 on the config-3 shape; merging the profile rows with one IADD3 instead of IMAD + add, or unrolling the
 // row loop, does not pay at that occupancy (profiles/r01_fold_variants.txt)
+#ifndef VTX_FOLD_UNROLL
+#define VTX_FOLD_UNROLL 1
+#endif
+// 1: the reverse profile is stored in the HIGH half, so the (forward | reverse) substitution word is a plain add of the two
+// profile words (eligible for IMAD.IADD / VIADD) instead of a full IMAD b * 65536 + a (half-rate FMA-heavy pipe)
+#ifndef VTX_FOLD_PRESHIFT
+#define VTX_FOLD_PRESHIFT 0
+#endif
 #ifndef VTX_FOLD_THREADS
 #define VTX_FOLD_THREADS 320
 #endif
 constexpr int kFoldThreads = VTX_FOLD_THREADS;
+constexpr int kFoldUnroll = VTX_FOLD_UNROLL;         // row-loop unrolling of the main pass
 
 __host__ __device__ constexpr size_t fold_warp_bytes()
 {
     size_t b = size_t(2 * 5 * kFoldP) * 4;                       // forward + reverse profile
     b += size_t(kFoldMaxMid) * 8 * 4;                            // allele-column table [column][read code]
-    b += size_t(kFoldPPW) * kFoldRows * 8;                       // boundary column (forward | reverse), per read and row
+    b += size_t(kFoldPPW) * kFoldRows * 8 + 32;                  // boundary column (forward | reverse), per read and row
     b += size_t(2 * kFoldPPW) * kFoldCodeStride;                 // row codes, forward and reversed
     return (b + 15) & ~size_t(15);
 }
@@ -77,7 +88,7 @@ __global__ void __launch_bounds__(kFoldThreads, 2) vtx_k_sw_fold(const SwArgs a)
     uint32_t* profR = profF + 5 * RS1;
     uint32_t* midtab = profR + 5 * RS1;
     uint2* bnd = reinterpret_cast<uint2*>(midtab + kFoldMaxMid * 8);
-    uint8_t* codes = reinterpret_cast<uint8_t*>(bnd + kFoldPPW * kFoldRows);
+    uint8_t* codes = reinterpret_cast<uint8_t*>(bnd + kFoldPPW * kFoldRows + 4);
 
     const uint32_t n_tiles = __ldg(a.tile_start + a.n_loci);
     uint32_t cached_locus = 0xFFFFFFFFu;
@@ -113,7 +124,7 @@ __global__ void __launch_bounds__(kFoldThreads, 2) vtx_k_sw_fold(const SwArgs a)
 #pragma unroll
                     for (uint32_t r = 0; r < 5; ++r) {
                         profF[r * RS1 + j] = uint32_t(r == fb ? kProfMatch : kProfMis);      // low half only: merged per step
-                        profR[r * RS1 + j] = uint32_t(r == sb ? kProfMatch : kProfMis);
+                        profR[r * RS1 + j] = uint32_t(r == sb ? kProfMatch : kProfMis) << (VTX_FOLD_PRESHIFT ? 16 : 0);
                     }
                 }
                 const int lmax = max(mid_ref, mid_alt);
@@ -153,7 +164,11 @@ __global__ void __launch_bounds__(kFoldThreads, 2) vtx_k_sw_fold(const SwArgs a)
             for (int o = 16; o >= 1; o >>= 1) mmax = max(mmax, __shfl_xor_sync(0xffffffffu, mmax, o));
             __syncwarp();
 
+            // The boundary of row r lives at entry r + 7: lane 7 stores at entry t in EVERY step (no `t >= 7` test in the
+            // loop); its first 7 stores are scratch.  Entries 156..158 of a read (rows 149..151) fall on the scratch entries
+            // 0..2 of the next read, which that read wrote 150 steps earlier and nobody reads; the last read has 4 spare.
             uint2* my_bnd = bnd + u * kFoldRows;
+            const uint2* row_bnd = my_bnd + 7;
             uint32_t best;
             // =========================== main pass: forward prefix | reversed suffix ===========================
             {
@@ -167,6 +182,7 @@ __global__ void __launch_bounds__(kFoldThreads, 2) vtx_k_sw_fold(const SwArgs a)
                 const uint32_t* lane_f = profF + g * C1;
                 const uint32_t* lane_r = profR + g * C1;
                 const int steps = mmax + 7;
+#pragma unroll kFoldUnroll
                 for (int t = 0; t < steps; ++t) {
                     uint32_t hl = __shfl_up_sync(0xffffffffu, hg_last, 1, 8);
                     uint32_t el = __shfl_up_sync(0xffffffffu, e_last, 1, 8);
@@ -180,18 +196,21 @@ __global__ void __launch_bounds__(kFoldThreads, 2) vtx_k_sw_fold(const SwArgs a)
                     for (int q = 0; q < C1 / 4; ++q) {
                         const uint4 a4 = pa[q], b4 = pb[q];
                         // {s_fwd, s_rev} = s_fwd + (s_rev << 16) as an IMAD (FMA pipe), like vtx_k_sw_split's phase 1
+#if VTX_FOLD_PRESHIFT
+                        const uint32_t sv[4] = { b4.x + a4.x, b4.y + a4.y, b4.z + a4.z, b4.w + a4.w };
+#else
                         const uint32_t sv[4] = { b4.x * k64k + a4.x, b4.y * k64k + a4.y, b4.z * k64k + a4.z, b4.w * k64k + a4.w };
+#endif
                         uint32_t hh[4];
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             const int c = 4 * q + k;
                             const uint32_t fc = __viaddmax_s16x2(f[c], kGE2, hg[c]);
-                            const uint32_t tf = __vimax3_s16x2(padd(diag, one, sv[k]), fc, kBIAS2);
                             e = __viaddmax_s16x2(e, kGE2, eg);
-                            const uint32_t h = __vmaxs2(tf, e);
+                            const uint32_t h = sw_h(diag, one, sv[k], fc, e);
                             hh[k] = h;
                             diag = hg[c];
-                            hleft = padd(h, one, kGoeAdd);
+                            hleft = hadd(h, one, c);
                             eg = hleft;
                             hg[c] = hleft;
                             f[c] = fc;
@@ -201,7 +220,7 @@ __global__ void __launch_bounds__(kFoldThreads, 2) vtx_k_sw_fold(const SwArgs a)
                     }
                     hg_last = hleft;
                     e_last = e;
-                    if (g == 7 && t >= 7) my_bnd[t - 7] = make_uint2(hleft, e);      // columns P-1 (fwd) / n-P (rev) of row t-7
+                    if (g == 7) my_bnd[t] = make_uint2(hleft, e);                    // columns P-1 (fwd) / n-P (rev) of row t-7
                 }
 #pragma unroll
                 for (int o = 4; o >= 1; o >>= 1) best = __vmaxs2(best, __shfl_xor_sync(0xffffffffu, best, o));
@@ -219,7 +238,7 @@ __global__ void __launch_bounds__(kFoldThreads, 2) vtx_k_sw_fold(const SwArgs a)
                 for (int c = 0; c < R; ++c) {
                     const int row = R * g + c;
                     uint2 b = make_uint2(kGOE2, kNEG2);
-                    if (row < mmax) b = my_bnd[row];
+                    if (row < mmax) b = row_bnd[row];
                     hg[c] = __byte_perm(b.x, 0, 0x1010);                             // forward half, for ref and alt
                     e[c] = __byte_perm(b.y, 0, 0x1010);
                     rc[c] = uint32_t(cf[c]) * 4u;
@@ -231,7 +250,7 @@ __global__ void __launch_bounds__(kFoldThreads, 2) vtx_k_sw_fold(const SwArgs a)
                     for (int c = 0; c < R; ++c) {
                         const int rr = m - 2 - (R * g + c);
                         uint2 b = make_uint2(kGOE2, kGOE2);                          // Hr = 0; Er such that E + Er - go < H
-                        if (rr >= 0) b = my_bnd[rr];
+                        if (rr >= 0) b = row_bnd[rr];
                         const uint32_t ph = __byte_perm(b.x, 0, 0x3232), pe = __byte_perm(b.y, 0, 0x3232);
                         const uint32_t x1 = hg[c] + ph + kJuncH2;
                         const uint32_t x2 = e[c] + pe + kJuncE2;
@@ -241,7 +260,7 @@ __global__ void __launch_bounds__(kFoldThreads, 2) vtx_k_sw_fold(const SwArgs a)
                 };
                 // H(row above the strip, column before the first allele column) + gap: the forward boundary of that row
                 uint32_t diag_save = kGOE2;
-                if (g > 0 && R * g - 1 < mmax) diag_save = __byte_perm(my_bnd[R * g - 1].x, 0, 0x1010);
+                if (g > 0 && R * g - 1 < mmax) diag_save = __byte_perm(row_bnd[R * g - 1].x, 0, 0x1010);
                 uint32_t hup_last = kGOE2, f_last = kNEG2;
                 const uint8_t* tab = reinterpret_cast<const uint8_t*>(midtab) - 32 * g;
                 const int steps = lmax + 7;
@@ -260,12 +279,11 @@ __global__ void __launch_bounds__(kFoldThreads, 2) vtx_k_sw_fold(const SwArgs a)
                         for (int c = 0; c < R; ++c) {
                             const uint32_t sv = *reinterpret_cast<const uint32_t*>(trow + rc[c]);
                             const uint32_t ec = __viaddmax_s16x2(e[c], kGE2, hg[c]);          // E(r, k)
-                            const uint32_t tf = __vimax3_s16x2(padd(diag, one, sv), ec, kBIAS2);
                             f = __viaddmax_s16x2(f, kGE2, fg);                                // F(r, k)
-                            const uint32_t h = __vmaxs2(tf, f);
+                            const uint32_t h = sw_h(diag, one, sv, ec, f);
                             hh[c & 1] = h;
                             diag = hg[c];
-                            hdown = padd(h, one, kGoeAdd);
+                            hdown = hadd(h, one, c);
                             fg = hdown;
                             hg[c] = hdown;
                             e[c] = ec;

@@ -192,18 +192,12 @@ __global__ void __launch_bounds__(SplitClass<SCLS>::THREADS, SplitClass<SCLS>::M
                         for (int k = 0; k < 4; ++k) {
                             const int c = 4 * q + k;
                             const uint32_t fc = __viaddmax_s16x2(f[c], kGE2, hg[c]);
-                            const uint32_t tf = __vimax3_s16x2(padd(diag, one, sv[k]), fc, kBIAS2);
                             e = __viaddmax_s16x2(e, kGE2, eg);
-#if VTX_SW_EG
-                            eg = padd(tf, one, kGoeAdd);
-#endif
-                            const uint32_t h = __vmaxs2(tf, e);
+                            const uint32_t h = sw_h(diag, one, sv[k], fc, e);
                             hh[k] = h;
                             diag = hg[c];
-                            hleft = padd(h, one, kGoeAdd);
-#if !VTX_SW_EG
+                            hleft = hadd(h, one, c);
                             eg = hleft;
-#endif
                             hg[c] = hleft;
                             f[c] = fc;
                         }
@@ -263,18 +257,12 @@ __global__ void __launch_bounds__(SplitClass<SCLS>::THREADS, SplitClass<SCLS>::M
                             const int c = 4 * q + k;
                             if (c < C2) {
                                 const uint32_t fc = __viaddmax_s16x2(f[c], kGE2, hg[c]);
-                                const uint32_t tf = __vimax3_s16x2(padd(diag, one, sv[k]), fc, kBIAS2);
                                 e = __viaddmax_s16x2(e, kGE2, eg);
-#if VTX_SW_EG
-                                eg = padd(tf, one, kGoeAdd);
-#endif
-                                const uint32_t h = __vmaxs2(tf, e);
+                                const uint32_t h = sw_h(diag, one, sv[k], fc, e);
                                 hh[k] = h;
                                 diag = hg[c];
-                                hleft = padd(h, one, kGoeAdd);
-#if !VTX_SW_EG
+                                hleft = hadd(h, one, c);
                                 eg = hleft;
-#endif
                                 hg[c] = hleft;
                                 f[c] = fc;
                             } else {
