@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define VTX_ABI_VERSION 1
+#define VTX_ABI_VERSION 2     /* 2: vtx_batch2 / vtx_submit2 (slim staging layout), vtx_gather_start / _wait, band fields in vtx_config */
 
 /* error codes */
 #define VTX_OK             0
@@ -64,7 +64,17 @@ typedef struct vtx_config {
     int32_t  min_score;     /* MIN_SCORE, main.rs:30 (25) */
     void*    stream;        /* cudaStream_t to enqueue on; NULL = library-owned non-blocking stream */
     uint32_t flags;         /* VTX_F_* */
+    /* The reference aligns with bio 0.30.0's banded aligner, Aligner::new(GAP_OPEN, GAP_EXTEND, score, K, W) (main.rs:27-38,
+     * 899).  VTX_BAND_FULL scores the whole matrix: the exact upper bound of every band, equal to the banded score
+     * whenever the optimal path stays inside the band, and what reproduces the reference's 12 golden matrices.
+     * band_k / band_w: 0 = the reference's constants (6 / 20); they only matter for VTX_BAND_MODEL. */
+    int32_t  band_k;        /* K, main.rs:33 */
+    int32_t  band_w;        /* W, main.rs:34 */
+    int32_t  band_mode;     /* VTX_BAND_* */
 } vtx_config;
+
+#define VTX_BAND_FULL   0   /* full-matrix affine local score (default) */
+#define VTX_BAND_MODEL  1   /* score restricted to the k-mer-chain band model of SURVEY Appendix B (oracle: vtxo_sw_band_model) */
 
 #define VTX_F_KEEP_SCORES 1u    /* also keep per-pair raw scores on the device (debug / parity) */
 #define VTX_F_NO_SPLIT    2u    /* use only the single-phase Smith-Waterman kernels (neither shared-prefix nor folded) */
@@ -115,6 +125,46 @@ typedef struct vtx_batch {
     const uint32_t* cand_read;     /* [n_cand] */
 } vtx_batch;
 
+/*
+ * The slim staging layout (ABI 2).  Same content as vtx_batch, ~95 instead of ~138 bytes per candidate on the
+ * BASELINE shapes, because host->device bytes are what the end-to-end path pays for:
+ *   reads      : `read_nib` holds the reads back to back in id order, each starting on a 4-byte boundary; read_off4 ==
+ *                NULL says exactly that (offsets are then derived on the device), else read_off4[r] * 4 is the byte offset
+ *                of read r.  read_len is u16 (longer reads: use vtx_batch).
+ *   cell tags  : one u64 per read -- vtx_pack_cb() of the tag bytes (an injective code of `[ACGT]{1,24}(-[1-9][0-9]?)?`,
+ *                i.e. of every Cell Ranger barcode), VTX_NO_CB_KEY when the read has no Z-typed tag, or
+ *                VTX_CB_EXOTIC | i for a tag the code cannot express: its bytes are cb_bytes[cb_off[i] .. cb_off[i+1]).
+ *                The comparison with the barcode list stays exact byte equality (main.rs:745): equal strings have equal
+ *                codes, and an exotic tag can only equal an exotic barcode.
+ *   UMIs       : read_umi_key may be NULL when the ctx was created with use_umi == 0 (the keys are never read).
+ *   candidates : cand_read == NULL means candidate c is read c (n_cand == n_reads: no read serves two loci).
+ */
+#define VTX_NO_CB_KEY  0xFFFFFFFFFFFFFFFFull
+#define VTX_CB_EXOTIC  0x8000000000000000ull   /* | index into cb_off */
+typedef struct vtx_batch2 {
+    uint32_t        n_loci;
+    const uint32_t* locus_row;     /* [n_loci] */
+    const uint8_t*  hap_bytes;
+    uint64_t        hap_bytes_len;
+    const uint32_t* ref_off;       /* [n_loci] multiples of 16 */
+    const uint32_t* ref_len;
+    const uint32_t* alt_off;
+    const uint32_t* alt_len;
+    const uint64_t* cand_start;    /* [n_loci + 1] */
+    uint32_t        n_reads;
+    const uint8_t*  read_nib;
+    uint64_t        read_nib_len;
+    const uint32_t* read_off4;     /* [n_reads] byte offset / 4, or NULL (dense) */
+    const uint16_t* read_len;      /* [n_reads] bases */
+    const uint64_t* read_cb_key;   /* [n_reads] */
+    uint32_t        n_exotic_cb;
+    const uint8_t*  cb_bytes;      /* exotic tags only */
+    const uint32_t* cb_off;        /* [n_exotic_cb + 1] */
+    const uint64_t* read_umi_key;  /* [n_reads] or NULL (use_umi == 0) */
+    uint64_t        n_cand;
+    const uint32_t* cand_read;     /* [n_cand] or NULL (identity) */
+} vtx_batch2;
+
 /* The device-side share of main.rs:449-459 (the host keeps the counters of its own filters). */
 typedef struct vtx_metrics {
     uint64_t num_not_cell_bc;      /* main.rs:874 */
@@ -159,9 +209,13 @@ int         vtx_set_barcodes(vtx_ctx* ctx, const uint8_t* bytes, const uint32_t*
 /* Enqueue one shard (asynchronous on the ctx stream).  Shards must arrive in ascending row order. */
 int         vtx_submit(vtx_ctx* ctx, const vtx_batch* host_batch);
 int         vtx_submit_device(vtx_ctx* ctx, const vtx_batch* device_batch);
+/* The same for the slim layout (host pointers / device pointers). */
+int         vtx_submit2(vtx_ctx* ctx, const vtx_batch2* host_batch);
+int         vtx_submit2_device(vtx_ctx* ctx, const vtx_batch2* device_batch, uint32_t max_read_len, uint32_t max_hap_len);
 /* Device batches cannot be scanned by the host: state the longest read and the widest haplotype window (upper
- * bounds; buffers are sized and kernels selected from them, so a batch that exceeds them is undefined behaviour;
- * plain vtx_submit_device assumes reads <= 1024 bases and windows <= 320 bytes). */
+ * bounds; buffers are sized and kernels selected from them.  A locus with a longer read or a wider window than promised
+ * is detected on the device and skipped, and the next vtx_finish / vtx_finish_device returns VTX_E_INVALID.  Plain
+ * vtx_submit_device promises reads <= 1024 bases and windows <= 320 bytes). */
 int         vtx_submit_device_ex(vtx_ctx* ctx, const vtx_batch* device_batch, uint32_t max_read_len, uint32_t max_hap_len);
 /* Wait for everything submitted since the last finish and hand back the triplets (host arrays). */
 int         vtx_finish(vtx_ctx* ctx, vtx_result* out);
@@ -184,6 +238,11 @@ int         vtx_score_pairs(vtx_ctx* ctx, const vtx_batch* host_batch, uint64_t 
 /* Injective UMI key for strings over {A,C,G,T,N} up to 18 bases (3 bits/base + 5-bit length, < 2^59).
  * Returns VTX_NO_UMI if the string does not fit; the caller then interns it as (1 << 61) | id. */
 uint64_t    vtx_pack_umi(const uint8_t* s, uint32_t len);
+
+/* Injective code of a cell-barcode tag of the form [ACGT]{1,24}(-N)? with N = 1..99 written without a leading zero:
+ * 2 bits per base, 5 bits length, 7 bits N (0 = no suffix); < 2^60.  Returns VTX_NO_CB_KEY if the bytes have another
+ * form -- the caller then lists them as an exotic tag (VTX_CB_EXOTIC | i). */
+uint64_t    vtx_pack_cb(const uint8_t* s, uint32_t len);
 
 /* Device-side timings of the last finished submit, milliseconds (CUDA events on the ctx stream). */
 typedef struct vtx_timing {
@@ -210,6 +269,14 @@ int         vtx_comm_init(vtx_ctx* ctx, const uint8_t id[128], int32_t rank, int
  * (= row order when rank r holds the r-th contiguous locus range), on every rank.  `out` holds DEVICE
  * pointers (metrics summed over ranks); the rank that writes the matrix calls vtx_fetch on it. */
 int         vtx_gather(vtx_ctx* ctx, vtx_result* out);
+/* The same exchange, asynchronous and optionally rooted.  vtx_gather_start enqueues it on the ctx's communication
+ * stream and returns; kernels of later submits overlap it (their first write into the local result arrays waits for
+ * it on the device).  root = VTX_GATHER_ALL: allgatherv (every rank ends up with everything).  root = r: only rank r
+ * -- the one that writes the matrix -- receives (ncclSend / ncclRecv); on the other ranks vtx_gather_wait returns the
+ * total `n` and the summed metrics with NULL arrays.  One gather may be in flight per ctx. */
+#define VTX_GATHER_ALL (-1)
+int         vtx_gather_start(vtx_ctx* ctx, int32_t root);
+int         vtx_gather_wait(vtx_ctx* ctx, vtx_result* out);
 
 #ifdef __cplusplus
 }

@@ -28,14 +28,20 @@ SYMBOLS = [
     "vtx_abi_version", "vtx_create", "vtx_destroy", "vtx_last_error", "vtx_host_alloc", "vtx_host_free",
     "vtx_set_barcodes", "vtx_submit", "vtx_submit_device", "vtx_submit_device_ex", "vtx_finish",
     "vtx_finish_device", "vtx_fetch", "vtx_sync", "vtx_wait_copies", "vtx_score_pairs", "vtx_pack_umi", "vtx_last_timing", "vtx_last_tile_counts",
-    "vtx_comm_unique_id", "vtx_comm_init", "vtx_gather",
+    "vtx_comm_unique_id", "vtx_comm_init", "vtx_gather", "vtx_gather_start", "vtx_gather_wait",
+    "vtx_submit2", "vtx_submit2_device", "vtx_pack_cb",
 ]
+NO_CB_KEY = 0xFFFFFFFFFFFFFFFF
+CB_EXOTIC = 0x8000000000000000
+GATHER_ALL = -1
+BAND_FULL, BAND_MODEL = 0, 1
 
 
 class Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("mode", C.c_int32), ("use_umi", C.c_int32), ("match", C.c_int32),
                 ("mismatch", C.c_int32), ("gap_open", C.c_int32), ("gap_extend", C.c_int32),
-                ("min_score", C.c_int32), ("stream", C.c_void_p), ("flags", C.c_uint32)]
+                ("min_score", C.c_int32), ("stream", C.c_void_p), ("flags", C.c_uint32),
+                ("band_k", C.c_int32), ("band_w", C.c_int32), ("band_mode", C.c_int32)]
 
 
 class Batch(C.Structure):
@@ -48,6 +54,20 @@ class Batch(C.Structure):
         ("read_off", C.c_void_p), ("read_len", C.c_void_p),
         ("cb_bytes", C.c_void_p), ("cb_bytes_len", C.c_uint64),
         ("read_cb_off", C.c_void_p), ("read_cb_len", C.c_void_p), ("read_umi_key", C.c_void_p),
+        ("n_cand", C.c_uint64), ("cand_read", C.c_void_p),
+    ]
+
+
+class Batch2(C.Structure):          # vtx_batch2: the slim staging layout
+    _fields_ = [
+        ("n_loci", C.c_uint32), ("locus_row", C.c_void_p),
+        ("hap_bytes", C.c_void_p), ("hap_bytes_len", C.c_uint64),
+        ("ref_off", C.c_void_p), ("ref_len", C.c_void_p), ("alt_off", C.c_void_p), ("alt_len", C.c_void_p),
+        ("cand_start", C.c_void_p),
+        ("n_reads", C.c_uint32), ("read_nib", C.c_void_p), ("read_nib_len", C.c_uint64),
+        ("read_off4", C.c_void_p), ("read_len", C.c_void_p), ("read_cb_key", C.c_void_p),
+        ("n_exotic_cb", C.c_uint32), ("cb_bytes", C.c_void_p), ("cb_off", C.c_void_p),
+        ("read_umi_key", C.c_void_p),
         ("n_cand", C.c_uint64), ("cand_read", C.c_void_p),
     ]
 
@@ -112,6 +132,16 @@ def load():
     L.vtx_last_timing.argtypes = [C.c_void_p, C.POINTER(Timing)]
     L.vtx_last_tile_counts.restype = C.c_int
     L.vtx_last_tile_counts.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.c_uint32]
+    L.vtx_submit2.restype = C.c_int
+    L.vtx_submit2.argtypes = [C.c_void_p, C.POINTER(Batch2)]
+    L.vtx_submit2_device.restype = C.c_int
+    L.vtx_submit2_device.argtypes = [C.c_void_p, C.POINTER(Batch2), C.c_uint32, C.c_uint32]
+    L.vtx_pack_cb.restype = C.c_uint64
+    L.vtx_pack_cb.argtypes = [C.c_char_p, C.c_uint32]
+    L.vtx_gather_start.restype = C.c_int
+    L.vtx_gather_start.argtypes = [C.c_void_p, C.c_int32]
+    L.vtx_gather_wait.restype = C.c_int
+    L.vtx_gather_wait.argtypes = [C.c_void_p, C.POINTER(Result)]
     L.vtx_comm_unique_id.restype = C.c_int
     L.vtx_comm_unique_id.argtypes = [C.c_void_p]
     L.vtx_comm_init.restype = C.c_int

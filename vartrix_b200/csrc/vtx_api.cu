@@ -17,6 +17,7 @@ using namespace vtx;
 namespace {
 
 thread_local std::string g_create_error;
+constexpr int kBandK = 6, kBandW = 20;       // K, W of banded::Aligner::new (main.rs:33-34, 899)
 
 struct DBuf {
     void* p = nullptr;
@@ -37,6 +38,7 @@ struct TimeRec {   // CUDA events of one submit
 struct InSlot {
     DBuf locus_row, hap, ref_off, ref_len, alt_off, alt_len, cand_start, read_nib, read_off, read_len, cb_bytes,
         read_cb_off, read_cb_len, read_umi, cand_read;
+    DBuf read_off4, read_len16, read_cb_key, cb_off_ex;     // slim layout (vtx_batch2)
     cudaEvent_t copy_done = nullptr, free_ev = nullptr;
     bool used = false;
 };
@@ -53,6 +55,9 @@ struct vtx_ctx {
 
     // barcode table
     DBuf bc_slot, bc_bytes, bc_off;
+    DBuf bck_key, bck_idx;            // the barcodes that have a vtx_pack_cb code, keyed by it
+    uint32_t bck_cap = 0;
+    DBuf x_read_off, x_read_len, x_units, x_off4;      // slim layout expanded to the internal read arrays
     uint32_t bc_cap = 0, n_barcodes = 0;
     bool have_barcodes = false;
 
@@ -92,6 +97,12 @@ struct vtx_ctx {
     size_t g_host_cap = 0;
     DBuf g_dev[7];
     DBuf g_counts;
+    cudaStream_t comm_stream = nullptr;          // the gather runs here so that later submits overlap it
+    cudaEvent_t ev_counts = nullptr, ev_gather = nullptr, ev_results = nullptr;
+    uint64_t* h_counts = nullptr;                // pinned: [n_ranks + 1][4]
+    bool gather_pending = false;                 // started, not yet waited for
+    bool gather_guard = false;                   // ev_gather must be awaited (on the device) before r_* are overwritten
+    vtx_result g_out{};
 };
 
 namespace {
@@ -163,11 +174,24 @@ struct DevBatch {   // device pointers
     const uint32_t* locus_row; const uint8_t* hap; const uint32_t *ref_off, *ref_len, *alt_off, *alt_len;
     const uint64_t* cand_start; const uint8_t* read_nib; const uint64_t* read_off; const uint32_t* read_len;
     const uint8_t* cb_bytes; const uint32_t* read_cb_off; const uint16_t* read_cb_len; const uint64_t* read_umi;
-    const uint32_t* cand_read;
+    const uint32_t* cand_read;       // nullptr: candidate c is read c
+    // slim layout: cell tags as codes (then cb_bytes / cb_off_ex hold the exotic tags only)
+    const uint64_t* read_cb_key = nullptr; const uint32_t* cb_off_ex = nullptr;
+    uint32_t class_mask = ~0u;       // tile classes that may get tiles (host batches: from the windows; device batches: all)
     uint32_t max_read_len = 0, max_hap_len = 0;
     uint64_t max_depth = ~0ull;      // most candidates of one locus (unknown for device batches: assume deep)
 };
 
+// the allow_* switches of run_sw, shared with the host-side class mask
+struct SwAllow { bool split, multi, fold; };
+SwAllow sw_allow(const vtx_ctx* ctx, uint32_t max_read, uint32_t max_hap)
+{
+    SwAllow a;
+    a.split = max_read <= uint32_t(kSplitMaxRead) && !(ctx->cfg.flags & VTX_F_NO_SPLIT);
+    a.multi = max_read <= uint32_t(kMultiMaxRead) && max_hap > uint32_t(class_max_n(kNumFastClasses - 1));
+    a.fold = !(ctx->cfg.flags & (VTX_F_NO_SPLIT | VTX_F_NO_FOLD));
+    return a;
+}
 template <int CLS>
 int launch_sw_class(vtx_ctx* ctx, SwArgs a, uint64_t* launches)
 {
@@ -228,12 +252,12 @@ int run_sw(vtx_ctx* ctx, const DevBatch& b, uint32_t n_pairs_ub, const uint32_t*
     ENS(ctx->tstart, size_t(kNumClasses) * (nl + 1) * 4);
     ENS(ctx->tile_counters, 64);
     const int force_slow = 0;       // reads of any supported length run on the single-phase classes (row blocks)
-    const int allow_split = (b.max_read_len <= uint32_t(kSplitMaxRead) && !(ctx->cfg.flags & VTX_F_NO_SPLIT)) ? 1 : 0;
-    const int allow_multi = (b.max_read_len <= uint32_t(kMultiMaxRead) && b.max_hap_len > uint32_t(class_max_n(kNumFastClasses - 1))) ? 1 : 0;
-    const int allow_fold = (ctx->cfg.flags & (VTX_F_NO_SPLIT | VTX_F_NO_FOLD)) ? 0 : 1;      // per locus: windows and read lengths decide
+    const SwAllow allow = sw_allow(ctx, b.max_read_len, b.max_hap_len);
+    const int allow_split = allow.split, allow_multi = allow.multi, allow_fold = allow.fold;   // fold: per locus, windows and read lengths decide
     vtx_k_locus_prep<<<blocks_for(uint64_t(nl) * 32, 256), 256, 0, ctx->stream>>>(
         nl, b.hap, b.ref_off, b.ref_len, b.alt_off, b.alt_len, P<uint32_t>(ctx->pair_start), P<uint32_t>(ctx->pair_read), b.read_len,
-        force_slow, allow_split, allow_multi, allow_fold, P<uint32_t>(ctx->tcount));
+        force_slow, allow_split, allow_multi, allow_fold, b.max_read_len, b.max_hap_len, P<unsigned long long>(ctx->d_metrics) + 4,
+        P<uint32_t>(ctx->tcount));
     ++*launches;
     vtx_k_scan_rows<<<kNumClasses, kScanThreads, 0, ctx->stream>>>(P<uint32_t>(ctx->tcount), P<uint32_t>(ctx->tstart), nl, nl + 1);
     ++*launches;
@@ -258,10 +282,12 @@ int run_sw(vtx_ctx* ctx, const DevBatch& b, uint32_t n_pairs_ub, const uint32_t*
     a.max_hap = b.max_hap_len;
 
     uint64_t before = *launches;
+    // b.class_mask: for host batches the classes the windows of this shard can select (scan_host_batch); all for device batches
     for (int c = 0; c < kNumFastClasses; ++c) {
         // a class whose narrowest window is wider than every window of this batch has no tiles: skip the empty launch
         // (max_hap_len is exact for host batches and a promised upper bound for device batches)
         if (c > 0 && b.max_hap_len <= uint32_t(class_max_n(c - 1))) continue;
+        if (!(b.class_mask >> c & 1u)) continue;
         a.tile_start = P<uint32_t>(ctx->tstart) + size_t(c) * (nl + 1);
         a.tile_counter = P<uint32_t>(ctx->tile_counters) + c;
         int rc = VTX_OK;
@@ -276,19 +302,20 @@ int run_sw(vtx_ctx* ctx, const DevBatch& b, uint32_t n_pairs_ub, const uint32_t*
     if (allow_split) {
         for (int c = 0; c < kNumSplitClasses; ++c) {
             if (c > 0 && b.max_hap_len <= uint32_t(split_max_n(c - 1))) continue;
+            if (!(b.class_mask >> (kSplitClass0 + c) & 1u)) continue;
             a.tile_start = P<uint32_t>(ctx->tstart) + size_t(kSplitClass0 + c) * (nl + 1);
             a.tile_counter = P<uint32_t>(ctx->tile_counters) + kSplitClass0 + c;
             int rc = c == 0 ? launch_sw_split<0>(ctx, a, launches) : launch_sw_split<1>(ctx, a, launches);
             if (rc) return rc;
         }
     }
-    if (allow_fold) {
+    if (allow_fold && (b.class_mask >> kFoldClass & 1u)) {
         a.tile_start = P<uint32_t>(ctx->tstart) + size_t(kFoldClass) * (nl + 1);
         a.tile_counter = P<uint32_t>(ctx->tile_counters) + kFoldClass;
         int rc = launch_sw_fold(ctx, a, launches);
         if (rc) return rc;
     }
-    {   // generic class (rare)
+    if (b.class_mask >> kSlowClass & 1u) {   // generic class (rare)
         const unsigned blocks = unsigned(ctx->n_sm) * 4, threads = 128;
         const size_t warps = size_t(blocks) * threads / 32;
         ENS(ctx->scratch, warps * (size_t(b.max_hap_len) + 1) * 32 * 4);
@@ -319,6 +346,7 @@ int grow_results(vtx_ctx* ctx, size_t need)
         if (bufs[i]->p) {
             CK(cudaStreamSynchronize(ctx->stream));
             if (ctx->fetch_stream) CK(cudaStreamSynchronize(ctx->fetch_stream));
+            if (ctx->comm_stream) CK(cudaStreamSynchronize(ctx->comm_stream));
             CK(cudaFree(bufs[i]->p));
         }
         bufs[i]->p = np; bufs[i]->cap = ncap * esz[i];
@@ -337,7 +365,7 @@ int process_batch(vtx_ctx* ctx, const DevBatch& b, TimeRec* tr)
 
     if (ctx->finished) {      // fresh result set
         CK(cudaMemsetAsync(ctx->d_res_n.p, 0, 8, st));
-        CK(cudaMemsetAsync(ctx->d_metrics.p, 0, 24, st));
+        CK(cudaMemsetAsync(ctx->d_metrics.p, 0, 40, st));
         ctx->res_ub = 0;
         ctx->finished = false;
     }
@@ -368,7 +396,12 @@ int process_batch(vtx_ctx* ctx, const DevBatch& b, TimeRec* tr)
 
     // ---- K1: CB lookup, filter, compaction --------------------------------------------------------
     BarcodeTable tab{ P<int32_t>(ctx->bc_slot), ctx->bc_cap - 1, P<uint8_t>(ctx->bc_bytes), P<uint32_t>(ctx->bc_off) };
-    vtx_k_cb_lookup<<<blocks_for(nr, 256), 256, 0, st>>>(tab, nr, b.cb_bytes, b.read_cb_off, b.read_cb_len, P<int32_t>(ctx->read_col));
+    if (b.read_cb_key) {
+        BarcodeKeyTable kt{ P<uint64_t>(ctx->bck_key), P<uint32_t>(ctx->bck_idx), ctx->bck_cap - 1 };
+        vtx_k_cb_lookup_key<<<blocks_for(nr, 256), 256, 0, st>>>(tab, kt, nr, b.read_cb_key, b.cb_bytes, b.cb_off_ex, P<int32_t>(ctx->read_col));
+    } else {
+        vtx_k_cb_lookup<<<blocks_for(nr, 256), 256, 0, st>>>(tab, nr, b.cb_bytes, b.read_cb_off, b.read_cb_len, P<int32_t>(ctx->read_col));
+    }
     vtx_k_cand_filter<<<blocks_for(nc, 256), 256, 0, st>>>(nc, b.cand_read, P<int32_t>(ctx->read_col), b.read_umi, use_umi,
                                                            P<uint32_t>(ctx->keep), P<unsigned long long>(ctx->d_metrics));
     launches += 2;
@@ -422,6 +455,10 @@ int process_batch(vtx_ctx* ctx, const DevBatch& b, TimeRec* tr)
     ++launches;
     rc = scan_u32(ctx, P<uint32_t>(ctx->keep2), nc, P<uint32_t>(ctx->oidx), &launches);
     if (rc) return rc;
+    if (ctx->gather_guard) {       // a gather started after the previous finish may still be reading the local result arrays
+        CK(cudaStreamWaitEvent(st, ctx->ev_gather, 0));
+        ctx->gather_guard = false;
+    }
     ResultArrays out{ P<uint32_t>(ctx->r_row), P<uint32_t>(ctx->r_col), P<uint32_t>(ctx->r_ref), P<uint32_t>(ctx->r_alt),
                       P<uint32_t>(ctx->r_unk), P<double>(ctx->r_val), P<double>(ctx->r_val2) };
     vtx_k_emit<<<blocks_for(nc, 256), 256, 0, st>>>(uint32_t(nc), ctx->cfg.mode, P<uint32_t>(ctx->keep2), P<uint32_t>(ctx->oidx),
@@ -440,61 +477,159 @@ int process_batch(vtx_ctx* ctx, const DevBatch& b, TimeRec* tr)
     return VTX_OK;
 }
 
-int validate_batch(vtx_ctx* ctx, const vtx_batch* b)
+// One view of a host batch for validation, whichever layout it arrived in.
+struct HostView {
+    uint32_t n_loci = 0, n_reads = 0; uint64_t n_cand = 0;
+    const uint32_t *locus_row = nullptr, *ref_off = nullptr, *ref_len = nullptr, *alt_off = nullptr, *alt_len = nullptr;
+    const uint64_t* cand_start = nullptr; const uint8_t* hap = nullptr; uint64_t hap_len = 0;
+    uint64_t nib_len = 0, cb_bytes_len = 0;
+    const uint64_t* read_off = nullptr; const uint32_t* read_len = nullptr; const uint32_t* cb_off = nullptr; const uint16_t* cb_len = nullptr;   // vtx_batch
+    const uint32_t* read_off4 = nullptr; const uint16_t* read_len16 = nullptr; const uint64_t* cb_key = nullptr;                                // vtx_batch2
+    uint32_t n_exotic = 0; const uint32_t* cb_off_ex = nullptr;
+    const uint64_t* umi = nullptr; const uint32_t* cand_read = nullptr;
+    bool v2 = false;
+};
+
+HostView view_of(const vtx_batch* b)
 {
-    if (!b) return set_err(ctx, VTX_E_INVALID, "batch is NULL");
-    if (b->n_cand >= 0xFFFFFFF0ull) return set_err(ctx, VTX_E_INVALID, "n_cand %llu exceeds 2^32 per shard; split the shard", (unsigned long long)b->n_cand);
-    if (b->n_loci && (!b->locus_row || !b->ref_off || !b->ref_len || !b->alt_off || !b->alt_len || !b->cand_start))
+    HostView v;
+    v.n_loci = b->n_loci; v.n_reads = b->n_reads; v.n_cand = b->n_cand;
+    v.locus_row = b->locus_row; v.ref_off = b->ref_off; v.ref_len = b->ref_len; v.alt_off = b->alt_off; v.alt_len = b->alt_len;
+    v.cand_start = b->cand_start; v.hap = b->hap_bytes; v.hap_len = b->hap_bytes_len; v.nib_len = b->read_nib_len; v.cb_bytes_len = b->cb_bytes_len;
+    v.read_off = b->read_off; v.read_len = b->read_len; v.cb_off = b->read_cb_off; v.cb_len = b->read_cb_len;
+    v.umi = b->read_umi_key; v.cand_read = b->cand_read;
+    return v;
+}
+HostView view_of(const vtx_batch2* b)
+{
+    HostView v;
+    v.v2 = true;
+    v.n_loci = b->n_loci; v.n_reads = b->n_reads; v.n_cand = b->n_cand;
+    v.locus_row = b->locus_row; v.ref_off = b->ref_off; v.ref_len = b->ref_len; v.alt_off = b->alt_off; v.alt_len = b->alt_len;
+    v.cand_start = b->cand_start; v.hap = b->hap_bytes; v.hap_len = b->hap_bytes_len; v.nib_len = b->read_nib_len;
+    v.read_off4 = b->read_off4; v.read_len16 = b->read_len; v.cb_key = b->read_cb_key; v.n_exotic = b->n_exotic_cb; v.cb_off_ex = b->cb_off;
+    v.cb_bytes_len = (b->n_exotic_cb && b->cb_off) ? b->cb_off[b->n_exotic_cb] : 0;
+    v.umi = b->read_umi_key; v.cand_read = b->cand_read;
+    return v;
+}
+
+int validate_batch(vtx_ctx* ctx, const HostView& b, bool device)
+{
+    if (b.n_cand >= 0xFFFFFFF0ull) return set_err(ctx, VTX_E_INVALID, "n_cand %llu exceeds 2^32 per shard; split the shard", (unsigned long long)b.n_cand);
+    if (b.n_loci && (!b.locus_row || !b.ref_off || !b.ref_len || !b.alt_off || !b.alt_len || !b.cand_start))
         return set_err(ctx, VTX_E_INVALID, "locus arrays missing");
-    if (b->n_reads && (!b->read_off || !b->read_len || !b->read_cb_off || !b->read_cb_len || !b->read_umi_key))
-        return set_err(ctx, VTX_E_INVALID, "read arrays missing");
-    if (b->n_cand && !b->cand_read) return set_err(ctx, VTX_E_INVALID, "cand_read missing");
-    if (b->hap_bytes_len >= 0xFFFFFFFFull) return set_err(ctx, VTX_E_INVALID, "haplotype pool exceeds 4 GiB; split the shard");
+    if (b.n_reads) {
+        const bool reads_ok = b.v2 ? (b.read_len16 && b.cb_key) : (b.read_off && b.read_len && b.cb_off && b.cb_len);
+        if (!reads_ok || (!b.umi && ctx->cfg.use_umi)) return set_err(ctx, VTX_E_INVALID, "read arrays missing");
+    }
+    if (b.v2 && b.n_exotic && !b.cb_off_ex) return set_err(ctx, VTX_E_INVALID, "cb_off missing for the exotic cell tags");
+    if (b.n_cand && !b.cand_read && !(b.v2 && b.n_cand == b.n_reads)) return set_err(ctx, VTX_E_INVALID, "cand_read missing (NULL means identity and needs n_cand == n_reads in a vtx_batch2)");
+    if (b.hap_len >= 0xFFFFFFFFull) return set_err(ctx, VTX_E_INVALID, "haplotype pool exceeds 4 GiB; split the shard");
+    if (b.v2 && b.nib_len >= (uint64_t(1) << 34)) return set_err(ctx, VTX_E_INVALID, "read pool exceeds 16 GiB; split the shard");
+    (void)device;
     return VTX_OK;
+}
+
+// Which Smith-Waterman tile classes can get tiles, from the windows alone: the same decision tree as vtx_k_locus_prep,
+// with the one input the host does not have (the longest SCORED read of a fold-shaped locus) resolved conservatively.
+// Index of the per-locus shape: bit 0 exotic, bit 1 common prefix, bit 2 fold-shaped windows, bits 3.. single-phase
+// class (kNumFastClasses = none), then the two-phase class (kNumSplitClasses = none).
+constexpr int kShapeFast = 3, kShapeSplit = kShapeFast + 3, kNumShapes = 1 << (kShapeSplit + 2);
+uint32_t shape_of(const uint8_t* rh, uint32_t nr, const uint8_t* ah, uint32_t na)
+{
+    auto is_exotic = [](uint8_t b) {
+        return b == '=' || b == 'M' || b == 'R' || b == 'S' || b == 'V' || b == 'W' || b == 'Y' || b == 'H' || b == 'K' || b == 'D' || b == 'B' || b == 'N';
+    };
+    bool exotic = false;
+    for (uint32_t j = 0; j < nr && !exotic; ++j) exotic = is_exotic(rh[j]);
+    for (uint32_t j = 0; j < na && !exotic; ++j) exotic = is_exotic(ah[j]);
+    const bool same = nr >= uint32_t(kSplitP) && na >= uint32_t(kSplitP) && memcmp(rh, ah, kSplitP) == 0;
+    const bool fold = same && std::min(nr, na) > uint32_t(2 * kFoldP) && std::max(nr, na) <= uint32_t(2 * kFoldP + kFoldMaxMid) &&
+                      memcmp(rh + nr - kFoldP, ah + na - kFoldP, kFoldP) == 0;
+    const uint32_t nmax = std::max(nr, na);
+    uint32_t fast = kNumFastClasses, split = kNumSplitClasses;
+    for (int c = kNumFastClasses - 1; c >= 0; --c) if (nmax <= uint32_t(class_max_n(c))) fast = uint32_t(c);
+    for (int c = kNumSplitClasses - 1; c >= 0; --c) if (nmax <= uint32_t(split_max_n(c))) split = uint32_t(c);
+    return uint32_t(exotic) | (uint32_t(same) << 1) | (uint32_t(fold) << 2) | (fast << kShapeFast) | (split << kShapeSplit);
+}
+uint32_t class_mask_of(const bool* seen, bool allow_split, bool allow_multi, bool allow_fold, uint32_t max_read)
+{
+    uint32_t mask = 0;
+    for (int i = 0; i < kNumShapes; ++i) {
+        if (!seen[i]) continue;
+        const bool exotic = i & 1, same = i & 2, fold = i & 4;
+        const uint32_t fast = (uint32_t(i) >> kShapeFast) & 7u, split = (uint32_t(i) >> kShapeSplit) & 3u;
+        int cls = kSlowClass;
+        if (!exotic) {
+            if (fast < uint32_t(kNumFastClasses)) cls = int(fast);
+            else if (allow_multi) cls = kMultiClass;
+            if (same && allow_split && split < uint32_t(kNumSplitClasses)) cls = kSplitClass0 + int(split);
+            if (fold && allow_fold) {
+                mask |= 1u << kFoldClass;
+                if (max_read <= uint32_t(kFoldMaxRead)) continue;        // every read fits: the locus cannot fall back
+            }
+        }
+        mask |= 1u << cls;
+    }
+    return mask;
 }
 
 // host-side checks that need to touch the (host) arrays; also returns max lengths.  Runs on a few host
 // threads while the shard's H2D copies are already in flight (the kernels are only enqueued afterwards).
-int scan_host_batch(vtx_ctx* ctx, const vtx_batch* b, uint32_t* max_read, uint32_t* max_hap, bool check_cands,
-                    uint64_t* max_depth = nullptr)
+int scan_host_batch(vtx_ctx* ctx, const HostView& b, uint32_t* max_read, uint32_t* max_hap, bool check_cands,
+                    uint64_t* max_depth = nullptr, bool* shapes_seen = nullptr)
 {
-    uint32_t mh = 0;
-    uint64_t md = 0;
-    for (uint32_t l = 0; l < b->n_loci; ++l) {
-        if ((b->ref_off[l] & 15) || (b->alt_off[l] & 15)) return set_err(ctx, VTX_E_INVALID, "locus %u: haplotype offsets must be multiples of 16", l);
-        if (uint64_t(b->ref_off[l]) + b->ref_len[l] > b->hap_bytes_len || uint64_t(b->alt_off[l]) + b->alt_len[l] > b->hap_bytes_len)
-            return set_err(ctx, VTX_E_INVALID, "locus %u: haplotype window outside hap_bytes", l);
-        if (l && b->locus_row[l] <= b->locus_row[l - 1]) return set_err(ctx, VTX_E_INVALID, "locus_row must be strictly ascending (locus %u)", l);
-        if (check_cands && b->cand_start[l] > b->cand_start[l + 1]) return set_err(ctx, VTX_E_INVALID, "cand_start must be ascending (locus %u)", l);
-        if (check_cands) md = std::max<uint64_t>(md, b->cand_start[l + 1] - b->cand_start[l]);
-        mh = std::max(mh, std::max(b->ref_len[l], b->alt_len[l]));
-    }
-    if (check_cands && b->n_loci && (b->cand_start[0] != 0 || b->cand_start[b->n_loci] != b->n_cand))
+    if (check_cands && b.n_loci && (b.cand_start[0] != 0 || b.cand_start[b.n_loci] != b.n_cand))
         return set_err(ctx, VTX_E_INVALID, "cand_start must span [0, n_cand]");
-    if (check_cands && !b->n_loci && b->n_cand) return set_err(ctx, VTX_E_INVALID, "candidates without loci");
-
-    const uint64_t work = uint64_t(b->n_reads) + (check_cands ? b->n_cand : 0);
+    if (check_cands && !b.n_loci && b.n_cand) return set_err(ctx, VTX_E_INVALID, "candidates without loci");
+    if (b.v2 && b.n_exotic) {
+        for (uint32_t i = 0; i < b.n_exotic; ++i)
+            if (b.cb_off_ex[i] > b.cb_off_ex[i + 1]) return set_err(ctx, VTX_E_INVALID, "cb_off must be ascending (exotic tag %u)", i);
+    }
+    const bool scan_cands = check_cands && b.cand_read != nullptr;
+    const uint64_t work = uint64_t(b.n_reads) + (scan_cands ? b.n_cand : 0) + uint64_t(b.n_loci) * 64;
     unsigned nt = std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency()));
     if (work < (1u << 16)) nt = 1;
-    struct Part { uint32_t mr = 0; int bad = 0; uint64_t where = 0; };
+    struct Part { uint32_t mr = 0, mh = 0; uint64_t md = 0, units = 0; int bad = 0; uint64_t where = 0; bool seen[kNumShapes] = {}; };
     std::vector<Part> parts(nt);
     auto worker = [&](unsigned t) {
         Part& pt = parts[t];
-        const uint32_t r0 = uint32_t(uint64_t(b->n_reads) * t / nt), r1 = uint32_t(uint64_t(b->n_reads) * (t + 1) / nt);
-        for (uint32_t r = r0; r < r1; ++r) {
-            int bad = 0;
-            if (b->read_off[r] & 15) bad = 1;
-            else if (b->read_off[r] + (uint64_t(b->read_len[r]) + 1) / 2 > b->read_nib_len) bad = 2;
-            else if (b->read_cb_off[r] != VTX_NO_CB && uint64_t(b->read_cb_off[r]) + b->read_cb_len[r] > b->cb_bytes_len) bad = 3;
-            else if (b->read_umi_key[r] != VTX_NO_UMI && b->read_umi_key[r] > VTX_UMI_KEY_MAX) bad = 4;
-            if (bad && !pt.bad) { pt.bad = bad; pt.where = r; }
-            pt.mr = std::max(pt.mr, b->read_len[r]);
+        auto flag = [&](int code, uint64_t where) { if (!pt.bad) { pt.bad = code; pt.where = where; } };
+        const uint32_t l0 = uint32_t(uint64_t(b.n_loci) * t / nt), l1 = uint32_t(uint64_t(b.n_loci) * (t + 1) / nt);
+        for (uint32_t l = l0; l < l1; ++l) {
+            if ((b.ref_off[l] & 15) || (b.alt_off[l] & 15)) { flag(10, l); continue; }
+            if (uint64_t(b.ref_off[l]) + b.ref_len[l] > b.hap_len || uint64_t(b.alt_off[l]) + b.alt_len[l] > b.hap_len) { flag(11, l); continue; }
+            if (l && b.locus_row[l] <= b.locus_row[l - 1]) flag(12, l);
+            if (check_cands && b.cand_start[l] > b.cand_start[l + 1]) flag(13, l);
+            if (check_cands) pt.md = std::max<uint64_t>(pt.md, b.cand_start[l + 1] - b.cand_start[l]);
+            pt.mh = std::max(pt.mh, std::max(b.ref_len[l], b.alt_len[l]));
+            if (shapes_seen) pt.seen[shape_of(b.hap + b.ref_off[l], b.ref_len[l], b.hap + b.alt_off[l], b.alt_len[l])] = true;
         }
-        if (check_cands) {
-            const uint64_t c0 = b->n_cand * t / nt, c1 = b->n_cand * (t + 1) / nt;
+        const uint32_t r0 = uint32_t(uint64_t(b.n_reads) * t / nt), r1 = uint32_t(uint64_t(b.n_reads) * (t + 1) / nt);
+        for (uint32_t r = r0; r < r1; ++r) {
+            uint32_t len;
+            if (b.v2) {
+                len = b.read_len16[r];
+                const uint64_t nb = (uint64_t(len) + 1) / 2;
+                if (b.read_off4) { if (uint64_t(b.read_off4[r]) * 4 + nb > b.nib_len) flag(2, r); }
+                else pt.units += (nb + 3) / 4;
+                const uint64_t k = b.cb_key[r];
+                if (k != VTX_NO_CB_KEY && (k & VTX_CB_EXOTIC) && (k & ~VTX_CB_EXOTIC) >= b.n_exotic) flag(3, r);
+                else if (k != VTX_NO_CB_KEY && !(k & VTX_CB_EXOTIC) && (k >> 60)) flag(6, r);
+            } else {
+                len = b.read_len[r];
+                if (b.read_off[r] & 15) flag(1, r);
+                else if (b.read_off[r] + (uint64_t(len) + 1) / 2 > b.nib_len) flag(2, r);
+                else if (b.cb_off[r] != VTX_NO_CB && uint64_t(b.cb_off[r]) + b.cb_len[r] > b.cb_bytes_len) flag(3, r);
+            }
+            if (b.umi && b.umi[r] != VTX_NO_UMI && b.umi[r] > VTX_UMI_KEY_MAX) flag(4, r);
+            pt.mr = std::max(pt.mr, len);
+        }
+        if (scan_cands) {
+            const uint64_t c0 = b.n_cand * t / nt, c1 = b.n_cand * (t + 1) / nt;
             uint32_t worst = 0;
-            for (uint64_t c = c0; c < c1; ++c) worst = std::max(worst, b->cand_read[c]);
-            if (c1 > c0 && worst >= b->n_reads && !pt.bad) { pt.bad = 5; pt.where = c0; }
+            for (uint64_t c = c0; c < c1; ++c) worst = std::max(worst, b.cand_read[c]);
+            if (c1 > c0 && worst >= b.n_reads) flag(5, c0);
         }
     };
     if (nt == 1) worker(0);
@@ -504,22 +639,37 @@ int scan_host_batch(vtx_ctx* ctx, const vtx_batch* b, uint32_t* max_read, uint32
         worker(0);
         for (auto& x : th) x.join();
     }
-    uint32_t mr = 0;
+    uint32_t mr = 0, mh = 0;
+    uint64_t md = 0, units = 0;
     for (const Part& pt : parts) {
-        mr = std::max(mr, pt.mr);
+        mr = std::max(mr, pt.mr); mh = std::max(mh, pt.mh); md = std::max(md, pt.md); units += pt.units;
+        if (shapes_seen) for (int i = 0; i < kNumShapes; ++i) shapes_seen[i] |= pt.seen[i];
+        const unsigned long long w = (unsigned long long)pt.where;
         switch (pt.bad) {
-        case 1: return set_err(ctx, VTX_E_INVALID, "read %llu: read_off must be a multiple of 16", (unsigned long long)pt.where);
-        case 2: return set_err(ctx, VTX_E_INVALID, "read %llu outside read_nib", (unsigned long long)pt.where);
-        case 3: return set_err(ctx, VTX_E_INVALID, "read %llu: CB outside cb_bytes", (unsigned long long)pt.where);
-        case 4: return set_err(ctx, VTX_E_INVALID, "read %llu: UMI key exceeds VTX_UMI_KEY_MAX", (unsigned long long)pt.where);
-        case 5: return set_err(ctx, VTX_E_INVALID, "cand_read out of range near candidate %llu", (unsigned long long)pt.where);
+        case 1: return set_err(ctx, VTX_E_INVALID, "read %llu: read_off must be a multiple of 16", w);
+        case 2: return set_err(ctx, VTX_E_INVALID, "read %llu outside read_nib", w);
+        case 3: return set_err(ctx, VTX_E_INVALID, "read %llu: CB outside cb_bytes", w);
+        case 4: return set_err(ctx, VTX_E_INVALID, "read %llu: UMI key exceeds VTX_UMI_KEY_MAX", w);
+        case 5: return set_err(ctx, VTX_E_INVALID, "cand_read out of range near candidate %llu", w);
+        case 6: return set_err(ctx, VTX_E_INVALID, "read %llu: read_cb_key is not a vtx_pack_cb code", w);
+        case 10: return set_err(ctx, VTX_E_INVALID, "locus %llu: haplotype offsets must be multiples of 16", w);
+        case 11: return set_err(ctx, VTX_E_INVALID, "locus %llu: haplotype window outside hap_bytes", w);
+        case 12: return set_err(ctx, VTX_E_INVALID, "locus_row must be strictly ascending (locus %llu)", w);
+        case 13: return set_err(ctx, VTX_E_INVALID, "cand_start must be ascending (locus %llu)", w);
         default: break;
         }
     }
+    if (b.v2 && !b.read_off4 && units * 4 > b.nib_len) return set_err(ctx, VTX_E_INVALID, "dense read pool is shorter than the reads it should hold");
     if (mr > uint32_t(kMaxRead)) return set_err(ctx, VTX_E_UNSUPPORTED, "reads longer than %d bases (biased int16 DP) are not supported (%u)", kMaxRead, mr);
     *max_read = mr; *max_hap = mh;
     if (max_depth) *max_depth = md;
     return VTX_OK;
+}
+
+uint32_t host_class_mask(const vtx_ctx* ctx, const bool* shapes, uint32_t max_read, uint32_t max_hap)
+{
+    const SwAllow a = sw_allow(ctx, max_read, max_hap);
+    return class_mask_of(shapes, a.split, a.multi, a.fold, max_read);
 }
 
 int upload(vtx_ctx* ctx, DBuf& d, const void* h, size_t bytes)
@@ -577,6 +727,12 @@ int vtx_create(const vtx_config* cfg, vtx_ctx** out)
         return set_err(nullptr, VTX_E_UNSUPPORTED, "scoring constants are compiled in: match %d mismatch %d gap_open %d gap_extend %d (main.rs:35-38)",
                        kMatch, kMismatch, kGapOpen, kGapExtend);
     if (cfg->mode < 0 || cfg->mode > 2) return set_err(nullptr, VTX_E_INVALID, "unknown mode %d", cfg->mode);
+    if (cfg->band_mode != VTX_BAND_FULL && cfg->band_mode != VTX_BAND_MODEL) return set_err(nullptr, VTX_E_INVALID, "unknown band_mode %d", cfg->band_mode);
+    if ((cfg->band_k != 0 && cfg->band_k != kBandK) || (cfg->band_w != 0 && cfg->band_w != kBandW))
+        return set_err(nullptr, VTX_E_UNSUPPORTED, "band constants are compiled in: K %d W %d (main.rs:33-34)", kBandK, kBandW);
+    if (cfg->band_mode == VTX_BAND_MODEL)
+        return set_err(nullptr, VTX_E_UNSUPPORTED, "band_mode VTX_BAND_MODEL is not available on the GPU: the k-mer-chain band of bio 0.30.0 is only "
+                                                   "modelled in the CPU oracle (vtxo_sw_band_model); the engine scores the full matrix");
     int n_dev = 0;
     cudaError_t e = cudaGetDeviceCount(&n_dev);
     if (e != cudaSuccess || n_dev == 0)
@@ -623,16 +779,19 @@ void vtx_destroy(vtx_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm_stream) cudaStreamSynchronize(ctx->comm_stream);
     vtx_comm_destroy_internal(ctx);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     for (auto& sl : ctx->slot) {
         DBuf* sb[] = { &sl.locus_row, &sl.hap, &sl.ref_off, &sl.ref_len, &sl.alt_off, &sl.alt_len, &sl.cand_start, &sl.read_nib,
-                       &sl.read_off, &sl.read_len, &sl.cb_bytes, &sl.read_cb_off, &sl.read_cb_len, &sl.read_umi, &sl.cand_read };
+                       &sl.read_off, &sl.read_len, &sl.cb_bytes, &sl.read_cb_off, &sl.read_cb_len, &sl.read_umi, &sl.cand_read,
+                       &sl.read_off4, &sl.read_len16, &sl.read_cb_key, &sl.cb_off_ex };
         for (DBuf* b : sb) if (b->p) cudaFree(b->p);
         if (sl.copy_done) cudaEventDestroy(sl.copy_done);
         if (sl.free_ev) cudaEventDestroy(sl.free_ev);
     }
-    DBuf* all[] = { &ctx->bc_slot, &ctx->bc_bytes, &ctx->bc_off, &ctx->read_col,
+    DBuf* all[] = { &ctx->bc_slot, &ctx->bc_bytes, &ctx->bc_off, &ctx->bck_key, &ctx->bck_idx, &ctx->x_read_off, &ctx->x_read_len,
+                    &ctx->x_units, &ctx->x_off4, &ctx->read_col,
                     &ctx->keep, &ctx->pidx, &ctx->scan_sums, &ctx->pair_read, &ctx->pair_col, &ctx->pair_umi, &ctx->pair_locus,
                     &ctx->pair_start, &ctx->tcount, &ctx->tstart, &ctx->pair_first, &ctx->pair_cslot, &ctx->pair_uslot, &ctx->cslot_col,
                     &ctx->cslot_locus, &ctx->uslot_cslot, &ctx->ccnt, &ctx->ucnt, &ctx->keep2, &ctx->oidx, &ctx->tile_counters,
@@ -644,6 +803,9 @@ void vtx_destroy(vtx_ctx* ctx)
     for (void* h : ctx->g_host) if (h) cudaFreeHost(h);
     if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
     for (auto& tr : ctx->trecs) for (auto& ev : tr.ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->comm_stream) { cudaStreamSynchronize(ctx->comm_stream); cudaStreamDestroy(ctx->comm_stream); }
+    for (cudaEvent_t e : { ctx->ev_counts, ctx->ev_gather, ctx->ev_results }) if (e) cudaEventDestroy(e);
+    if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->fetch_stream) cudaStreamDestroy(ctx->fetch_stream);
     if (ctx->h_cum) cudaFreeHost(ctx->h_cum);
@@ -684,11 +846,23 @@ int vtx_set_barcodes(vtx_ctx* ctx, const uint8_t* bytes, const uint32_t* off, ui
             h = (h + 1) & (cap - 1);
         }
     }
+    // second table for the slim layout: the barcodes that have a vtx_pack_cb code, keyed by the code
+    std::vector<uint64_t> kkey(cap, kNoCbKey);
+    std::vector<uint32_t> kidx(cap, 0);
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint64_t k = pack_cb(bytes + off[i], off[i + 1] - off[i]);
+        if (k == kNoCbKey) continue;
+        uint32_t h = uint32_t(mix64(k)) & (cap - 1);
+        while (kkey[h] != kNoCbKey) h = (h + 1) & (cap - 1);       // codes are injective and the strings distinct: no equal key
+        kkey[h] = k; kidx[h] = i;
+    }
     UP(ctx->bc_slot, slot.data(), size_t(cap) * 4);
     UP(ctx->bc_bytes, bytes, off[n]);
     UP(ctx->bc_off, off, size_t(n + 1) * 4);
-    CK(cudaStreamSynchronize(ctx->copy_stream));   // `slot` is a local; the table must be resident before any submit
-    ctx->bc_cap = cap; ctx->n_barcodes = n; ctx->have_barcodes = true;
+    UP(ctx->bck_key, kkey.data(), size_t(cap) * 8);
+    UP(ctx->bck_idx, kidx.data(), size_t(cap) * 4);
+    CK(cudaStreamSynchronize(ctx->copy_stream));   // the tables are locals; they must be resident before any submit
+    ctx->bc_cap = cap; ctx->bck_cap = cap; ctx->n_barcodes = n; ctx->have_barcodes = true;
     return VTX_OK;
 }
 
@@ -696,7 +870,9 @@ int vtx_submit(vtx_ctx* ctx, const vtx_batch* hb)
 {
     if (!ctx) return VTX_E_INVALID;
     if (!ctx->have_barcodes) return set_err(ctx, VTX_E_STATE, "vtx_set_barcodes must be called before vtx_submit");
-    int rc = validate_batch(ctx, hb);
+    if (!hb) return set_err(ctx, VTX_E_INVALID, "batch is NULL");
+    const HostView hv = view_of(hb);
+    int rc = validate_batch(ctx, hv, false);
     if (rc) return rc;
     CK(cudaSetDevice(ctx->device));
     TimeRec* tr = new_trec(ctx);
@@ -713,7 +889,7 @@ int vtx_submit(vtx_ctx* ctx, const vtx_batch* hb)
     UP(sl->cand_start, hb->cand_start, size_t(nl + 1) * 8);
     UP(sl->cb_bytes, hb->cb_bytes, hb->cb_bytes_len);
     UP(sl->read_cb_off, hb->read_cb_off, size_t(nr) * 4); UP(sl->read_cb_len, hb->read_cb_len, size_t(nr) * 2);
-    UP(sl->read_umi, hb->read_umi_key, size_t(nr) * 8);
+    if (hb->read_umi_key) UP(sl->read_umi, hb->read_umi_key, size_t(nr) * 8);
     UP(sl->cand_read, hb->cand_read, size_t(hb->n_cand) * 4);
     CK(cudaEventRecord(tr->ev[EV_H2D], ctx->copy_stream));
     CK(cudaEventRecord(sl->copy_done, ctx->copy_stream));
@@ -721,10 +897,12 @@ int vtx_submit(vtx_ctx* ctx, const vtx_batch* hb)
     d.n_cand = hb->n_cand;
     d.cand_start = P<uint64_t>(sl->cand_start); d.cb_bytes = P<uint8_t>(sl->cb_bytes);
     d.read_cb_off = P<uint32_t>(sl->read_cb_off); d.read_cb_len = P<uint16_t>(sl->read_cb_len);
-    d.read_umi = P<uint64_t>(sl->read_umi); d.cand_read = P<uint32_t>(sl->cand_read);
+    d.read_umi = hb->read_umi_key ? P<uint64_t>(sl->read_umi) : nullptr; d.cand_read = P<uint32_t>(sl->cand_read);
     // 2. ... validate the host arrays meanwhile; nothing has been launched on them yet
-    rc = scan_host_batch(ctx, hb, &d.max_read_len, &d.max_hap_len, true, &d.max_depth);
+    bool shapes[kNumShapes] = {};
+    rc = scan_host_batch(ctx, hv, &d.max_read_len, &d.max_hap_len, true, &d.max_depth, shapes);
     if (rc) { cudaStreamSynchronize(ctx->copy_stream); --ctx->trec_used; return rc; }
+    d.class_mask = host_class_mask(ctx, shapes, d.max_read_len, d.max_hap_len);
     // 3. kernels wait for the copy, and release the slot when done
     CK(cudaStreamWaitEvent(ctx->stream, sl->copy_done, 0));
     CK(cudaEventRecord(tr->ev[EV_C0], ctx->stream));
@@ -740,7 +918,8 @@ int vtx_submit_device_ex(vtx_ctx* ctx, const vtx_batch* db, uint32_t max_read_le
 {
     if (!ctx) return VTX_E_INVALID;
     if (!ctx->have_barcodes) return set_err(ctx, VTX_E_STATE, "vtx_set_barcodes must be called before vtx_submit_device");
-    int rc = validate_batch(ctx, db);
+    if (!db) return set_err(ctx, VTX_E_INVALID, "batch is NULL");
+    int rc = validate_batch(ctx, view_of(db), true);
     if (rc) return rc;
     if (max_read_len > uint32_t(kMaxRead)) return set_err(ctx, VTX_E_UNSUPPORTED, "reads longer than %d bases are not supported", kMaxRead);
     CK(cudaSetDevice(ctx->device));
@@ -764,6 +943,113 @@ int vtx_submit_device(vtx_ctx* ctx, const vtx_batch* db)
     return vtx_submit_device_ex(ctx, db, kFastMaxRead, class_max_n(kNumFastClasses - 1));
 }
 
+// ---- slim layout -------------------------------------------------------------------------------------------------
+namespace {
+// slim read arrays (device) -> the engine's internal read_off (u64 bytes) / read_len (u32)
+int expand_reads(vtx_ctx* ctx, uint32_t nr, const uint16_t* d_len16, const uint32_t* d_off4, DevBatch& d, uint64_t* launches_unused = nullptr)
+{
+    (void)launches_unused;
+    ENS(ctx->x_read_off, size_t(nr ? nr : 1) * 8); ENS(ctx->x_read_len, size_t(nr ? nr : 1) * 4);
+    if (nr) {
+        if (!d_off4) {          // dense pool: offsets are the running sum of the 4-byte units of the reads before
+            ENS(ctx->x_units, size_t(nr) * 4); ENS(ctx->x_off4, size_t(nr + 1) * 4);
+            vtx_k_read_units<<<blocks_for(nr, 256), 256, 0, ctx->stream>>>(nr, d_len16, P<uint32_t>(ctx->x_units));
+            int rc = scan_u32(ctx, P<uint32_t>(ctx->x_units), nr, P<uint32_t>(ctx->x_off4), nullptr);
+            if (rc) return rc;
+            d_off4 = P<uint32_t>(ctx->x_off4);
+        }
+        vtx_k_expand_reads<<<blocks_for(nr, 256), 256, 0, ctx->stream>>>(nr, d_len16, d_off4, P<uint64_t>(ctx->x_read_off), P<uint32_t>(ctx->x_read_len));
+        CK(cudaGetLastError());
+    }
+    d.read_off = P<uint64_t>(ctx->x_read_off); d.read_len = P<uint32_t>(ctx->x_read_len);
+    return VTX_OK;
+}
+}  // namespace
+
+int vtx_submit2(vtx_ctx* ctx, const vtx_batch2* hb)
+{
+    if (!ctx) return VTX_E_INVALID;
+    if (!ctx->have_barcodes) return set_err(ctx, VTX_E_STATE, "vtx_set_barcodes must be called before vtx_submit2");
+    if (!hb) return set_err(ctx, VTX_E_INVALID, "batch is NULL");
+    const HostView hv = view_of(hb);
+    int rc = validate_batch(ctx, hv, false);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    TimeRec* tr = new_trec(ctx);
+    if (!tr) return set_err(ctx, VTX_E_CUDA, "cudaEventCreate failed");
+    InSlot* sl = nullptr;
+    rc = claim_slot(ctx, &sl);
+    if (rc) return rc;
+    DevBatch d{};
+    const uint32_t nl = hb->n_loci, nr = hb->n_reads;
+    CK(cudaEventRecord(tr->ev[EV_START], ctx->copy_stream));
+    UP(sl->locus_row, hb->locus_row, size_t(nl) * 4);
+    UP(sl->hap, hb->hap_bytes, hb->hap_bytes_len);
+    UP(sl->ref_off, hb->ref_off, size_t(nl) * 4); UP(sl->ref_len, hb->ref_len, size_t(nl) * 4);
+    UP(sl->alt_off, hb->alt_off, size_t(nl) * 4); UP(sl->alt_len, hb->alt_len, size_t(nl) * 4);
+    UP(sl->cand_start, hb->cand_start, size_t(nl + 1) * 8);
+    UP(sl->read_nib, hb->read_nib, hb->read_nib_len);
+    if (hb->read_off4) UP(sl->read_off4, hb->read_off4, size_t(nr) * 4);
+    UP(sl->read_len16, hb->read_len, size_t(nr) * 2);
+    UP(sl->read_cb_key, hb->read_cb_key, size_t(nr) * 8);
+    if (hb->n_exotic_cb) { UP(sl->cb_bytes, hb->cb_bytes, hv.cb_bytes_len); UP(sl->cb_off_ex, hb->cb_off, size_t(hb->n_exotic_cb + 1) * 4); }
+    if (hb->read_umi_key) UP(sl->read_umi, hb->read_umi_key, size_t(nr) * 8);
+    if (hb->cand_read) UP(sl->cand_read, hb->cand_read, size_t(hb->n_cand) * 4);
+    CK(cudaEventRecord(tr->ev[EV_H2D], ctx->copy_stream));
+    CK(cudaEventRecord(sl->copy_done, ctx->copy_stream));
+    tr->had_h2d = true;
+    d.n_loci = nl; d.n_reads = nr; d.n_cand = hb->n_cand;
+    d.locus_row = P<uint32_t>(sl->locus_row); d.hap = P<uint8_t>(sl->hap);
+    d.ref_off = P<uint32_t>(sl->ref_off); d.ref_len = P<uint32_t>(sl->ref_len);
+    d.alt_off = P<uint32_t>(sl->alt_off); d.alt_len = P<uint32_t>(sl->alt_len);
+    d.cand_start = P<uint64_t>(sl->cand_start); d.read_nib = P<uint8_t>(sl->read_nib);
+    d.read_cb_key = P<uint64_t>(sl->read_cb_key);
+    d.cb_bytes = hb->n_exotic_cb ? P<uint8_t>(sl->cb_bytes) : nullptr; d.cb_off_ex = hb->n_exotic_cb ? P<uint32_t>(sl->cb_off_ex) : nullptr;
+    d.read_cb_off = nullptr; d.read_cb_len = nullptr;
+    d.read_umi = hb->read_umi_key ? P<uint64_t>(sl->read_umi) : nullptr;
+    d.cand_read = hb->cand_read ? P<uint32_t>(sl->cand_read) : nullptr;
+    bool shapes[kNumShapes] = {};
+    rc = scan_host_batch(ctx, hv, &d.max_read_len, &d.max_hap_len, true, &d.max_depth, shapes);
+    if (rc) { cudaStreamSynchronize(ctx->copy_stream); --ctx->trec_used; return rc; }
+    d.class_mask = host_class_mask(ctx, shapes, d.max_read_len, d.max_hap_len);
+    CK(cudaStreamWaitEvent(ctx->stream, sl->copy_done, 0));
+    CK(cudaEventRecord(tr->ev[EV_C0], ctx->stream));
+    rc = expand_reads(ctx, nr, P<uint16_t>(sl->read_len16), hb->read_off4 ? P<uint32_t>(sl->read_off4) : nullptr, d);
+    if (rc) return rc;
+    rc = process_batch(ctx, d, tr);
+    if (rc) return rc;
+    CK(cudaEventRecord(sl->free_ev, ctx->stream));
+    return VTX_OK;
+}
+
+int vtx_submit2_device(vtx_ctx* ctx, const vtx_batch2* db, uint32_t max_read_len, uint32_t max_hap_len)
+{
+    if (!ctx) return VTX_E_INVALID;
+    if (!ctx->have_barcodes) return set_err(ctx, VTX_E_STATE, "vtx_set_barcodes must be called before vtx_submit2_device");
+    if (!db) return set_err(ctx, VTX_E_INVALID, "batch is NULL");
+    HostView hv = view_of(db); hv.cb_bytes_len = 0;       // device pointers: nothing may be dereferenced here
+    hv.cb_off_ex = db->cb_off;
+    int rc = validate_batch(ctx, hv, true);
+    if (rc) return rc;
+    if (max_read_len > uint32_t(kMaxRead)) return set_err(ctx, VTX_E_UNSUPPORTED, "reads longer than %d bases are not supported", kMaxRead);
+    CK(cudaSetDevice(ctx->device));
+    DevBatch d{};
+    d.n_loci = db->n_loci; d.n_reads = db->n_reads; d.n_cand = db->n_cand;
+    d.locus_row = db->locus_row; d.hap = db->hap_bytes; d.ref_off = db->ref_off; d.ref_len = db->ref_len;
+    d.alt_off = db->alt_off; d.alt_len = db->alt_len; d.cand_start = db->cand_start; d.read_nib = db->read_nib;
+    d.read_cb_key = db->read_cb_key; d.cb_bytes = db->cb_bytes; d.cb_off_ex = db->cb_off; d.read_cb_off = nullptr; d.read_cb_len = nullptr;
+    d.read_umi = db->read_umi_key; d.cand_read = db->cand_read;
+    d.max_read_len = max_read_len; d.max_hap_len = max_hap_len;
+    TimeRec* tr = new_trec(ctx);
+    if (!tr) return set_err(ctx, VTX_E_CUDA, "cudaEventCreate failed");
+    CK(cudaEventRecord(tr->ev[EV_C0], ctx->stream));
+    rc = expand_reads(ctx, db->n_reads, db->read_len, db->read_off4, d);
+    if (rc) return rc;
+    return process_batch(ctx, d, tr);
+}
+
+uint64_t vtx_pack_cb(const uint8_t* s, uint32_t len) { return (s || len == 0) ? pack_cb(s, len) : VTX_NO_CB_KEY; }
+
 int vtx_sync(vtx_ctx* ctx)
 {
     if (!ctx) return VTX_E_INVALID;
@@ -785,14 +1071,18 @@ static int finish_scalars(vtx_ctx* ctx)
     CK(cudaSetDevice(ctx->device));
     uint64_t* hs = static_cast<uint64_t*>(ctx->h_scalars);
     CK(cudaMemcpyAsync(hs, ctx->d_res_n.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(hs + 1, ctx->d_metrics.p, 24, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(hs + 1, ctx->d_metrics.p, 40, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    const uint64_t violated = ctx->finished ? 0 : hs[5];
     ctx->last_n = ctx->finished ? 0 : hs[0];
     ctx->last_metrics.num_not_cell_bc = ctx->finished ? 0 : hs[1];
     ctx->last_metrics.num_non_umi = ctx->finished ? 0 : hs[2];
     ctx->last_metrics.num_scored = ctx->finished ? 0 : hs[3];
     ctx->t_pairs = ctx->last_metrics.num_scored;
     ctx->finished = true;
+    if (violated)
+        return set_err(ctx, VTX_E_INVALID, "%llu loci of a device batch exceeded the bounds given to vtx_submit_device(_ex) (longest read / widest "
+                                           "haplotype window); they were skipped, the result is incomplete", (unsigned long long)violated);
     return VTX_OK;
 }
 
@@ -951,12 +1241,15 @@ int vtx_score_pairs(vtx_ctx* ctx, const vtx_batch* hb, uint64_t n_pairs, const u
                     const uint32_t* pair_locus, int16_t* ref_score, int16_t* alt_score)
 {
     if (!ctx) return VTX_E_INVALID;
-    int rc = validate_batch(ctx, hb);
+    if (!hb) return set_err(ctx, VTX_E_INVALID, "batch is NULL");
+    const HostView hv = view_of(hb);
+    HostView hv0 = hv; hv0.n_cand = 0; hv0.cand_read = nullptr;          // the cand_* fields are ignored here
+    int rc = validate_batch(ctx, hv0, false);
     if (rc) return rc;
     if (n_pairs >= 0xFFFFFFF0ull) return set_err(ctx, VTX_E_INVALID, "too many pairs");
     if (n_pairs && (!pair_read || !pair_locus || !ref_score || !alt_score)) return set_err(ctx, VTX_E_INVALID, "NULL pair arrays");
     DevBatch d{};
-    rc = scan_host_batch(ctx, hb, &d.max_read_len, &d.max_hap_len, false);
+    rc = scan_host_batch(ctx, hv0, &d.max_read_len, &d.max_hap_len, false);
     if (rc) return rc;
     if (n_pairs == 0) return VTX_OK;
     const uint32_t nl = hb->n_loci;
@@ -1031,6 +1324,8 @@ struct NcclApi {
     int (*CommDestroy)(nccl_comm) = nullptr;
     int (*AllGather)(const void*, void*, size_t, int, nccl_comm, cudaStream_t) = nullptr;
     int (*Broadcast)(const void*, void*, size_t, int, int, nccl_comm, cudaStream_t) = nullptr;
+    int (*Send)(const void*, size_t, int, int, nccl_comm, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, nccl_comm, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
@@ -1048,7 +1343,7 @@ bool load_nccl(std::string* why)
 #define SYM(field, name) *(void**)(&g_nccl.field) = dlsym(g_nccl.h, name); if (!g_nccl.field) { *why = std::string("missing symbol ") + name; return false; }
     SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
     SYM(AllGather, "ncclAllGather") SYM(Broadcast, "ncclBroadcast") SYM(GroupStart, "ncclGroupStart")
-    SYM(GroupEnd, "ncclGroupEnd") SYM(GetErrorString, "ncclGetErrorString")
+    SYM(GroupEnd, "ncclGroupEnd") SYM(GetErrorString, "ncclGetErrorString") SYM(Send, "ncclSend") SYM(Recv, "ncclRecv")
 #undef SYM
     g_nccl.ok = true;
     return true;
@@ -1089,62 +1384,111 @@ int vtx_comm_init(vtx_ctx* ctx, const uint8_t id[128], int32_t rank, int32_t n_r
     return VTX_OK;
 }
 
-int vtx_gather(vtx_ctx* ctx, vtx_result* out)
+int vtx_gather_start(vtx_ctx* ctx, int32_t root)
 {
-    if (!ctx || !out) return VTX_E_INVALID;
+    if (!ctx) return VTX_E_INVALID;
     if (!ctx->finished) return set_err(ctx, VTX_E_STATE, "vtx_gather must follow vtx_finish / vtx_finish_device");
+    if (ctx->gather_pending) return set_err(ctx, VTX_E_STATE, "a gather is already in flight: call vtx_gather_wait first");
+    const int nrk = ctx->n_ranks;
+    if (root != VTX_GATHER_ALL && (root < 0 || root >= nrk)) return set_err(ctx, VTX_E_INVALID, "gather root %d out of range", root);
+    if (nrk != 1 && !ctx->comm) return set_err(ctx, VTX_E_STATE, "vtx_comm_init has not been called");
     CK(cudaSetDevice(ctx->device));
     const size_t esz[7] = { 4, 4, 4, 4, 4, 8, 8 };
     DBuf* loc[7] = { &ctx->r_row, &ctx->r_col, &ctx->r_ref, &ctx->r_alt, &ctx->r_unk, &ctx->r_val, &ctx->r_val2 };
-    const int nrk = ctx->n_ranks;
-    std::vector<uint64_t> counts(size_t(nrk) * 4, 0);     // {n, not_cell_bc, non_umi, scored} per rank
-    if (nrk == 1 || !ctx->comm) {
-        if (nrk != 1) return set_err(ctx, VTX_E_STATE, "vtx_comm_init has not been called");
-        counts[0] = ctx->last_n; counts[1] = ctx->last_metrics.num_not_cell_bc; counts[2] = ctx->last_metrics.num_non_umi; counts[3] = ctx->last_metrics.num_scored;
-    } else {
-        ENS(ctx->g_counts, size_t(nrk + 1) * 32);
-        uint64_t mine[4] = { ctx->last_n, ctx->last_metrics.num_not_cell_bc, ctx->last_metrics.num_non_umi, ctx->last_metrics.num_scored };
-        uint64_t* dmine = P<uint64_t>(ctx->g_counts) + size_t(nrk) * 4;
-        CK(cudaMemcpyAsync(dmine, mine, 32, cudaMemcpyHostToDevice, ctx->stream));
-        NK(g_nccl.AllGather(dmine, ctx->g_counts.p, 4, kNcclUint64, static_cast<nccl_comm>(ctx->comm), ctx->stream));
-        CK(cudaMemcpyAsync(counts.data(), ctx->g_counts.p, size_t(nrk) * 32, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-    }
-    size_t total = 0;
-    std::vector<size_t> offs(nrk);
-    vtx_metrics met{};
-    for (int r = 0; r < nrk; ++r) {
-        offs[r] = total; total += counts[size_t(r) * 4];
-        met.num_not_cell_bc += counts[size_t(r) * 4 + 1]; met.num_non_umi += counts[size_t(r) * 4 + 2]; met.num_scored += counts[size_t(r) * 4 + 3];
-    }
     const bool values_only = (ctx->cfg.flags & VTX_F_VALUES_ONLY) != 0;     // then only row / col / val (/ val2) travel
     const bool want[7] = { true, true, !values_only, !values_only, !values_only, true, !values_only || ctx->cfg.mode == VTX_MODE_COVERAGE };
+    vtx_result& out = ctx->g_out;
+    memset(&out, 0, sizeof(out));
     const void* src[7] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
     if (nrk == 1) {
         for (int i = 0; i < 7; ++i) if (want[i]) src[i] = loc[i]->p;
+        out.n = ctx->last_n; out.metrics = ctx->last_metrics;
     } else {
-        for (int i = 0; i < 7; ++i) if (want[i]) ENS(ctx->g_dev[i], (total ? total : 1) * esz[i]);
+        if (!ctx->comm_stream) {
+            CK(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&ctx->ev_counts, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ctx->ev_gather, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ctx->ev_results, cudaEventDisableTiming));
+            CK(cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_counts), size_t(nrk + 1) * 32, cudaHostAllocDefault));
+        }
+        cudaStream_t cs = ctx->comm_stream;
+        nccl_comm comm = static_cast<nccl_comm>(ctx->comm);
+        // the local results are complete on the engine stream (vtx_finish synchronised it); order the comm stream behind it anyway
+        CK(cudaEventRecord(ctx->ev_results, ctx->stream));
+        CK(cudaStreamWaitEvent(cs, ctx->ev_results, 0));
+        // 1. counts: {n, not_cell_bc, non_umi, scored} of every rank.  One tiny allgather; the host needs the sizes to post
+        //    exact-size receives, and waits for this one event only (tens of microseconds, nothing else is blocked).
+        ENS(ctx->g_counts, size_t(nrk + 1) * 32);
+        uint64_t* mine = ctx->h_counts + size_t(nrk) * 4;
+        mine[0] = ctx->last_n; mine[1] = ctx->last_metrics.num_not_cell_bc; mine[2] = ctx->last_metrics.num_non_umi; mine[3] = ctx->last_metrics.num_scored;
+        uint64_t* dmine = P<uint64_t>(ctx->g_counts) + size_t(nrk) * 4;
+        CK(cudaMemcpyAsync(dmine, mine, 32, cudaMemcpyHostToDevice, cs));
+        NK(g_nccl.AllGather(dmine, ctx->g_counts.p, 4, kNcclUint64, comm, cs));
+        CK(cudaMemcpyAsync(ctx->h_counts, ctx->g_counts.p, size_t(nrk) * 32, cudaMemcpyDeviceToHost, cs));
+        CK(cudaEventRecord(ctx->ev_counts, cs));
+        CK(cudaEventSynchronize(ctx->ev_counts));
+        const uint64_t* counts = ctx->h_counts;
+        size_t total = 0;
+        std::vector<size_t> offs(nrk);
+        vtx_metrics met{};
+        for (int r = 0; r < nrk; ++r) {
+            offs[r] = total; total += counts[size_t(r) * 4];
+            met.num_not_cell_bc += counts[size_t(r) * 4 + 1]; met.num_non_umi += counts[size_t(r) * 4 + 2]; met.num_scored += counts[size_t(r) * 4 + 3];
+        }
+        out.n = total; out.metrics = met;
+        const bool receiver = root == VTX_GATHER_ALL || root == ctx->rank;
+        if (receiver) for (int i = 0; i < 7; ++i) if (want[i]) ENS(ctx->g_dev[i], (total ? total : 1) * esz[i]);
+        // 2. the triplets, exact sizes, one NCCL group.  Rooted: ncclSend / ncclRecv, only the writer's GPU receives;
+        //    all: one broadcast per (array, rank) = allgatherv.
         NK(g_nccl.GroupStart());
         for (int i = 0; i < 7; ++i) {
             if (!want[i]) continue;
-            for (int r = 0; r < nrk; ++r) {
-                const size_t n = counts[size_t(r) * 4];
-                if (!n) continue;
-                NK(g_nccl.Broadcast(loc[i]->p, static_cast<uint8_t*>(ctx->g_dev[i].p) + offs[r] * esz[i], n * esz[i], kNcclUint8, r,
-                                    static_cast<nccl_comm>(ctx->comm), ctx->stream));
+            if (root == VTX_GATHER_ALL) {
+                for (int r = 0; r < nrk; ++r) {
+                    const size_t n = counts[size_t(r) * 4];
+                    if (n) NK(g_nccl.Broadcast(loc[i]->p, static_cast<uint8_t*>(ctx->g_dev[i].p) + offs[r] * esz[i], n * esz[i], kNcclUint8, r, comm, cs));
+                }
+            } else if (ctx->rank == root) {
+                for (int r = 0; r < nrk; ++r) {
+                    const size_t n = counts[size_t(r) * 4];
+                    if (!n) continue;
+                    uint8_t* dst = static_cast<uint8_t*>(ctx->g_dev[i].p) + offs[r] * esz[i];
+                    if (r == root) CK(cudaMemcpyAsync(dst, loc[i]->p, n * esz[i], cudaMemcpyDeviceToDevice, cs));
+                    else NK(g_nccl.Recv(dst, n * esz[i], kNcclUint8, r, comm, cs));
+                }
+            } else if (ctx->last_n) {
+                NK(g_nccl.Send(loc[i]->p, size_t(ctx->last_n) * esz[i], kNcclUint8, root, comm, cs));
             }
         }
         NK(g_nccl.GroupEnd());
-        for (int i = 0; i < 7; ++i) if (want[i]) src[i] = ctx->g_dev[i].p;
+        CK(cudaEventRecord(ctx->ev_gather, cs));
+        ctx->gather_guard = true;
+        if (receiver) for (int i = 0; i < 7; ++i) if (want[i]) src[i] = ctx->g_dev[i].p;
     }
-    CK(cudaStreamSynchronize(ctx->stream));
-    out->n = total;
-    out->row = static_cast<const uint32_t*>(src[0]); out->col = static_cast<const uint32_t*>(src[1]);
-    out->ref_cnt = static_cast<const uint32_t*>(src[2]); out->alt_cnt = static_cast<const uint32_t*>(src[3]);
-    out->unk_cnt = static_cast<const uint32_t*>(src[4]);
-    out->val = static_cast<const double*>(src[5]); out->val2 = static_cast<const double*>(src[6]);
-    out->metrics = met;
+    out.row = static_cast<const uint32_t*>(src[0]); out.col = static_cast<const uint32_t*>(src[1]);
+    out.ref_cnt = static_cast<const uint32_t*>(src[2]); out.alt_cnt = static_cast<const uint32_t*>(src[3]);
+    out.unk_cnt = static_cast<const uint32_t*>(src[4]);
+    out.val = static_cast<const double*>(src[5]); out.val2 = static_cast<const double*>(src[6]);
+    ctx->gather_pending = true;
     return VTX_OK;
+}
+
+int vtx_gather_wait(vtx_ctx* ctx, vtx_result* out)
+{
+    if (!ctx || !out) return VTX_E_INVALID;
+    if (!ctx->gather_pending) return set_err(ctx, VTX_E_STATE, "no gather in flight");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->n_ranks > 1) CK(cudaEventSynchronize(ctx->ev_gather));
+    ctx->gather_pending = false;
+    *out = ctx->g_out;
+    return VTX_OK;
+}
+
+int vtx_gather(vtx_ctx* ctx, vtx_result* out)
+{
+    if (!ctx || !out) return VTX_E_INVALID;
+    const int rc = vtx_gather_start(ctx, VTX_GATHER_ALL);
+    return rc ? rc : vtx_gather_wait(ctx, out);
 }
 
 }  // extern "C"

@@ -37,6 +37,23 @@ struct BarcodeTable {
     const uint32_t* off;      // [n + 1]
 };
 
+// exact byte-string lookup of a CB tag in the barcode list: column id or -1
+__device__ __forceinline__ int32_t cb_lookup_bytes(const BarcodeTable& t, const uint8_t* __restrict__ key, uint32_t len)
+{
+    uint32_t h = uint32_t(fnv1a64(key, len)) & t.cap_mask;
+    for (;;) {
+        const int32_t s = t.slot[h];
+        if (s < 0) return -1;
+        const uint32_t o = t.off[s], l2 = t.off[s + 1] - o;
+        if (l2 == len) {
+            bool eq = true;
+            for (uint32_t i = 0; i < len; ++i) eq &= (t.bytes[o + i] == key[i]);
+            if (eq) return s;
+        }
+        h = (h + 1) & t.cap_mask;
+    }
+}
+
 // one thread per read: exact byte-string lookup of the CB tag in the barcode list
 __global__ void vtx_k_cb_lookup(BarcodeTable t, uint32_t n_reads, const uint8_t* __restrict__ cb_bytes,
                                 const uint32_t* __restrict__ read_cb_off, const uint16_t* __restrict__ read_cb_len,
@@ -45,24 +62,88 @@ __global__ void vtx_k_cb_lookup(BarcodeTable t, uint32_t n_reads, const uint8_t*
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_reads) return;
     const uint32_t off = read_cb_off[r];
+    read_col[r] = off != kNoCb ? cb_lookup_bytes(t, cb_bytes + off, read_cb_len[r]) : -1;
+}
+
+// ---- slim layout (vtx_batch2): cell tags travel as one injective u64 code per read -------------------------------
+constexpr uint64_t kNoCbKey = 0xFFFFFFFFFFFFFFFFull;
+constexpr uint64_t kCbExotic = 0x8000000000000000ull;
+
+// [ACGT]{1,24}(-N)?, N = 1..99 without a leading zero -> bases (2 bits each) << 12 | n_bases << 7 | N ; else kNoCbKey
+__host__ __device__ inline uint64_t pack_cb(const uint8_t* s, uint32_t len)
+{
+    uint32_t n = 0;
+    uint64_t k = 0;
+    while (n < len && n < 25) {
+        uint64_t c;
+        const uint8_t b = s[n];
+        if (b == 'A') c = 0; else if (b == 'C') c = 1; else if (b == 'G') c = 2; else if (b == 'T') c = 3; else break;
+        if (n == 24) return kNoCbKey;
+        k = (k << 2) | c;
+        ++n;
+    }
+    if (n == 0) return kNoCbKey;
+    uint64_t suffix = 0;
+    if (n < len) {
+        if (s[n] != '-') return kNoCbKey;
+        const uint32_t d = len - n - 1;
+        if (d < 1 || d > 2 || s[n + 1] < '1' || s[n + 1] > '9') return kNoCbKey;
+        suffix = uint64_t(s[n + 1] - '0');
+        if (d == 2) { if (s[n + 2] < '0' || s[n + 2] > '9') return kNoCbKey; suffix = suffix * 10 + uint64_t(s[n + 2] - '0'); }
+    }
+    return (k << 12) | (uint64_t(n) << 7) | suffix;
+}
+
+__host__ __device__ inline uint64_t mix64(uint64_t x)
+{
+    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull; x ^= x >> 27; x *= 0x94d049bb133111ebull; x ^= x >> 31;
+    return x;
+}
+
+struct BarcodeKeyTable {      // the barcodes that have a code: open addressing on the code itself
+    const uint64_t* key;      // [cap] code or kNoCbKey (empty)
+    const uint32_t* idx;      // [cap] column id
+    uint32_t cap_mask;
+};
+
+// one thread per read: one or two 8-byte probes instead of a byte-wise string compare
+__global__ void vtx_k_cb_lookup_key(BarcodeTable t, BarcodeKeyTable kt, uint32_t n_reads, const uint64_t* __restrict__ read_cb_key,
+                                    const uint8_t* __restrict__ cb_bytes, const uint32_t* __restrict__ cb_off,
+                                    int32_t* __restrict__ read_col)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    const uint64_t key = read_cb_key[r];
     int32_t col = -1;
-    if (off != kNoCb) {
-        const uint32_t len = read_cb_len[r];
-        const uint8_t* key = cb_bytes + off;
-        uint32_t h = uint32_t(fnv1a64(key, len)) & t.cap_mask;
+    if (key == kNoCbKey) {
+    } else if (key & kCbExotic) {
+        const uint32_t i = uint32_t(key & 0xFFFFFFFFu);
+        col = cb_lookup_bytes(t, cb_bytes + cb_off[i], cb_off[i + 1] - cb_off[i]);
+    } else {
+        uint32_t h = uint32_t(mix64(key)) & kt.cap_mask;
         for (;;) {
-            const int32_t s = t.slot[h];
-            if (s < 0) break;
-            const uint32_t o = t.off[s], l2 = t.off[s + 1] - o;
-            if (l2 == len) {
-                bool eq = true;
-                for (uint32_t i = 0; i < len; ++i) eq &= (t.bytes[o + i] == key[i]);
-                if (eq) { col = s; break; }
-            }
-            h = (h + 1) & t.cap_mask;
+            const uint64_t k = kt.key[h];
+            if (k == key) { col = int32_t(kt.idx[h]); break; }
+            if (k == kNoCbKey) break;
+            h = (h + 1) & kt.cap_mask;
         }
     }
     read_col[r] = col;
+}
+
+// slim layout -> the engine's internal read arrays.  Dense pools: 4-byte units per read first, offsets after a scan.
+__global__ void vtx_k_read_units(uint32_t n_reads, const uint16_t* __restrict__ read_len, uint32_t* __restrict__ units)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n_reads) units[r] = ((uint32_t(read_len[r]) + 1) / 2 + 3) / 4;
+}
+__global__ void vtx_k_expand_reads(uint32_t n_reads, const uint16_t* __restrict__ read_len, const uint32_t* __restrict__ off4,
+                                   uint64_t* __restrict__ read_off, uint32_t* __restrict__ read_len32)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    read_off[r] = uint64_t(off4[r]) * 4;
+    read_len32[r] = read_len[r];
 }
 
 // one thread per candidate: keep flag (for the compaction scan) + metric counters, warp-aggregated
@@ -73,7 +154,7 @@ __global__ void vtx_k_cand_filter(uint64_t n_cand, const uint32_t* __restrict__ 
     const uint64_t c = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     bool miss_cb = false, miss_umi = false, ok = false;
     if (c < n_cand) {
-        const uint32_t r = cand_read[c];
+        const uint32_t r = cand_read ? cand_read[c] : uint32_t(c);           // NULL: candidate c is read c
         if (read_col[r] < 0) miss_cb = true;                                 // main.rs:868-876
         else if (use_umi && read_umi_key[r] == kNoUmi) miss_umi = true;      // main.rs:880-888
         else ok = true;
@@ -115,7 +196,7 @@ __global__ void vtx_k_compact(uint64_t n_cand, const uint32_t* __restrict__ cand
 {
     const uint64_t c = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (c >= n_cand || !keep[c]) return;
-    const uint32_t p = pidx[c], r = cand_read[c];
+    const uint32_t p = pidx[c], r = cand_read ? cand_read[c] : uint32_t(c);
     pair_read[p] = r;
     pair_col[p] = uint32_t(read_col[r]);
     if (use_umi) pair_umi[p] = read_umi_key[r];
@@ -145,6 +226,7 @@ __global__ void vtx_k_locus_prep(uint32_t n_loci, const uint8_t* __restrict__ ha
                                  const uint32_t* __restrict__ alt_off, const uint32_t* __restrict__ alt_len,
                                  const uint32_t* __restrict__ pair_start, const uint32_t* __restrict__ pair_read,
                                  const uint32_t* __restrict__ read_len, int force_slow, int allow_split, int allow_multi, int allow_fold,
+                                 uint32_t max_read, uint32_t max_hap, unsigned long long* __restrict__ bounds_violated,
                                  uint32_t* __restrict__ tcount /* [kNumClasses][n_loci + 1] */)
 {
     const uint32_t l = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -170,13 +252,22 @@ __global__ void vtx_k_locus_prep(uint32_t n_loci, const uint8_t* __restrict__ ha
     bool fold = same && allow_fold && min(nr, na) > uint32_t(2 * kFoldP) && max(nr, na) <= uint32_t(2 * kFoldP + kFoldMaxMid);
     if (fold) for (uint32_t j = lane; j < uint32_t(kFoldP); j += 32) fold &= (rh[nr - 1 - j] == ah[na - 1 - j]);
     fold = __all_sync(0xffffffffu, fold);
-    if (fold) {                       // the folded kernel keeps 8 x 19 read rows in registers: every read of the locus must fit
-        uint32_t longest = 0;
-        for (uint32_t p = pair_start[l] + lane; p < pair_start[l + 1]; p += 32) longest = max(longest, read_len[pair_read[p]]);
-        fold = __reduce_max_sync(0xffffffffu, longest) <= uint32_t(kFoldMaxRead);
-    }
+    uint32_t longest = 0;
+    for (uint32_t p = pair_start[l] + lane; p < pair_start[l + 1]; p += 32) longest = max(longest, read_len[pair_read[p]]);
+    longest = __reduce_max_sync(0xffffffffu, longest);
+    // the folded kernel keeps 8 x 19 read rows in registers: every read of the locus must fit
+    fold = fold && longest <= uint32_t(kFoldMaxRead);
     if (lane != 0) return;
     const uint32_t nmax = max(nr, na);
+    // Buffers and kernel shapes were sized from max_read / max_hap (exact for host batches, the caller's promise for
+    // device batches).  A locus that breaks the promise gets no tiles -- nothing is read or written out of bounds --
+    // and the next vtx_finish reports the violation.
+    if (longest > max_read || nmax > max_hap) {
+        atomicAdd(bounds_violated, 1ull);
+#pragma unroll
+        for (int c = 0; c < kNumClasses; ++c) tcount[size_t(c) * (n_loci + 1) + l] = 0u;
+        return;
+    }
     int cls = kSlowClass;
     if (!exotic && !force_slow) {
 #pragma unroll

@@ -150,6 +150,188 @@ class StagedBatch:
             read_umi_key=self.read_umi_key[used], cand_read=inv.astype(np.uint32), n_rows=self.n_rows)
 
 
+_CB_CODE = np.full(256, 255, np.uint8)
+for _i, _b in enumerate(b"ACGT"):
+    _CB_CODE[_b] = _i
+
+
+def pack_cb_keys(cb_bytes: np.ndarray, read_cb_off: np.ndarray, read_cb_len: np.ndarray):
+    """vtx_pack_cb over all reads -> (keys u64 [n_reads], exotic tag bytes, exotic offsets u32 [n_exotic + 1]).
+    Tags the code cannot express (anything but [ACGT]{1,24}(-N)?) are listed as exotic: key = CB_EXOTIC | index."""
+    n = len(read_cb_off)
+    keys = np.full(n, _capi.NO_CB_KEY, np.uint64)
+    has = read_cb_off != NO_CB
+    ex_bytes, ex_off = [], [0]
+    lens = read_cb_len.astype(np.int64)
+    done = np.zeros(n, bool)
+    # fast path: tags of one common length, vectorised (synthetic shards and Cell Ranger BAMs: 16 bases + "-1")
+    if has.any():
+        L = int(np.bincount(lens[has]).argmax())
+        sel = np.nonzero(has & (lens == L))[0]
+        if L > 0 and len(sel):
+            mat = cb_bytes[read_cb_off[sel].astype(np.int64)[:, None] + np.arange(L)[None, :]]
+            code = _CB_CODE[mat]
+            nb = np.where((code == 255).any(axis=1), (code == 255).argmax(axis=1), L)          # leading ACGT run
+            ok = (nb >= 1) & (nb <= 24)
+            suffix = np.zeros(len(sel), np.uint64)
+            rest = L - nb
+            # suffix forms: none, "-d", "-dd" (no leading zero)
+            good = ok & (rest == 0)
+            for d in (1, 2):
+                cand = ok & (rest == d + 1)
+                if not cand.any():
+                    continue
+                idx = np.nonzero(cand)[0]
+                dash = mat[idx, nb[idx]] == ord("-")
+                d1 = mat[idx, nb[idx] + 1].astype(np.int64) - 48
+                val = d1.copy(); okd = dash & (d1 >= 1) & (d1 <= 9)
+                if d == 2:
+                    d2 = mat[idx, nb[idx] + 2].astype(np.int64) - 48
+                    okd &= (d2 >= 0) & (d2 <= 9); val = d1 * 10 + d2
+                suffix[idx[okd]] = val[okd].astype(np.uint64)
+                good[idx[okd]] = True
+            if good.any():
+                g = np.nonzero(good)[0]
+                k = np.zeros(len(g), np.uint64)
+                cg, nbg = code[g].astype(np.uint64), nb[g]
+                for j in range(min(L, 24)):
+                    use = j < nbg
+                    k = np.where(use, (k << np.uint64(2)) | (cg[:, j] & np.uint64(3)), k)
+                keys[sel[g]] = (k << np.uint64(12)) | (nbg.astype(np.uint64) << np.uint64(7)) | suffix[g]
+                done[sel[g]] = True
+    L_ = _capi.load()
+    for r in np.nonzero(has & ~done)[0]:
+        o, ln = int(read_cb_off[r]), int(lens[r])
+        raw = cb_bytes[o:o + ln].tobytes()
+        k = int(L_.vtx_pack_cb(raw, ln))
+        if k == _capi.NO_CB_KEY:
+            k = _capi.CB_EXOTIC | (len(ex_off) - 1)
+            ex_bytes.append(raw); ex_off.append(ex_off[-1] + ln)
+        keys[r] = k
+    exb = np.frombuffer(b"".join(ex_bytes), np.uint8).copy() if ex_bytes else np.zeros(0, np.uint8)
+    return keys, exb, np.asarray(ex_off, np.uint32)
+
+
+@dataclass
+class SlimBatch:
+    """The same shard in the slim staging layout `vtx_batch2` (include/vartrix_b200.h): reads packed back to back on
+    4-byte boundaries, u16 lengths, one u64 code per cell tag, UMI keys only with --umi, no candidate list when every
+    read serves exactly one locus."""
+    locus_row: np.ndarray
+    hap_bytes: np.ndarray
+    ref_off: np.ndarray
+    ref_len: np.ndarray
+    alt_off: np.ndarray
+    alt_len: np.ndarray
+    cand_start: np.ndarray
+    read_nib: np.ndarray
+    read_len: np.ndarray            # u16
+    read_cb_key: np.ndarray         # u64
+    cb_bytes: np.ndarray            # exotic tags only
+    cb_off: np.ndarray              # u32 [n_exotic + 1]
+    read_umi_key: np.ndarray        # u64 or None
+    cand_read: np.ndarray           # u32 or None (identity)
+    n_rows: int = 0
+
+    ARRAYS = ("locus_row", "hap_bytes", "ref_off", "ref_len", "alt_off", "alt_len", "cand_start", "read_nib", "read_len",
+              "read_cb_key", "cb_bytes", "cb_off", "read_umi_key", "cand_read")
+
+    @property
+    def n_loci(self): return int(self.locus_row.size)
+    @property
+    def n_reads(self): return int(self.read_len.size)
+    @property
+    def n_cand(self): return int(self.cand_start[-1]) if self.cand_start.size else 0
+    @property
+    def n_exotic(self): return int(self.cb_off.size) - 1
+
+    def nbytes(self) -> int:
+        return int(sum(getattr(self, f).nbytes for f in self.ARRAYS if getattr(self, f) is not None))
+
+    @staticmethod
+    def units(read_len):
+        return ((read_len.astype(np.int64) + 1) // 2 + 3) // 4
+
+    @classmethod
+    def from_staged(cls, sb: "StagedBatch", umi: bool) -> "SlimBatch":
+        assert sb.n_reads == 0 or int(sb.read_len.max()) <= 0xFFFF, "reads longer than 65535 bases need the vtx_batch layout"
+        units = cls.units(sb.read_len)
+        nb = (sb.read_len.astype(np.int64) + 1) // 2
+        n = sb.n_reads
+        st0 = int(sb.read_off[1] - sb.read_off[0]) if n > 1 else 0
+        uniform = (n > 1 and st0 > 0 and sb.read_nib.size >= st0 * n and bool((np.diff(sb.read_off.astype(np.int64)) == st0).all())
+                   and bool((units == units[0]).all()) and int(sb.read_off[0]) == 0)
+        if uniform:
+            w = int(units[0]) * 4
+            nib = np.ascontiguousarray(sb.read_nib[:st0 * n].reshape(n, st0)[:, :w]).copy() if w <= st0 else None
+            if nib is not None and w > int(nb[0]):
+                nib[:, int(nb[0]):] = 0
+        if not uniform or nib is None:
+            off = np.zeros(n + 1, np.int64); off[1:] = np.cumsum(units * 4)
+            nib = np.zeros(int(off[-1]), np.uint8)
+            for r in range(n):
+                o = int(sb.read_off[r]); nib[off[r]: off[r] + nb[r]] = sb.read_nib[o:o + nb[r]]
+        keys, exb, exo = pack_cb_keys(sb.cb_bytes, sb.read_cb_off, sb.read_cb_len)
+        ident = sb.n_cand == n and bool((sb.cand_read == np.arange(n, dtype=np.uint32)).all())
+        return cls(sb.locus_row, sb.hap_bytes, sb.ref_off, sb.ref_len, sb.alt_off, sb.alt_len, sb.cand_start,
+                   nib.reshape(-1), sb.read_len.astype(np.uint16), keys, exb, exo,
+                   np.ascontiguousarray(sb.read_umi_key) if umi else None, None if ident else sb.cand_read, n_rows=sb.n_rows)
+
+    def shard(self, lo: int, hi: int) -> "SlimBatch":
+        """Loci [lo, hi) as a self-contained slim shard."""
+        cs = self.cand_start
+        c0, c1 = int(cs[lo]), int(cs[hi])
+        if self.cand_read is None:
+            used = np.arange(c0, c1, dtype=np.int64); new_cand = None
+        else:
+            used, inv = np.unique(self.cand_read[c0:c1], return_inverse=True)
+            new_cand = inv.astype(np.uint32)
+        units = self.units(self.read_len)
+        off = np.zeros(self.n_reads + 1, np.int64); off[1:] = np.cumsum(units * 4)
+        if len(used) and int(used[-1]) - int(used[0]) + 1 == len(used):
+            nib = self.read_nib[off[used[0]]: off[used[-1] + 1]].copy()          # a contiguous run of reads
+        else:
+            nib = np.concatenate([self.read_nib[off[r]: off[r + 1]] for r in used]) if len(used) else np.zeros(0, np.uint8)
+        keys = self.read_cb_key[used].copy()
+        exb, exo = np.zeros(0, np.uint8), np.zeros(1, np.uint32)
+        ex = np.nonzero((keys != np.uint64(_capi.NO_CB_KEY)) & ((keys & np.uint64(_capi.CB_EXOTIC)) != 0))[0]
+        if len(ex):
+            pieces, offs = [], [0]
+            for j, r in enumerate(ex):
+                i = int(keys[r] & np.uint64(0xFFFFFFFF))
+                pieces.append(self.cb_bytes[int(self.cb_off[i]): int(self.cb_off[i + 1])]); offs.append(offs[-1] + len(pieces[-1]))
+                keys[r] = np.uint64(_capi.CB_EXOTIC | j)
+            exb, exo = np.concatenate(pieces), np.asarray(offs, np.uint32)
+        nl = hi - lo
+        ro, ra = self.ref_off[lo:hi].astype(np.int64), self.alt_off[lo:hi].astype(np.int64)
+        h0 = int(min(ro.min(), ra.min())) if nl else 0
+        h1 = int(max((ro + self.ref_len[lo:hi]).max(), (ra + self.alt_len[lo:hi]).max())) if nl else 0
+        h1 = (h1 + 15) // 16 * 16
+        hap = self.hap_bytes[h0:h1].copy()           # windows of consecutive loci are stored consecutively
+        return SlimBatch(self.locus_row[lo:hi].copy(), hap, (ro - h0).astype(np.uint32), self.ref_len[lo:hi].copy(),
+                         (ra - h0).astype(np.uint32), self.alt_len[lo:hi].copy(), (cs[lo:hi + 1] - cs[lo]), nib, self.read_len[used].copy(),
+                         keys, exb, exo, None if self.read_umi_key is None else self.read_umi_key[used].copy(), new_cand, n_rows=self.n_rows)
+
+    def to_c(self, ptr=None) -> _capi.Batch2:
+        """ptr: optional {field: address} of copies of the arrays elsewhere (pinned / device memory)."""
+        b = _capi.Batch2()
+        def p(f):
+            a = getattr(self, f)
+            if a is None or a.size == 0:
+                return None
+            return ptr[f] if ptr is not None else a.ctypes.data
+        b.n_loci = self.n_loci; b.locus_row = p("locus_row")
+        b.hap_bytes = p("hap_bytes"); b.hap_bytes_len = self.hap_bytes.size
+        b.ref_off = p("ref_off"); b.ref_len = p("ref_len"); b.alt_off = p("alt_off"); b.alt_len = p("alt_len")
+        b.cand_start = p("cand_start")
+        b.n_reads = self.n_reads; b.read_nib = p("read_nib"); b.read_nib_len = self.read_nib.size
+        b.read_off4 = None; b.read_len = p("read_len"); b.read_cb_key = p("read_cb_key")
+        b.n_exotic_cb = self.n_exotic; b.cb_bytes = p("cb_bytes"); b.cb_off = p("cb_off") if self.n_exotic else None
+        b.read_umi_key = p("read_umi_key")
+        b.n_cand = self.n_cand; b.cand_read = p("cand_read")
+        return b
+
+
 @dataclass
 class Barcodes:
     """De-duplicated barcode list in first-seen order (load_barcodes, main.rs:697-718)."""
@@ -193,12 +375,13 @@ class Engine:
 
     def __init__(self, scoring_method: str = "consensus", umi: bool = False, device: int = 0, stream: int = 0,
                  keep_scores: bool = False, min_score: int = 25, no_split: bool = False,
-                 values_only: bool = False, no_fold: bool = False):
+                 values_only: bool = False, no_fold: bool = False, band_k: int = 0, band_w: int = 0, band_mode: int = 0):
         self._L = _capi.load()
         cfg = _capi.Config(device=device, mode=MODES[scoring_method], use_umi=int(bool(umi)), match=1, mismatch=-5,
                            gap_open=-5, gap_extend=-1, min_score=min_score, stream=stream or None,
                            flags=(_capi.F_KEEP_SCORES if keep_scores else 0) | (_capi.F_NO_SPLIT if no_split else 0) |
-                           (_capi.F_VALUES_ONLY if values_only else 0) | (_capi.F_NO_FOLD if no_fold else 0))
+                           (_capi.F_VALUES_ONLY if values_only else 0) | (_capi.F_NO_FOLD if no_fold else 0),
+                           band_k=band_k, band_w=band_w, band_mode=band_mode)
         h = C.c_void_p()
         rc = self._L.vtx_create(C.byref(cfg), C.byref(h))
         if rc != 0:
@@ -231,6 +414,15 @@ class Engine:
         cb = batch.to_c()
         self._keep.append(batch)
         self._ck(self._L.vtx_submit(self._h, C.byref(cb)), "vtx_submit")
+
+    def submit2(self, slim: "SlimBatch"):
+        """One shard in the slim staging layout (vtx_submit2)."""
+        cb = slim.to_c()
+        self._keep.append(slim)
+        self._ck(self._L.vtx_submit2(self._h, C.byref(cb)), "vtx_submit2")
+
+    def submit2_device(self, cbatch2: _capi.Batch2, max_read_len: int, max_hap_len: int):
+        self._ck(self._L.vtx_submit2_device(self._h, C.byref(cbatch2), max_read_len, max_hap_len), "vtx_submit2_device")
 
     def submit_device(self, cbatch: _capi.Batch, max_read_len: int, max_hap_len: int):
         self._ck(self._L.vtx_submit_device_ex(self._h, C.byref(cbatch), max_read_len, max_hap_len), "vtx_submit_device_ex")
@@ -307,10 +499,23 @@ class Engine:
         self._ck(self._L.vtx_gather(self._h, C.byref(res)), "vtx_gather")
         return res
 
+    def gather_start(self, root: int = _capi.GATHER_ALL):
+        """Asynchronous gather (root = rank that receives; GATHER_ALL = allgatherv); later submits overlap it."""
+        self._ck(self._L.vtx_gather_start(self._h, root), "vtx_gather_start")
+
+    def gather_wait(self) -> _capi.Result:
+        res = _capi.Result()
+        self._ck(self._L.vtx_gather_wait(self._h, C.byref(res)), "vtx_gather_wait")
+        return res
+
     def fetch(self, dev_res: _capi.Result, copy: bool = True) -> Triplets:
         out = _capi.Result()
         self._ck(self._L.vtx_fetch(self._h, C.byref(dev_res), C.byref(out)), "vtx_fetch")
         return self._triplets(out, copy)
+
+
+def pack_cb(s: bytes) -> int:
+    return int(_capi.load().vtx_pack_cb(s, len(s)))
 
 
 def pack_umi(s: bytes) -> int:
