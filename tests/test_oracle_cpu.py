@@ -115,7 +115,7 @@ def test_header_symbols_are_exported():
     lib = ctypes.CDLL(_capi.LIB_PATH)
     for s in _capi.SYMBOLS:
         assert hasattr(lib, s), s
-    assert lib.vtx_abi_version() == 1
+    assert lib.vtx_abi_version() == 2
 
 
 def test_header_is_plain_c(tmp_path):
@@ -125,8 +125,8 @@ def test_header_is_plain_c(tmp_path):
     from vartrix_b200 import _capi
     src = tmp_path / "abi.c"
     src.write_text('#include "vartrix_b200.h"\n'
-                   'int main(void) { vtx_config c; vtx_batch b; vtx_result r; vtx_timing t; (void)c; (void)b; (void)r; (void)t;\n'
-                   '  return vtx_abi_version() == 1 && vtx_pack_umi((const unsigned char*)"ACGT", 4) != VTX_NO_UMI ? 0 : 1; }\n')
+                   'int main(void) { vtx_config c; vtx_batch b; vtx_batch2 b2; vtx_result r; vtx_timing t; (void)c; (void)b; (void)b2; (void)r; (void)t;\n'
+                   '  return vtx_abi_version() == 2 && vtx_pack_cb((const unsigned char*)"ACGT-1", 6) == 111105ull && vtx_pack_umi((const unsigned char*)"ACGT", 4) != VTX_NO_UMI ? 0 : 1; }\n')
     exe = tmp_path / "abi"
     libdir = os.path.dirname(_capi.LIB_PATH)
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
