@@ -45,6 +45,24 @@ def _worker(rank, world, port, out_dir):
         full = eng.fetch(eng.gather())
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), row=full.row, col=full.col, val=full.val, val2=full.val2,
                  ref=full.ref_cnt, alt=full.alt_cnt, scored=full.metrics["num_scored"])
+        # the asynchronous, rooted form: two steps in flight, the gather of step 1 overlaps the kernels of step 2, and only
+        # rank 1 (the "writer") receives; the slim layout feeds the second pass
+        sl = vb.SlimBatch.from_staged(sb, True)
+        eng.submit2(sl); eng.finish_device(); eng.gather_start(1)
+        eng.submit2(sl); eng.finish_device()
+        r1 = eng.gather_wait()
+        got1 = eng.fetch(r1) if rank == 1 else None
+        n1, scored1 = int(r1.n), int(r1.metrics.num_scored)
+        eng.gather_start(1)
+        r2 = eng.gather_wait()
+        got2 = eng.fetch(r2) if rank == 1 else None
+        assert int(r2.n) == n1 == len(full.row) and scored1 == full.metrics["num_scored"]
+        if rank == 1:
+            for g in (got1, got2):
+                assert np.array_equal(g.row, full.row) and np.array_equal(g.col, full.col) and np.array_equal(g.val, full.val)
+                assert np.array_equal(g.val2, full.val2) and np.array_equal(g.alt_cnt, full.alt_cnt)
+        else:
+            assert not r1.row and not r2.val            # non-root ranks get the totals only
     dist.barrier()
     dist.destroy_process_group()
 
@@ -68,3 +86,23 @@ def test_two_gpu_gather_matches_oracle(tmp_path, oracle):
         assert np.array_equal(got["row"], np.concatenate(exp["row"])) and np.array_equal(got["col"], np.concatenate(exp["col"]))
         assert np.array_equal(got["val"], np.concatenate(exp["val"])) and np.array_equal(got["val2"], np.concatenate(exp["val2"]))
         assert np.array_equal(got["ref"], np.concatenate(exp["ref_cnt"])) and int(got["scored"]) == scored
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs two CUDA devices")
+def test_cli_shards_loci_over_two_gpus(tmp_path):
+    """`--devices 0,1`: contiguous locus ranges per GPU, one rooted NCCL gather, outputs byte-identical to one GPU."""
+    import subprocess
+    from vartrix_b200 import synth_files
+    ds = synth_files.write_dataset(str(tmp_path / "files"), n_loci=600, n_barcodes=80, depth=25, read_len=100, seed=13)
+    cli = os.path.join(ROOT, "vartrix_b200", "bin", "vartrix_b200")
+    outs = {}
+    for name, dev in (("one", ["--device", "0"]), ("two", ["--devices", "0,1"]), ("two_rev", ["--devices", "1,0"])):
+        d = tmp_path / name; d.mkdir()
+        cmd = [cli, "-v", ds["vcf"], "-b", ds["bam"], "-f", ds["fasta"], "-c", ds["barcodes"], "-o", str(d / "out.mtx"), "--ref-matrix", str(d / "ref.mtx"),
+               "-s", "coverage", "--umi", "--threads", "4", "--shard-loci", "37", "--log-level", "info", *dev]
+        r = subprocess.run(cmd, cwd=str(d), capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs[name] = (open(d / "out.mtx").read(), open(d / "ref.mtx").read(),
+                      [ln for ln in r.stderr.splitlines() if "Number of" in ln])
+    assert outs["one"][0].count("\n") > 1000
+    assert outs["two"] == outs["one"] and outs["two_rev"] == outs["one"]

@@ -34,6 +34,15 @@ __global__ void __launch_bounds__(1024, 1) k(uint32_t* out, int iters, long long
             if (OP == 14) { x[i] = __viaddmax_s16x2(x[i], 0xFFFFFFFFu, y); z = (z & x[i]) + 0x10001u; y = y ^ (z >> 3); }  // DPX + 3 alu
             if (OP == 15) x[i] = __vcmpeq2(x[i], y) + z;                             // packed compare (emulated?)
             if (OP == 16) x[i] = max((int)x[i], (int)y) + 1;                         // 32-bit max
+            // which DPX instructions share an issue resource?  independent chains, alternating kinds
+            if (OP == 17) x[i] = (i & 1) ? __viaddmax_s16x2(x[i], 0xFFFFFFFFu, y) : __vimax3_s16x2(x[i], y, z);
+            if (OP == 18) x[i] = (i & 1) ? __viaddmax_s16x2(x[i], 0xFFFFFFFFu, y) : __vmaxs2(x[i], y);
+            if (OP == 19) x[i] = (i & 1) ? __vimax3_s16x2(x[i], y, z) : __vmaxs2(x[i], y);
+            if (OP == 20) x[i] = __vmaxs2(x[i], y);
+            if (OP == 21) x[i] = (i & 1) ? __viaddmax_s16x2(x[i], 0xFFFFFFFFu, y) : x[i] + 0xFFFAFFFAu;
+            if (OP == 22) x[i] = (i & 1) ? __vimax3_s16x2(x[i], y, z) : x[i] + 0xFFFAFFFAu;
+            if (OP == 23) x[i] = (i % 3 == 0) ? __viaddmax_s16x2(x[i], 0xFFFFFFFFu, y) : (i % 3 == 1) ? __vimax3_s16x2(x[i], y, z) : x[i] + 0xFFFAFFFAu;
+            if (OP == 24) x[i] = (i & 1) ? __viaddmax_s16x2(x[i], 0xFFFFFFFFu, y) : __viaddmax_s16x2_relu(x[i], y, z);
         }
     }
     long long t1 = clock64();
@@ -76,6 +85,14 @@ int main()
     run<14>("VIADDMNMX + 3-4 int ops (per DPX)", 8);
     run<15>("__vcmpeq2 (+IADD)", 8);
     run<16>("IMNMX.S32 (+IADD)", 8);
+    run<20>("VIMNMX.S16x2 (2-input)", 8);
+    run<17>("VIADDMNMX + VIMNMX3 1:1", 8);
+    run<18>("VIADDMNMX + VIMNMX 1:1", 8);
+    run<19>("VIMNMX3 + VIMNMX 1:1", 8);
+    run<21>("VIADDMNMX + plain add 1:1", 8);
+    run<22>("VIMNMX3 + plain add 1:1", 8);
+    run<23>("VIADDMNMX + VIMNMX3 + plain add 3:3:2", 8);
+    run<24>("VIADDMNMX + VIADDMNMX.RELU 1:1", 8);
     run<6>("SHFL.UP", 8);
     run<7>("LDS.128 (+3 IADD)", 8);
     return 0;

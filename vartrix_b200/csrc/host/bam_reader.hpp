@@ -390,6 +390,17 @@ public:
     bool bad() const { return !err_.empty(); }
     const std::string& error() const { return err_; }
     void set_check_crc(bool on) { bg_.set_check_crc(on); }
+    // compressed file offset where the 16 kb window of `pos` starts (BAI linear index; monotone within a contig).
+    // Differences of it estimate how much BAM a range of loci spans -- used to balance loci over GPUs before any decode.
+    uint64_t linear_offset(int tid, int64_t pos) const
+    {
+        if (tid < 0 || size_t(tid) >= refs_.size() || refs_[size_t(tid)].linear.empty()) return 0;
+        const std::vector<uint64_t>& lin = refs_[size_t(tid)].linear;
+        size_t w = pos < 0 ? 0 : size_t(pos >> 14);
+        if (w >= lin.size()) w = lin.size() - 1;
+        while (w > 0 && lin[w] == 0) --w;           // empty windows carry 0: walk back to the last filled one
+        return lin[w] >> 16;
+    }
 
 private:
     bool fail(const std::string& what)

@@ -47,6 +47,7 @@ struct Opts {
     std::string vcf, bam, fasta, barcodes, out_matrix = "out_matrix.mtx", ref_matrix = "ref_matrix.mtx", out_variants, out_barcodes;
     std::string scoring = "consensus", bam_tag = "CB", valid_chars = "ATGCatgc", dump_staged;
     long padding = 100, threads = 1, mapq = 0, device = 0, shard_loci = 0;      // 0: chosen from the number of loci and threads
+    std::vector<int> devices;          // --devices: the loci are sharded over these GPUs (contiguous ranges, main.rs:250-254)
     bool primary = false, no_dups = false, umi = false, ref_matrix_given = false;
 };
 
@@ -73,8 +74,31 @@ void usage()
          "      --bam-tag TAG           BAM tag marking cells [CB]\n"
          "      --valid-chars CHARS     Valid characters in an alternative haplotype [ATGCatgc]\n"
          "      --device INT            CUDA device ordinal [0]\n"
+         "      --devices LIST          Shard the loci over several GPUs: e.g. 0-7 or 0,2,5 (one NCCL gather at the end)\n"
          "      --shard-loci INT        VCF records per staged shard [up to 2048, fewer for short VCFs]\n"
          "      --dump-staged FILE      Stage only, write the shards to FILE (no GPU)");
+}
+
+// "0-3", "0,2,5", "1": CUDA device ordinals, no duplicates
+bool parse_devices(const std::string& spec, std::vector<int>* out)
+{
+    out->clear();
+    size_t p = 0;
+    while (p <= spec.size()) {
+        size_t q = spec.find(',', p);
+        if (q == std::string::npos) q = spec.size();
+        const std::string tok = spec.substr(p, q - p);
+        if (tok.empty()) return false;
+        const size_t dash = tok.find('-');
+        char* end = nullptr;
+        const long a = strtol(tok.c_str(), &end, 10);
+        long b = a;
+        if (dash != std::string::npos) { if (end != tok.c_str() + dash) return false; b = strtol(tok.c_str() + dash + 1, &end, 10); }
+        if (*end != 0 || a < 0 || b < a || b > 1023) return false;
+        for (long d = a; d <= b; ++d) { if (std::find(out->begin(), out->end(), int(d)) != out->end()) return false; out->push_back(int(d)); }
+        p = q + 1;
+    }
+    return !out->empty();
 }
 
 bool parse(int argc, char** argv, Opts* o)
@@ -104,6 +128,7 @@ bool parse(int argc, char** argv, Opts* o)
         else if (a == "--bam-tag") o->bam_tag = v();
         else if (a == "--valid-chars") o->valid_chars = v();
         else if (a == "--device") o->device = atol(v().c_str());
+        else if (a == "--devices") { if (!parse_devices(v(), &o->devices)) { fprintf(stderr, "error: bad --devices list\n"); return false; } }
         else if (a == "--shard-loci") o->shard_loci = atol(v().c_str());
         else if (a == "--dump-staged") o->dump_staged = v();
         else if (a == "-h" || a == "--help") { usage(); exit(0); }
@@ -115,6 +140,7 @@ bool parse(int argc, char** argv, Opts* o)
     if (o->bam_tag.size() != 2) { fprintf(stderr, "error: --bam-tag must have two characters\n"); return false; }
     if (o->threads < 1) o->threads = 1;
     if (o->shard_loci < 0) o->shard_loci = 0;
+    if (o->devices.empty()) o->devices.push_back(int(o->device));
     return true;
 }
 
@@ -144,14 +170,36 @@ void check_inputs_exist(const Opts& o)
     } else { LOG_ERR("BAM file did not end in .bam or .cram. Unable to validate"); exit(1); }
 }
 
+// --dump-staged writes the shard in the vtx_batch layout (16-byte aligned reads, tag bytes per read) that the staging
+// tests compare with the oracle's decode; the codes are turned back into the tag bytes they stand for.
 void dump_shard(FILE* f, const StagedShard& s)
 {
     auto put = [&](const void* p, size_t bytes) { uint64_t n = bytes; fwrite(&n, 8, 1, f); if (bytes) fwrite(p, 1, bytes, f); };
 #define PUTV(v) put((v).data(), (v).size() * sizeof((v)[0]))
+    const size_t nr = s.read_len.size();
+    std::vector<uint8_t> nib, cb;
+    std::vector<uint64_t> read_off(nr), umi(nr, VTX_NO_UMI);
+    std::vector<uint32_t> read_len(nr), cb_off(nr);
+    std::vector<uint16_t> cb_len(nr);
+    size_t src = 0;
+    for (size_t r = 0; r < nr; ++r) {
+        const size_t nb = (size_t(s.read_len[r]) + 1) / 2;
+        while (nib.size() & 15) nib.push_back(0);
+        read_off[r] = nib.size(); read_len[r] = s.read_len[r];
+        nib.insert(nib.end(), s.read_nib.begin() + src, s.read_nib.begin() + src + nb);
+        src += (nb + 3) / 4 * 4;
+        const uint64_t k = s.read_cb_key[r];
+        if (k == VTX_NO_CB_KEY) { cb_off[r] = VTX_NO_CB; cb_len[r] = 0; continue; }
+        cb_off[r] = uint32_t(cb.size());
+        if (k & VTX_CB_EXOTIC) { const uint32_t i = uint32_t(k & 0xFFFFFFFFu); cb.insert(cb.end(), s.cb_bytes.begin() + s.cb_off[i], s.cb_bytes.begin() + s.cb_off[i + 1]); }
+        else { const std::string t = unpack_cb(k); cb.insert(cb.end(), t.begin(), t.end()); }
+        cb_len[r] = uint16_t(cb.size() - cb_off[r]);
+    }
+    while (nib.size() & 15) nib.push_back(0);
+    if (s.with_umi) umi = s.read_umi_key;
     fwrite("VTXS", 1, 4, f);
     PUTV(s.locus_row); PUTV(s.hap_bytes); PUTV(s.ref_off); PUTV(s.ref_len); PUTV(s.alt_off); PUTV(s.alt_len); PUTV(s.cand_start);
-    PUTV(s.read_nib); PUTV(s.read_off); PUTV(s.read_len); PUTV(s.cb_bytes); PUTV(s.read_cb_off); PUTV(s.read_cb_len);
-    PUTV(s.read_umi_key); PUTV(s.cand_read);
+    PUTV(nib); PUTV(read_off); PUTV(read_len); PUTV(cb); PUTV(cb_off); PUTV(cb_len); PUTV(umi); PUTV(s.cand_read);
 #undef PUTV
     uint64_t m[7] = { s.met.num_reads, s.met.num_low_mapq, s.met.num_non_primary, s.met.num_duplicates, s.met.num_not_useful,
                       s.met.num_invalid_recs, s.met.num_multiallelic_recs };
@@ -176,7 +224,7 @@ struct Arena {
 // Copies the shard's arrays into the pinned arena.  This runs on the submitting thread while up to `--threads` workers
 // stage; with many workers a single memcpy stream (~10 GB/s) would cap the whole pipeline near 70 M reads/s, so shards
 // above a few megabytes are copied in 4 MB pieces by the caller plus up to three helper threads.
-void stage_into_arena(const StagedShard& s, Arena& a, vtx_batch* b)
+void stage_into_arena(const StagedShard& s, Arena& a, vtx_batch2* b)
 {
     struct Job { uint8_t* dst; const uint8_t* src; size_t bytes; };
     std::vector<Job> jobs;
@@ -192,9 +240,10 @@ void stage_into_arena(const StagedShard& s, Arena& a, vtx_batch* b)
     s.fill(b);
 #define MV(field, vec) b->field = static_cast<decltype(b->field)>(put((vec).data(), (vec).size() * sizeof((vec)[0])))
     MV(locus_row, s.locus_row); MV(hap_bytes, s.hap_bytes); MV(ref_off, s.ref_off); MV(ref_len, s.ref_len); MV(alt_off, s.alt_off);
-    MV(alt_len, s.alt_len); MV(cand_start, s.cand_start); MV(read_nib, s.read_nib); MV(read_off, s.read_off); MV(read_len, s.read_len);
-    MV(cb_bytes, s.cb_bytes); MV(read_cb_off, s.read_cb_off); MV(read_cb_len, s.read_cb_len); MV(read_umi_key, s.read_umi_key);
-    MV(cand_read, s.cand_read);
+    MV(alt_len, s.alt_len); MV(cand_start, s.cand_start); MV(read_nib, s.read_nib); MV(read_len, s.read_len); MV(read_cb_key, s.read_cb_key);
+    if (b->n_exotic_cb) { MV(cb_bytes, s.cb_bytes); MV(cb_off, s.cb_off); } else { b->cb_bytes = nullptr; b->cb_off = nullptr; }
+    if (s.with_umi) MV(read_umi_key, s.read_umi_key);
+    if (!s.identity) MV(cand_read, s.cand_read);
 #undef MV
     std::atomic<size_t> next{ 0 };
     auto run = [&]() {
@@ -209,6 +258,19 @@ void stage_into_arena(const StagedShard& s, Arena& a, vtx_batch* b)
 
 }  // namespace
 
+// One GPU of the run: its own engine context, a contiguous range of shards, a thread that feeds it in order.
+struct Lane {
+    int device = 0, rank = 0;
+    size_t lo = 0, hi = 0;              // shard index range [lo, hi)
+    vtx_ctx* ctx = nullptr;
+    size_t consumed = 0;                // shards of this lane handed to the engine so far (guarded by the staging mutex)
+    Arena arenas[3];
+    HostMetrics hm;
+    std::string err;
+    int rc = 0;
+    vtx_result dev{};                   // this lane's triplets on its device
+};
+
 int main(int argc, char** argv)
 {
     // staging grows multi-megabyte vectors on many threads: keep them on the heap arenas instead of
@@ -219,27 +281,36 @@ int main(int argc, char** argv)
     if (!parse(argc, argv, &o)) { usage(); return 1; }
     check_inputs_exist(o);
     std::string err;
+    const bool dumping = !o.dump_staged.empty();
 
     BarcodeList bcs;
     if (!load_barcodes(o.barcodes, &bcs, &err)) { LOG_ERR("%s", err.c_str()); return 1; }
     LOG_INFO("Loaded %zu barcodes", bcs.keys.size());
 
-    // CUDA context creation takes ~1 s: start it now, in the background, while the VCF is parsed and the first
-    // shards are staged
-    vtx_ctx* ctx = nullptr;
-    std::string engine_err;
-    std::future<int> engine_ready;
-    if (o.dump_staged.empty()) {
-        engine_ready = std::async(std::launch::async, [&]() -> int {
-            vtx_config cfg{};
-            cfg.device = int(o.device);
-            cfg.mode = o.scoring == "consensus" ? VTX_MODE_CONSENSUS : o.scoring == "coverage" ? VTX_MODE_COVERAGE : VTX_MODE_ALT_FRAC;
-            cfg.flags = VTX_F_VALUES_ONLY;       // the writers need row, col and the matrix values only
-            cfg.use_umi = o.umi; cfg.match = 1; cfg.mismatch = -5; cfg.gap_open = -5; cfg.gap_extend = -1; cfg.min_score = 25;
-            if (vtx_create(&cfg, &ctx) != VTX_OK) { engine_err = vtx_last_error(nullptr); return 1; }
-            if (vtx_set_barcodes(ctx, bcs.bytes.data(), bcs.off.data(), uint32_t(bcs.keys.size())) != VTX_OK) { engine_err = vtx_last_error(ctx); return 1; }
-            return 0;
-        });
+    // CUDA context creation takes ~1 s per device: start it now, in the background, while the VCF is parsed and the
+    // first shards are staged.  With several devices every lane also joins the engine's NCCL communicator.
+    const size_t n_dev = dumping ? 1 : o.devices.size();
+    std::vector<Lane> lanes(n_dev);
+    uint8_t nccl_id[128] = {};
+    if (!dumping && n_dev > 1 && vtx_comm_unique_id(nccl_id) != VTX_OK) { printf("Vartrix error.\nError: %s\n", vtx_last_error(nullptr)); return 1; }
+    std::vector<std::future<int>> engine_ready(n_dev);
+    if (!dumping) {
+        for (size_t d = 0; d < n_dev; ++d) {
+            lanes[d].device = o.devices[d]; lanes[d].rank = int(d);
+            engine_ready[d] = std::async(std::launch::async, [&, d]() -> int {
+                Lane& ln = lanes[d];
+                vtx_config cfg{};
+                cfg.device = ln.device;
+                cfg.mode = o.scoring == "consensus" ? VTX_MODE_CONSENSUS : o.scoring == "coverage" ? VTX_MODE_COVERAGE : VTX_MODE_ALT_FRAC;
+                cfg.flags = VTX_F_VALUES_ONLY;       // the writers need row, col and the matrix values only
+                cfg.use_umi = o.umi; cfg.match = 1; cfg.mismatch = -5; cfg.gap_open = -5; cfg.gap_extend = -1; cfg.min_score = 25;
+                cfg.band_k = 6; cfg.band_w = 20; cfg.band_mode = VTX_BAND_FULL;          // main.rs:33-34
+                if (vtx_create(&cfg, &ln.ctx) != VTX_OK) { ln.err = vtx_last_error(nullptr); return 1; }
+                if (vtx_set_barcodes(ln.ctx, bcs.bytes.data(), bcs.off.data(), uint32_t(bcs.keys.size())) != VTX_OK) { ln.err = vtx_last_error(ln.ctx); return 1; }
+                if (n_dev > 1 && vtx_comm_init(ln.ctx, nccl_id, int32_t(d), int32_t(n_dev)) != VTX_OK) { ln.err = vtx_last_error(ln.ctx); return 1; }
+                return 0;
+            });
+        }
     }
 
     std::vector<VcfRecord> recs;
@@ -251,36 +322,67 @@ int main(int argc, char** argv)
     // validate_inputs (main.rs:545-594): contigs present in FASTA and BAM, record end inside the contig
     Fasta fa0;
     if (!fa0.open(o.fasta, &err)) { LOG_ERR("%s", err.c_str()); return 1; }
-    {
-        BamFile b0;
-        if (!b0.open(o.bam, &err)) { printf("Vartrix error.\nError: error opening bam file: %s (%s)\n", o.bam.c_str(), err.c_str()); return 1; }
-        for (const VcfRecord& r : recs) {
-            if (!fa0.has(r.chrom)) { LOG_ERR("Sequence %s not seen in FASTA", r.chrom.c_str()); return 1; }
-            if (b0.tid_of(r.chrom) < 0) { LOG_ERR("Sequence %s not seen in BAM", r.chrom.c_str()); return 1; }
-            const int64_t end = r.pos0 + int64_t(r.alleles[0].size());
-            if (end > fa0.length(r.chrom)) {
-                LOG_ERR("Record %s:%lld has end position %lld, which is larger than the chromosome length (%lld). Does your FASTA match your VCF?",
-                        r.chrom.c_str(), (long long)r.pos0, (long long)end, (long long)fa0.length(r.chrom));
-                return 1;
-            }
+    BamFile b0;
+    if (!b0.open(o.bam, &err)) { printf("Vartrix error.\nError: error opening bam file: %s (%s)\n", o.bam.c_str(), err.c_str()); return 1; }
+    for (const VcfRecord& r : recs) {
+        if (!fa0.has(r.chrom)) { LOG_ERR("Sequence %s not seen in FASTA", r.chrom.c_str()); return 1; }
+        if (b0.tid_of(r.chrom) < 0) { LOG_ERR("Sequence %s not seen in BAM", r.chrom.c_str()); return 1; }
+        const int64_t end = r.pos0 + int64_t(r.alleles[0].size());
+        if (end > fa0.length(r.chrom)) {
+            LOG_ERR("Record %s:%lld has end position %lld, which is larger than the chromosome length (%lld). Does your FASTA match your VCF?",
+                    r.chrom.c_str(), (long long)r.pos0, (long long)end, (long long)fa0.length(r.chrom));
+            return 1;
         }
     }
 
     StageArgs sa;
     sa.padding = o.padding; sa.mapq = uint32_t(o.mapq); sa.primary_only = o.primary; sa.no_duplicates = o.no_dups;
     sa.bam_tag[0] = o.bam_tag[0]; sa.bam_tag[1] = o.bam_tag[1];
+    sa.with_umi = o.umi || dumping;            // without --umi the engine never looks at the UB keys: they are not staged
     for (unsigned char c : o.valid_chars) sa.valid[c] = true;
 
-    // ---- staging: worker threads produce shards of `shard_loci` records; the main thread consumes them in order ----
+    // ---- staging: worker threads produce shards of `shard_loci` records; one lane per GPU consumes its range in order ----
     // default shard size: 2048 loci (~100 k candidates at 50x, enough to fill the GPU), smaller when the VCF is short so that
     // every staging thread still gets ~10 shards (load balance; the GPU is idle most of the time anyway)
     if (o.shard_loci == 0) o.shard_loci = long(std::min<size_t>(2048, std::max<size_t>(128, recs.size() / (size_t(o.threads) * 10 + 1))));
     const size_t n_shards = (recs.size() + size_t(o.shard_loci) - 1) / size_t(o.shard_loci);
+
+    // Loci -> GPUs: contiguous ranges like the reference's static chunks (main.rs:250-254), balanced by the compressed
+    // bytes of BAM each shard spans (BAI linear index) -- a cheap stand-in for the candidate count, known before any decode.
+    {
+        std::vector<double> w(n_shards, 1.0);
+        double total = 0;
+        for (size_t k = 0; k < n_shards; ++k) {
+            const VcfRecord& a = recs[k * size_t(o.shard_loci)];
+            const VcfRecord& z = recs[std::min(recs.size(), (k + 1) * size_t(o.shard_loci)) - 1];
+            if (a.chrom == z.chrom) {
+                const int tid = b0.tid_of(a.chrom);
+                const uint64_t f0 = b0.linear_offset(tid, a.pos0), f1 = b0.linear_offset(tid, z.pos0 + int64_t(z.alleles[0].size()) + (1 << 14));
+                if (f1 > f0) w[k] = double(f1 - f0);
+            }
+            total += w[k];
+        }
+        size_t k = 0;
+        double acc = 0;
+        for (size_t d = 0; d < n_dev; ++d) {
+            lanes[d].lo = k;
+            const double target = total * double(d + 1) / double(n_dev);
+            while (k < n_shards && (d + 1 == n_dev || acc + w[k] * 0.5 <= target)) acc += w[k++];
+            lanes[d].hi = k;
+        }
+        lanes[n_dev - 1].hi = n_shards;
+    }
+    // staging order: round robin over the lanes so that every GPU is fed from the start
+    std::vector<size_t> order; order.reserve(n_shards);
+    std::vector<size_t> lane_of(n_shards, 0);
+    for (size_t i = 0, left = n_shards; left; ++i)
+        for (size_t d = 0; d < n_dev; ++d)
+            if (lanes[d].lo + i < lanes[d].hi) { order.push_back(lanes[d].lo + i); lane_of[lanes[d].lo + i] = d; --left; }
+
     std::vector<std::unique_ptr<StagedShard>> ready(n_shards);
     std::mutex mu; std::condition_variable cv;
     std::atomic<size_t> next{ 0 };
-    size_t consumed = 0;                       // guarded by mu
-    const size_t window = size_t(o.threads) * 2 + 2;
+    const size_t window = std::max<size_t>(2, (size_t(o.threads) * 2 + 2 + n_dev - 1) / n_dev);
     bool failed = false; std::string fail_msg;
     UmiInterner umis;
     std::vector<std::unique_ptr<StagedShard>> recycled;      // guarded by mu
@@ -288,9 +390,11 @@ int main(int argc, char** argv)
         Fasta fa; BamFile bam; std::string e;
         if (!fa.open(o.fasta, &e) || !bam.open(o.bam, &e)) { std::lock_guard<std::mutex> g(mu); failed = true; fail_msg = e; cv.notify_all(); return; }
         for (;;) {
-            const size_t k = next.fetch_add(1);
-            if (k >= n_shards) break;
-            { std::unique_lock<std::mutex> g(mu); cv.wait(g, [&] { return failed || k < consumed + window; }); if (failed) return; }
+            const size_t i = next.fetch_add(1);
+            if (i >= n_shards) break;
+            const size_t k = order[i];
+            Lane& ln = lanes[lane_of[k]];
+            { std::unique_lock<std::mutex> g(mu); cv.wait(g, [&] { return failed || k - ln.lo < ln.consumed + window; }); if (failed) return; }
             std::unique_ptr<StagedShard> sh;
             { std::lock_guard<std::mutex> g(mu); if (!recycled.empty()) { sh = std::move(recycled.back()); recycled.pop_back(); } }
             if (!sh) sh = std::make_unique<StagedShard>();
@@ -300,10 +404,9 @@ int main(int argc, char** argv)
             cv.notify_all();
         }
     };
-    HostMetrics hm;
+
     FILE* dump = nullptr;
-    Arena arenas[3];
-    if (!o.dump_staged.empty()) {            // before the pool starts: an early return must not leave joinable threads behind
+    if (dumping) {            // before the pool starts: an early return must not leave joinable threads behind
         dump = fopen(o.dump_staged.c_str(), "wb");
         if (!dump) { LOG_ERR("cannot write %s", o.dump_staged.c_str()); return 1; }
         uint64_t hdr[2] = { recs.size(), bcs.keys.size() };
@@ -312,46 +415,62 @@ int main(int argc, char** argv)
     std::vector<std::thread> pool;
     for (long t = 0; t < o.threads; ++t) pool.emplace_back(worker);
 
-    if (!dump && engine_ready.get() != 0) {
-        printf("Vartrix error.\nError: %s\n", engine_err.c_str());
-        { std::lock_guard<std::mutex> g(mu); failed = true; }
-        cv.notify_all();
-        for (auto& t : pool) t.join();
-        return 1;
-    }
-    LOG_INFO("[%.3f s] engine ready, staging on %ld thread(s)", now_s(), o.threads);
-    int rc = 0;
-    for (size_t k = 0; k < n_shards && rc == 0; ++k) {
-        std::unique_ptr<StagedShard> sh;
-        {
-            std::unique_lock<std::mutex> g(mu);
-            cv.wait(g, [&] { return failed || ready[k]; });
-            if (failed) { rc = 1; break; }
-            sh = std::move(ready[k]);
-            consumed = k + 1;
+    // one consumer per lane: shards of its range, in order, into its engine (or into the dump file)
+    auto consume = [&](Lane& ln) {
+        if (!dumping && engine_ready[size_t(ln.rank)].get() != 0) { ln.rc = 1; std::lock_guard<std::mutex> g(mu); failed = true; cv.notify_all(); return; }
+        for (size_t k = ln.lo; k < ln.hi && ln.rc == 0; ++k) {
+            std::unique_ptr<StagedShard> sh;
+            {
+                std::unique_lock<std::mutex> g(mu);
+                cv.wait(g, [&] { return failed || ready[k]; });
+                if (failed) { ln.rc = 1; break; }
+                sh = std::move(ready[k]);
+                ln.consumed = k - ln.lo + 1;
+            }
+            cv.notify_all();
+            ln.hm.add(sh->met);
+            auto recycle = [&]() { sh->clear(); std::lock_guard<std::mutex> g(mu); recycled.push_back(std::move(sh)); };
+            if (dump) { dump_shard(dump, *sh); recycle(); continue; }
+            Arena& ar = ln.arenas[(k - ln.lo) % 3];
+            if (k - ln.lo >= 3 && vtx_wait_copies(ln.ctx) != VTX_OK) { ln.err = vtx_last_error(ln.ctx); ln.rc = 1; break; }     // the arena's previous copy must have landed
+            if (!ar.ensure(sh->bytes())) { ln.err = "pinned allocation failed"; ln.rc = 1; break; }
+            vtx_batch2 b;
+            stage_into_arena(*sh, ar, &b);
+            if (vtx_submit2(ln.ctx, &b) != VTX_OK) { ln.err = vtx_last_error(ln.ctx); ln.rc = 1; }
+            recycle();
         }
-        cv.notify_all();
-        hm.add(sh->met);
-        auto recycle = [&]() { sh->clear(); std::lock_guard<std::mutex> g(mu); recycled.push_back(std::move(sh)); };
-        if (dump) { dump_shard(dump, *sh); recycle(); continue; }
-        Arena& ar = arenas[k % 3];
-        if (k >= 3 && vtx_wait_copies(ctx) != VTX_OK) { rc = 1; break; }     // the arena's previous copy must have landed
-        if (!ar.ensure(sh->bytes())) { LOG_ERR("pinned allocation failed"); rc = 1; break; }
-        vtx_batch b;
-        stage_into_arena(*sh, ar, &b);
-        if (vtx_submit(ctx, &b) != VTX_OK) { printf("Vartrix error.\nError: %s\n", vtx_last_error(ctx)); rc = 1; }
-        recycle();
+        if (ln.rc) { std::lock_guard<std::mutex> g(mu); failed = true; cv.notify_all(); return; }
+        if (dump || n_dev == 1) return;
+        // several GPUs: results stay on the device; one rooted gather over NCCL brings them to lane 0 (the writer)
+        vtx_result tmp{};
+        if (vtx_finish_device(ln.ctx, &ln.dev) != VTX_OK || vtx_gather_start(ln.ctx, 0) != VTX_OK || vtx_gather_wait(ln.ctx, &tmp) != VTX_OK) {
+            ln.err = vtx_last_error(ln.ctx); ln.rc = 1; return;
+        }
+        ln.dev = tmp;
+    };
+    LOG_INFO("[%.3f s] staging on %ld thread(s) for %zu GPU(s), %zu shards of %ld records", now_s(), o.threads, n_dev, n_shards, o.shard_loci);
+    {
+        std::vector<std::thread> lane_threads;
+        for (size_t d = 1; d < n_dev; ++d) lane_threads.emplace_back(consume, std::ref(lanes[d]));
+        consume(lanes[0]);
+        for (auto& t : lane_threads) t.join();
     }
+    int rc = 0;
+    HostMetrics hm;
+    for (Lane& ln : lanes) { hm.add(ln.hm); if (ln.rc) rc = 1; }
     if (rc) { std::lock_guard<std::mutex> g(mu); failed = true; }
     cv.notify_all();
     for (auto& t : pool) t.join();
     if (failed && !fail_msg.empty()) { printf("Vartrix error.\nError: %s\n", fail_msg.c_str()); rc = 1; }
+    for (Lane& ln : lanes) if (!ln.err.empty()) { printf("Vartrix error.\nError: %s\n", ln.err.c_str()); rc = 1; }
     if (dump) { fclose(dump); return rc; }
-    if (rc) { vtx_destroy(ctx); return rc; }
+    if (rc) { fflush(nullptr); _exit(rc); }
 
     LOG_INFO("[%.3f s] all shards staged and submitted", now_s());
+    vtx_ctx* ctx = lanes[0].ctx;
     vtx_result res{};
-    if (vtx_finish(ctx, &res) != VTX_OK) { printf("Vartrix error.\nError: %s\n", vtx_last_error(ctx)); vtx_destroy(ctx); return 1; }
+    const int frc = n_dev == 1 ? vtx_finish(ctx, &res) : vtx_fetch(ctx, &lanes[0].dev, &res);
+    if (frc != VTX_OK) { printf("Vartrix error.\nError: %s\n", vtx_last_error(ctx)); fflush(nullptr); _exit(1); }
 
     LOG_INFO("[%.3f s] triplets on the host", now_s());
     // metrics (main.rs:350-379)
@@ -386,7 +505,7 @@ int main(int argc, char** argv)
     double sum = 0;
     for (uint64_t k = 0; k < res.n; ++k) sum += res.val[k];
     if (sum == 0.0) LOG_ERR("The resulting matrix has a sum of 0. Did you use the --umi flag on data without UMIs?");   // main.rs:410-415
-    // every output is closed; tearing the CUDA context and the pinned arenas down costs 0.5-0.9 s that a one-shot CLI
+    // every output is closed; tearing the CUDA contexts and the pinned arenas down costs 0.5-0.9 s that a one-shot CLI
     // does not need to spend (the driver reclaims everything at process exit)
     fflush(nullptr);
     _exit(rc);

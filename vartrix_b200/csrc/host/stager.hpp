@@ -33,28 +33,67 @@ struct StageArgs {
     bool no_duplicates = false;  // --no-duplicates
     char bam_tag[2] = { 'C', 'B' };
     bool valid[256] = {};        // --valid-chars
+    bool with_umi = true;        // stage the UB keys (--umi, or a dump for the tests); without --umi nobody reads them
 };
 
+// vtx_pack_cb (include/vartrix_b200.h), kept local so that staging can run without the CUDA library: an injective code of
+// [ACGT]{1,24}(-N)?, N = 1..99 without a leading zero; VTX_NO_CB_KEY for anything else (the tag is then staged as bytes)
+inline uint64_t pack_cb(const uint8_t* s, uint32_t len)
+{
+    uint32_t n = 0;
+    uint64_t k = 0;
+    while (n < len && n < 25) {
+        uint64_t c;
+        const uint8_t b = s[n];
+        if (b == 'A') c = 0; else if (b == 'C') c = 1; else if (b == 'G') c = 2; else if (b == 'T') c = 3; else break;
+        if (n == 24) return VTX_NO_CB_KEY;
+        k = (k << 2) | c;
+        ++n;
+    }
+    if (n == 0) return VTX_NO_CB_KEY;
+    uint64_t suffix = 0;
+    if (n < len) {
+        if (s[n] != '-') return VTX_NO_CB_KEY;
+        const uint32_t d = len - n - 1;
+        if (d < 1 || d > 2 || s[n + 1] < '1' || s[n + 1] > '9') return VTX_NO_CB_KEY;
+        suffix = uint64_t(s[n + 1] - '0');
+        if (d == 2) { if (s[n + 2] < '0' || s[n + 2] > '9') return VTX_NO_CB_KEY; suffix = suffix * 10 + uint64_t(s[n + 2] - '0'); }
+    }
+    return (k << 12) | (uint64_t(n) << 7) | suffix;
+}
+inline std::string unpack_cb(uint64_t key)
+{
+    const uint32_t n = uint32_t(key >> 7) & 31u, suffix = uint32_t(key & 127u);
+    std::string s(n, 'A');
+    uint64_t k = key >> 12;
+    for (uint32_t i = n; i-- > 0;) { s[i] = "ACGT"[k & 3]; k >>= 2; }
+    if (suffix) { s += '-'; s += std::to_string(suffix); }
+    return s;
+}
+
+// One shard in the slim staging layout (vtx_batch2): reads back to back on 4-byte boundaries, u16 lengths, cell tags as
+// codes (+ the few that have none as bytes), UMI keys only when asked for, candidate list only when a read serves two loci.
 struct StagedShard {
-    std::vector<uint32_t> locus_row, ref_off, ref_len, alt_off, alt_len, read_len, read_cb_off, cand_read;
-    std::vector<uint64_t> cand_start, read_off, read_umi_key;
-    std::vector<uint16_t> read_cb_len;
+    std::vector<uint32_t> locus_row, ref_off, ref_len, alt_off, alt_len, cand_read, cb_off;
+    std::vector<uint64_t> cand_start, read_cb_key, read_umi_key;
+    std::vector<uint16_t> read_len;
     std::vector<uint8_t> hap_bytes, read_nib, cb_bytes;
+    bool identity = true;        // candidate c is read c so far (no read shared between loci)
+    bool with_umi = true;        // read_umi_key is filled
     HostMetrics met;
 
     void clear()          // keeps the capacity: shards are recycled so steady-state staging does not page-fault
     {
-        locus_row.clear(); ref_off.clear(); ref_len.clear(); alt_off.clear(); alt_len.clear(); read_len.clear(); read_cb_off.clear();
-        cand_read.clear(); cand_start.clear(); read_off.clear(); read_umi_key.clear(); read_cb_len.clear(); hap_bytes.clear();
-        read_nib.clear(); cb_bytes.clear(); met = HostMetrics();
+        locus_row.clear(); ref_off.clear(); ref_len.clear(); alt_off.clear(); alt_len.clear(); read_len.clear(); read_cb_key.clear();
+        cand_read.clear(); cand_start.clear(); cb_off.clear(); read_umi_key.clear(); hap_bytes.clear();
+        read_nib.clear(); cb_bytes.clear(); met = HostMetrics(); identity = true;
     }
     size_t bytes() const
     {
-        return (locus_row.size() + ref_off.size() * 4 + read_len.size() * 2 + cand_read.size()) * 4 +
-               (cand_start.size() + read_off.size() * 2) * 8 + read_cb_len.size() * 2 + hap_bytes.size() + read_nib.size() +
-               cb_bytes.size() + 16 * 16;
+        return (locus_row.size() * 5 + cand_read.size() + cb_off.size()) * 4 + (cand_start.size() + read_cb_key.size() + read_umi_key.size()) * 8 +
+               read_len.size() * 2 + hap_bytes.size() + read_nib.size() + cb_bytes.size() + 16 * 16;
     }
-    void fill(vtx_batch* b) const
+    void fill(vtx_batch2* b) const
     {
         memset(b, 0, sizeof(*b));
         b->n_loci = uint32_t(locus_row.size()); b->locus_row = locus_row.data();
@@ -62,10 +101,10 @@ struct StagedShard {
         b->ref_off = ref_off.data(); b->ref_len = ref_len.data(); b->alt_off = alt_off.data(); b->alt_len = alt_len.data();
         b->cand_start = cand_start.data();
         b->n_reads = uint32_t(read_len.size()); b->read_nib = read_nib.data(); b->read_nib_len = read_nib.size();
-        b->read_off = read_off.data(); b->read_len = read_len.data();
-        b->cb_bytes = cb_bytes.data(); b->cb_bytes_len = cb_bytes.size();
-        b->read_cb_off = read_cb_off.data(); b->read_cb_len = read_cb_len.data(); b->read_umi_key = read_umi_key.data();
-        b->n_cand = cand_read.size(); b->cand_read = cand_read.data();
+        b->read_off4 = nullptr; b->read_len = read_len.data(); b->read_cb_key = read_cb_key.data();
+        b->n_exotic_cb = cb_off.empty() ? 0 : uint32_t(cb_off.size() - 1); b->cb_bytes = cb_bytes.data(); b->cb_off = cb_off.data();
+        b->read_umi_key = with_umi ? read_umi_key.data() : nullptr;
+        b->n_cand = cand_read.size(); b->cand_read = identity ? nullptr : cand_read.data();
     }
 };
 
@@ -172,6 +211,8 @@ private:
 inline bool stage_loci(const std::vector<VcfRecord>& recs, size_t lo, size_t hi, const Fasta& fa, BamFile& bam,
                        const StageArgs& a, UmiInterner& umis, StagedShard* out, std::string* err)
 {
+    out->with_umi = a.with_umi;
+    out->cb_off.push_back(0);
     static thread_local ReadIndex read_index;               // record virtual offset -> staged read id (table reused across shards)
     read_index.clear();
     BamRecord rec;
@@ -216,24 +257,35 @@ inline bool stage_loci(const std::vector<VcfRecord>& recs, size_t lo, size_t hi,
                 const uint32_t rid = read_index.find_or_insert(rec.voff, uint32_t(out->read_len.size()), &fresh);
                 if (fresh) {
                     const int32_t ls = rec.l_seq() < 0 ? 0 : rec.l_seq();
-                    pad16(out->read_nib);
-                    out->read_off.push_back(out->read_nib.size());
-                    out->read_len.push_back(uint32_t(ls));
+                    if (ls > 0xFFFF) { *err = "read longer than 65535 bases at " + v.chrom + ":" + std::to_string(rec.pos()); return false; }
+                    while (out->read_nib.size() & 3) out->read_nib.push_back(0);                              // every read starts on a 4-byte boundary
+                    out->read_len.push_back(uint16_t(ls));
                     out->read_nib.insert(out->read_nib.end(), rec.seq(), rec.seq() + (ls + 1) / 2);
                     uint32_t n = 0;
                     const uint8_t* cb = rec.aux_z(a.bam_tag, &n);                                             // main.rs:737-750
-                    if (cb && n <= 0xFFFF) { out->read_cb_off.push_back(uint32_t(out->cb_bytes.size())); out->read_cb_len.push_back(uint16_t(n)); out->cb_bytes.insert(out->cb_bytes.end(), cb, cb + n); }
-                    else { out->read_cb_off.push_back(VTX_NO_CB); out->read_cb_len.push_back(0); }
-                    const uint8_t* ub = rec.aux_z("UB", &n);                                                  // main.rs:752-757
-                    out->read_umi_key.push_back(ub ? umis.key(ub, n) : VTX_NO_UMI);
+                    uint64_t key = VTX_NO_CB_KEY;
+                    if (cb && n <= 0xFFFF) {
+                        key = pack_cb(cb, n);
+                        if (key == VTX_NO_CB_KEY) {        // a tag the code cannot express travels as bytes
+                            key = VTX_CB_EXOTIC | uint64_t(out->cb_off.size() - 1);
+                            out->cb_bytes.insert(out->cb_bytes.end(), cb, cb + n);
+                            out->cb_off.push_back(uint32_t(out->cb_bytes.size()));
+                        }
+                    }
+                    out->read_cb_key.push_back(key);
+                    if (a.with_umi) {
+                        const uint8_t* ub = rec.aux_z("UB", &n);                                              // main.rs:752-757
+                        out->read_umi_key.push_back(ub ? umis.key(ub, n) : VTX_NO_UMI);
+                    }
                 }
+                if (rid != out->cand_read.size()) out->identity = false;
                 out->cand_read.push_back(rid);
             }
             if (bam.bad()) { *err = bam.error(); return false; }            // corrupt / truncated BAM: abort (main.rs:830)
         }
         out->cand_start.push_back(out->cand_read.size());
     }
-    pad16(out->read_nib);
+    while (out->read_nib.size() & 3) out->read_nib.push_back(0);
     pad16(out->hap_bytes);
     return true;
 }
