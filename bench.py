@@ -17,8 +17,8 @@ the rank that writes the matrix (`--gather root`, ncclSend/Recv) and overlapped 
 `e2e`    : pairs/s through the host-facing C ABI from pinned HOST buffers (vtx_submit2 + vtx_finish), i.e. with the
            host->device copy of the shard (slim staging layout, ~96 B per candidate) and the device->host copy of the
            triplets in the timed region.  The step's shard is handed over the way a staging producer would: a 1 % shard
-           first, then shards growing by up to 1.4x (less when the measured copy/kernel ratio asks for it) up to 1/6 of
-           the step, so that every copy hides behind the previous shard's kernels.
+           (at least 100 k candidates) first, then shards growing by up to 2x (less when the measured copy/kernel ratio
+           asks for it) up to 1/6 of the step, so that every copy hides behind the previous shard's kernels.
 `roofline`: the dominant kernel (vtx_k_sw_fold for windows built with --padding >= 96) against the measured HBM
            peak, from CUDA events recorded on the engine's stream inside the library (vtx_last_timing), averaged over
            the timed steps; `roofline.issue_bound` is the same kernel against the ALU-pipe bound that actually binds.
@@ -59,8 +59,9 @@ def parse_args(argv=None):
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--chunks", type=int, default=6, help="staged shards per step on the e2e path (copy/compute overlap); with --growth: largest shard = 1/chunks of the step")
-    ap.add_argument("--growth", type=float, default=1.4, help="e2e shards grow geometrically from --first-chunk by this factor (0: equal shards after the first)")
+    ap.add_argument("--growth", type=float, default=2.0, help="e2e shards grow geometrically from --first-chunk by this factor (0: equal shards after the first)")
     ap.add_argument("--first-chunk", type=float, default=0.01, help="fraction of the candidates in the first (priming) shard")
+    ap.add_argument("--min-shard", type=int, default=100_000, help="e2e shards are not made smaller than this many candidates (per-submit fixed costs)")
     return ap.parse_args(argv)
 
 
@@ -103,13 +104,6 @@ def describe(args, cfg, world, info, extra=None):
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle's C port of the reference algorithm on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_threads():
-    try:
-        return len(os.sched_getaffinity(0))
-    except Exception:
-        return os.cpu_count() or 1
-
-
 def cgroup_cpu_quota():
     """-> cores the cgroup lets this process use (cpu.max quota / period), or None when unlimited / unknown."""
     for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
@@ -126,6 +120,19 @@ def cgroup_cpu_quota():
         except Exception:
             continue
     return None
+
+
+def cpu_threads():
+    """Threads the CPU arm may use: the affinity mask, capped at twice the cgroup CPU quota when there is one (a box that
+    shows 128 logical CPUs but grants 16 cores of quota runs 128 busy threads slower than 32)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    q = cgroup_cpu_quota()
+    if q:
+        n = max(1, min(n, int(round(2 * q))))
+    return n
 
 
 def pick_growth(h2d_ms, kernel_ms, cap):
@@ -161,12 +168,19 @@ def cpu_baseline(sb, bcs, cfg, info, target_s):
     pairs, dt = cpu_sample_run(sb, bcs, cfg, n_loci, threads)
     value = pairs / dt
     scaling = {}
-    for t in sorted({1, 8, 32, threads}):
-        if t > threads:
+    try:
+        all_threads = len(os.sched_getaffinity(0))
+    except Exception:
+        all_threads = threads
+    for t in sorted({1, 8, 32, threads, all_threads}):
+        if t > all_threads:
             continue
         nl = int(min(sb.n_loci, max(t * 4, 0.1 * target_s * (value * t / threads) / per_locus, 32)))
         p, d = cpu_sample_run(sb, bcs, cfg, nl, t)
         scaling[str(t)] = p / d
+    best_t = max(scaling, key=lambda k: scaling[k])
+    if scaling[best_t] > value:             # the headline is the best the box gives, whatever the thread count
+        value, threads = scaling[best_t], int(best_t)
     v1 = scaling.get("1", value / threads)
     eff = value / (v1 * threads) if v1 > 0 else None
     nb = int(min(sb.n_loci, max(threads * 4, 0.25 * target_s * value / per_locus)))
@@ -388,7 +402,8 @@ def run_gpu(args):
     # the copy of shard k+1 overlaps the kernels of shard k
     def stage_e2e_shards(growth):
         parts, nbytes = [], 0
-        for lo, hi in vb.shard_bounds(sb.cand_start, max(1, args.chunks), first_frac=args.first_chunk, growth=growth):
+        first = max(args.first_chunk, min(1.0, args.min_shard / max(info["n_cand"], 1)))
+        for lo, hi in vb.shard_bounds(sb.cand_start, max(1, args.chunks), first_frac=first, growth=growth):
             if hi <= lo:
                 continue
             part = staged.shard(lo, hi)

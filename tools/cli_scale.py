@@ -1,0 +1,97 @@
+"""File -> matrix throughput of the C++ CLI at scale: a config-3-sized synthetic file set (BAM + BAI + VCF + FASTA +
+barcodes), the CLI at several staging-thread counts (and GPU counts), reads/s per phase.
+
+    python tools/cli_scale.py --loci 100000 --threads 16 64 128 [--devices 0 0-7]  > profiles/r02_cli_scale.json
+
+Phases (from the CLI's --log-level info output): staging thread-seconds split into file read / inflate / crc32 / record
+scan + filters + packing; copy into the pinned arenas; device milliseconds (h2d, prep, Smith-Waterman, post); wall clock
+to "all shards submitted", "triplets on the host" and "outputs written"."""
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def quota():
+    try:
+        a, b = open("/sys/fs/cgroup/cpu.max").read().split()
+        return None if a == "max" else float(a) / float(b)
+    except Exception:
+        return None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--loci", type=int, default=100000)
+    ap.add_argument("--depth", type=int, default=50)
+    ap.add_argument("--barcodes", type=int, default=50000)
+    ap.add_argument("--threads", type=int, nargs="+", default=[16, 64, 128])
+    ap.add_argument("--devices", nargs="+", default=["0"])
+    ap.add_argument("--mode", default="consensus")
+    ap.add_argument("--keep", default="")
+    a = ap.parse_args()
+    from vartrix_b200 import synth_files
+    d = a.keep or tempfile.mkdtemp(prefix="vtx_scale_")
+    t0 = time.time()
+    if not os.path.exists(os.path.join(d, "reads.bam")):
+        ds = synth_files.write_dataset_fast(d, n_loci=a.loci, n_barcodes=a.barcodes, depth=a.depth, read_len=150, seed=2)
+    else:
+        ds = {k: os.path.join(d, v) for k, v in dict(fasta="genome.fa", vcf="variants.vcf", bam="reads.bam", barcodes="barcodes.tsv").items()}
+        ds["n_reads"] = a.loci * a.depth
+    gen_s = time.time() - t0
+    cli = os.path.join(ROOT, "vartrix_b200", "bin", "vartrix_b200")
+    runs = []
+    for dev in a.devices:
+        for th in a.threads:
+            o = os.path.join(d, f"out_{dev}_{th}.mtx")
+            for p in (o, os.path.join(d, "ref_matrix.mtx")):
+                if os.path.exists(p):
+                    os.remove(p)
+            cmd = [cli, "-v", ds["vcf"], "-b", ds["bam"], "-f", ds["fasta"], "-c", ds["barcodes"], "-o", o, "-s", a.mode, "--threads", str(th),
+                   "--log-level", "info", "--devices", dev]
+            t0 = time.time()
+            p = subprocess.run(cmd, capture_output=True, text=True, cwd=d)
+            wall = time.time() - t0
+            err = p.stderr
+            def grab(pat, cast=float):
+                m = re.search(pat, err)
+                return cast(m.group(1)) if m else None
+            reads = grab(r"Number of alignments evaluated: (\d+)", int)
+            pairs = grab(r"pairs scored on the GPU: (\d+)", int)
+            marks = {k: grab(r"\[(\d+\.\d+) s\] " + re.escape(v)) for k, v in dict(parsed="inputs parsed", staging="staging on", submitted="all shards staged and submitted",
+                                                                                   host="triplets on the host", written="outputs written").items()}
+            st = re.search(r"Staging thread-seconds: total ([\d.]+) = file read ([\d.]+) \+ inflate ([\d.]+) \+ crc32 ([\d.]+) \+ record scan / filters / packing ([\d.]+); (\d+) BGZF blocks, ([\d.]+) MB inflated; copy into pinned arenas ([\d.]+) s \(([\d.]+) MB\)", err)
+            gpu = [dict(device=int(m.group(1)), h2d_ms=float(m.group(2)), prep_ms=float(m.group(3)), sw_ms=float(m.group(4)), post_ms=float(m.group(5)), pairs=int(m.group(6)))
+                   for m in re.finditer(r"GPU (\d+) device ms: h2d ([\d.]+), prep ([\d.]+), Smith-Waterman ([\d.]+), post ([\d.]+) \((\d+) pairs", err)]
+            run = dict(devices=dev, threads=th, rc=p.returncode, wall_s=round(wall, 3), reads_fetched=reads, pairs_scored=pairs, marks_s=marks, gpu=gpu,
+                       mtx_bytes=os.path.getsize(o) if os.path.exists(o) else None)
+            if st and reads:
+                tot, rd, inf, crc, scan = (float(st.group(i)) for i in range(1, 6))
+                run["staging_thread_seconds"] = dict(total=tot, file_read=rd, inflate=inf, crc32=crc, record_scan_filters_packing=scan, bgzf_blocks=int(st.group(6)),
+                                                     inflated_mb=float(st.group(7)), pinned_copy_s=float(st.group(8)), staged_mb=float(st.group(9)))
+                run["reads_per_s"] = dict(
+                    per_staging_thread=round(reads / tot) if tot else None,
+                    inflate_only_per_thread=round(reads / inf) if inf else None,
+                    record_scan_only_per_thread=round(reads / scan) if scan else None,
+                    staging_wall=round(reads / max((marks["submitted"] or 0) - (marks["staging"] or 0), 1e-9)) if marks["submitted"] else None,
+                    file_to_matrix_wall=round(reads / wall),
+                    gpu_kernels=round(reads / (sum(g["prep_ms"] + g["sw_ms"] + g["post_ms"] for g in gpu) / max(len(gpu), 1) * 1e-3)) if gpu else None,
+                    mtx_writer=round(reads / max((marks["written"] or 0) - (marks["host"] or 0), 1e-9)) if marks["written"] else None)
+            if p.returncode != 0:
+                run["stderr_tail"] = err[-600:] + p.stdout[-300:]
+            runs.append(run)
+            print(json.dumps(run)[:400], file=sys.stderr)
+    print(json.dumps(dict(what="vartrix_b200 CLI, file -> matrix, config-3-sized synthetic file set", loci=a.loci, depth=a.depth, barcodes=a.barcodes,
+                          reads_in_bam=ds.get("n_reads"), bam_bytes=os.path.getsize(ds["bam"]), dataset_generation_s=round(gen_s, 1),
+                          host_logical_cpus=os.cpu_count(), cgroup_cpu_quota_cores=quota(), runs=runs), indent=1))
+
+
+if __name__ == "__main__":
+    main()

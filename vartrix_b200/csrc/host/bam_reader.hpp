@@ -7,6 +7,8 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -19,6 +21,13 @@
 #include "inflate_fast.hpp"
 
 namespace vtxhost {
+
+// thread-seconds the staging threads spend per phase (reported by the CLI at --log-level info)
+struct StageClock {
+    std::atomic<uint64_t> read_ns{ 0 }, inflate_ns{ 0 }, crc_ns{ 0 }, blocks{ 0 }, inflated_bytes{ 0 };
+    static uint64_t now() { return uint64_t(std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count()); }
+};
+inline StageClock& stage_clock() { static StageClock c; return c; }
 
 inline uint16_t rd16(const uint8_t* p) { return uint16_t(p[0] | (p[1] << 8)); }
 inline uint32_t rd32(const uint8_t* p) { return uint32_t(p[0]) | (uint32_t(p[1]) << 8) | (uint32_t(p[2]) << 16) | (uint32_t(p[3]) << 24); }
@@ -121,6 +130,8 @@ private:
         Slot* v = &slots_[clock_]; clock_ = (clock_ + 1) % kSlots;      // round robin; the outgoing current block is not needed again
         v->coff = ~0ull;
         if (cur_ == v) cur_ = nullptr;
+        StageClock& clk = stage_clock();
+        const uint64_t t_read = StageClock::now();
         uint8_t hdr[18];
         if (pread(fd_, hdr, 18, off_t(coff)) != 18) return fail(coff, "truncated file (short read of the member header)");
         if (hdr[0] != 31 || hdr[1] != 139 || hdr[2] != 8 || !(hdr[3] & 4)) return fail(coff, "not a BGZF member (bad gzip magic)");
@@ -145,6 +156,7 @@ private:
         if (pread(fd_, cbuf_.data(), clen + 8, off_t(coff + 12 + xlen)) != ssize_t(clen + 8)) return fail(coff, "truncated file (short read of the member body)");
         const uint32_t crc = rd32(cbuf_.data() + clen), isize = rd32(cbuf_.data() + clen + 4);
         if (isize > (1u << 16)) return fail(coff, "ISIZE above 64 KiB");
+        const uint64_t t_inf = StageClock::now();
         if (v->data.size() < (size_t(1) << 16) + kInflateOutPad) v->data.resize((size_t(1) << 16) + kInflateOutPad);
         if (isize && !vtx_inflate_raw(cbuf_.data(), clen, v->data.data(), isize)) {
             // the single-pass decoder refused the member: let zlib have the last word before calling the file corrupt
@@ -153,7 +165,10 @@ private:
             zs_.next_out = v->data.data(); zs_.avail_out = isize;
             if (inflate(&zs_, Z_FINISH) != Z_STREAM_END || zs_.total_out != isize) return fail(coff, "inflate failed (corrupt data)");
         }
+        const uint64_t t_crc = StageClock::now();
         if (check_crc_ && uint32_t(crc32(crc32(0L, Z_NULL, 0), v->data.data(), isize)) != crc) return fail(coff, "CRC32 mismatch (corrupt data)");
+        const uint64_t t_end = StageClock::now();
+        clk.read_ns += t_inf - t_read; clk.inflate_ns += t_crc - t_inf; clk.crc_ns += t_end - t_crc; clk.blocks += 1; clk.inflated_bytes += isize;
         v->coff = coff; v->next = coff + total; v->len = isize;
         cur_ = v; block_pos_ = 0;
         return true;

@@ -386,6 +386,7 @@ int main(int argc, char** argv)
     bool failed = false; std::string fail_msg;
     UmiInterner umis;
     std::vector<std::unique_ptr<StagedShard>> recycled;      // guarded by mu
+    std::atomic<uint64_t> stage_ns{ 0 }, arena_ns{ 0 }, staged_bytes{ 0 };
     auto worker = [&]() {
         Fasta fa; BamFile bam; std::string e;
         if (!fa.open(o.fasta, &e) || !bam.open(o.bam, &e)) { std::lock_guard<std::mutex> g(mu); failed = true; fail_msg = e; cv.notify_all(); return; }
@@ -399,7 +400,10 @@ int main(int argc, char** argv)
             { std::lock_guard<std::mutex> g(mu); if (!recycled.empty()) { sh = std::move(recycled.back()); recycled.pop_back(); } }
             if (!sh) sh = std::make_unique<StagedShard>();
             const size_t lo = k * size_t(o.shard_loci), hi = std::min(recs.size(), lo + size_t(o.shard_loci));
-            if (!stage_loci(recs, lo, hi, fa, bam, sa, umis, sh.get(), &e)) { std::lock_guard<std::mutex> g(mu); failed = true; fail_msg = e; cv.notify_all(); return; }
+            const uint64_t t_stage = StageClock::now();
+            const bool staged_ok = stage_loci(recs, lo, hi, fa, bam, sa, umis, sh.get(), &e);
+            stage_ns += StageClock::now() - t_stage;
+            if (!staged_ok) { std::lock_guard<std::mutex> g(mu); failed = true; fail_msg = e; cv.notify_all(); return; }
             { std::lock_guard<std::mutex> g(mu); ready[k] = std::move(sh); }
             cv.notify_all();
         }
@@ -435,7 +439,9 @@ int main(int argc, char** argv)
             if (k - ln.lo >= 3 && vtx_wait_copies(ln.ctx) != VTX_OK) { ln.err = vtx_last_error(ln.ctx); ln.rc = 1; break; }     // the arena's previous copy must have landed
             if (!ar.ensure(sh->bytes())) { ln.err = "pinned allocation failed"; ln.rc = 1; break; }
             vtx_batch2 b;
+            const uint64_t t_ar = StageClock::now();
             stage_into_arena(*sh, ar, &b);
+            arena_ns += StageClock::now() - t_ar; staged_bytes += sh->bytes();
             if (vtx_submit2(ln.ctx, &b) != VTX_OK) { ln.err = vtx_last_error(ln.ctx); ln.rc = 1; }
             recycle();
         }
@@ -473,6 +479,19 @@ int main(int argc, char** argv)
     if (frc != VTX_OK) { printf("Vartrix error.\nError: %s\n", vtx_last_error(ctx)); fflush(nullptr); _exit(1); }
 
     LOG_INFO("[%.3f s] triplets on the host", now_s());
+    {   // where the time went: thread-seconds of the staging pool, device milliseconds of the last finish
+        const StageClock& c = stage_clock();
+        LOG_INFO("Staging thread-seconds: total %.3f = file read %.3f + inflate %.3f + crc32 %.3f + record scan / filters / packing %.3f; %llu BGZF blocks, %.1f MB inflated; copy into pinned arenas %.3f s (%.1f MB)",
+                 stage_ns.load() * 1e-9, c.read_ns.load() * 1e-9, c.inflate_ns.load() * 1e-9, c.crc_ns.load() * 1e-9,
+                 (double(stage_ns.load()) - double(c.read_ns.load()) - double(c.inflate_ns.load()) - double(c.crc_ns.load())) * 1e-9,
+                 (unsigned long long)c.blocks.load(), c.inflated_bytes.load() * 1e-6, arena_ns.load() * 1e-9, staged_bytes.load() * 1e-6);
+        for (Lane& ln : lanes) {
+            vtx_timing t{};
+            if (vtx_last_timing(ln.ctx, &t) == VTX_OK)
+                LOG_INFO("GPU %d device ms: h2d %.2f, prep %.2f, Smith-Waterman %.2f, post %.2f (%llu pairs, %llu launches)", ln.device, t.h2d_ms, t.prep_ms,
+                         t.sw_ms, t.post_ms, (unsigned long long)t.n_pairs, (unsigned long long)t.total_launches);
+        }
+    }
     // metrics (main.rs:350-379)
     LOG_INFO("Number of alignments evaluated: %llu", (unsigned long long)hm.num_reads);
     LOG_INFO("Number of alignments skipped due to low mapping quality: %llu", (unsigned long long)hm.num_low_mapq);

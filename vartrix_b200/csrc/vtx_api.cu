@@ -4,6 +4,8 @@
 #include "vtx_pipeline.cuh"
 #include "vtx_sw.cuh"
 
+#include <nvtx3/nvToolsExt.h>     // header-only; ranges cost nothing unless a profiler (nsys / ncu --nvtx) is attached
+
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
@@ -17,6 +19,12 @@ using namespace vtx;
 namespace {
 
 thread_local std::string g_create_error;
+
+// NVTX range around a host-side phase of the API (submit: copies / validation / kernel enqueue; finish; gather)
+struct Nvtx {
+    explicit Nvtx(const char* name) { nvtxRangePushA(name); }
+    ~Nvtx() { nvtxRangePop(); }
+};
 constexpr int kBandK = 6, kBandW = 20;       // K, W of banded::Aligner::new (main.rs:33-34, 899)
 
 struct DBuf {
@@ -394,6 +402,7 @@ int process_batch(vtx_ctx* ctx, const DevBatch& b, TimeRec* tr)
         return VTX_OK;
     }
 
+    Nvtx r_prep("vtx: prep kernels (CB lookup, filter, compaction, slots)");
     // ---- K1: CB lookup, filter, compaction --------------------------------------------------------
     BarcodeTable tab{ P<int32_t>(ctx->bc_slot), ctx->bc_cap - 1, P<uint8_t>(ctx->bc_bytes), P<uint32_t>(ctx->bc_off) };
     if (b.read_cb_key) {
@@ -439,12 +448,14 @@ int process_batch(vtx_ctx* ctx, const DevBatch& b, TimeRec* tr)
     CK(cudaGetLastError());
 
     // ---- K2 + K3: Smith-Waterman, call, atomic scatter ----------------------------------------------
+    nvtxRangePop(); nvtxRangePushA("vtx: Smith-Waterman kernels");
     rc = run_sw(ctx, b, uint32_t(nc), use_umi ? P<uint32_t>(ctx->pair_uslot) : P<uint32_t>(ctx->pair_cslot),
                 use_umi ? P<uint32_t>(ctx->ucnt) : P<uint32_t>(ctx->ccnt), pair_scores, &launches, &sw_launches, tr);
     if (rc) return rc;
     CK(cudaEventRecord(tr->ev[EV_SW], st));
 
     // ---- K4 + K5: UMI collapse, mode value, row-major emit ------------------------------------------
+    nvtxRangePop(); nvtxRangePushA("vtx: post kernels (UMI collapse, finalize, emit)");
     if (use_umi) {
         vtx_k_umi_collapse<<<blocks_for(nc, 256), 256, 0, st>>>(uint32_t(nc), n_pairs_ptr, P<uint32_t>(ctx->uslot_cslot),
                                                                 P<uint32_t>(ctx->ucnt), P<uint32_t>(ctx->ccnt));
@@ -537,12 +548,9 @@ int validate_batch(vtx_ctx* ctx, const HostView& b, bool device)
 constexpr int kShapeFast = 3, kShapeSplit = kShapeFast + 3, kNumShapes = 1 << (kShapeSplit + 2);
 uint32_t shape_of(const uint8_t* rh, uint32_t nr, const uint8_t* ah, uint32_t na)
 {
-    auto is_exotic = [](uint8_t b) {
-        return b == '=' || b == 'M' || b == 'R' || b == 'S' || b == 'V' || b == 'W' || b == 'Y' || b == 'H' || b == 'K' || b == 'D' || b == 'B' || b == 'N';
-    };
-    bool exotic = false;
-    for (uint32_t j = 0; j < nr && !exotic; ++j) exotic = is_exotic(rh[j]);
-    for (uint32_t j = 0; j < na && !exotic; ++j) exotic = is_exotic(ah[j]);
+    // The alphabet test of vtx_k_locus_prep ("=MRSVWYHKDBN" bytes send a locus to the generic kernel) is not repeated on
+    // the host -- a byte-wise scan of every window would cost more than the launch it can save: the generic class is
+    // always launched, and bit 0 stays clear.
     const bool same = nr >= uint32_t(kSplitP) && na >= uint32_t(kSplitP) && memcmp(rh, ah, kSplitP) == 0;
     const bool fold = same && std::min(nr, na) > uint32_t(2 * kFoldP) && std::max(nr, na) <= uint32_t(2 * kFoldP + kFoldMaxMid) &&
                       memcmp(rh + nr - kFoldP, ah + na - kFoldP, kFoldP) == 0;
@@ -550,11 +558,11 @@ uint32_t shape_of(const uint8_t* rh, uint32_t nr, const uint8_t* ah, uint32_t na
     uint32_t fast = kNumFastClasses, split = kNumSplitClasses;
     for (int c = kNumFastClasses - 1; c >= 0; --c) if (nmax <= uint32_t(class_max_n(c))) fast = uint32_t(c);
     for (int c = kNumSplitClasses - 1; c >= 0; --c) if (nmax <= uint32_t(split_max_n(c))) split = uint32_t(c);
-    return uint32_t(exotic) | (uint32_t(same) << 1) | (uint32_t(fold) << 2) | (fast << kShapeFast) | (split << kShapeSplit);
+    return (uint32_t(same) << 1) | (uint32_t(fold) << 2) | (fast << kShapeFast) | (split << kShapeSplit);
 }
 uint32_t class_mask_of(const bool* seen, bool allow_split, bool allow_multi, bool allow_fold, uint32_t max_read)
 {
-    uint32_t mask = 0;
+    uint32_t mask = 1u << kSlowClass;          // loci with IUPAC / "=" bytes are only recognised on the device
     for (int i = 0; i < kNumShapes; ++i) {
         if (!seen[i]) continue;
         const bool exotic = i & 1, same = i & 2, fold = i & 4;
@@ -868,6 +876,7 @@ int vtx_set_barcodes(vtx_ctx* ctx, const uint8_t* bytes, const uint32_t* off, ui
 
 int vtx_submit(vtx_ctx* ctx, const vtx_batch* hb)
 {
+    Nvtx nvtx_range("vtx_submit");
     if (!ctx) return VTX_E_INVALID;
     if (!ctx->have_barcodes) return set_err(ctx, VTX_E_STATE, "vtx_set_barcodes must be called before vtx_submit");
     if (!hb) return set_err(ctx, VTX_E_INVALID, "batch is NULL");
@@ -900,7 +909,8 @@ int vtx_submit(vtx_ctx* ctx, const vtx_batch* hb)
     d.read_umi = hb->read_umi_key ? P<uint64_t>(sl->read_umi) : nullptr; d.cand_read = P<uint32_t>(sl->cand_read);
     // 2. ... validate the host arrays meanwhile; nothing has been launched on them yet
     bool shapes[kNumShapes] = {};
-    rc = scan_host_batch(ctx, hv, &d.max_read_len, &d.max_hap_len, true, &d.max_depth, shapes);
+    { Nvtx r_val("vtx: validate host batch (copies in flight)");
+      rc = scan_host_batch(ctx, hv, &d.max_read_len, &d.max_hap_len, true, &d.max_depth, shapes); }
     if (rc) { cudaStreamSynchronize(ctx->copy_stream); --ctx->trec_used; return rc; }
     d.class_mask = host_class_mask(ctx, shapes, d.max_read_len, d.max_hap_len);
     // 3. kernels wait for the copy, and release the slot when done
@@ -968,6 +978,7 @@ int expand_reads(vtx_ctx* ctx, uint32_t nr, const uint16_t* d_len16, const uint3
 
 int vtx_submit2(vtx_ctx* ctx, const vtx_batch2* hb)
 {
+    Nvtx nvtx_range("vtx_submit2");
     if (!ctx) return VTX_E_INVALID;
     if (!ctx->have_barcodes) return set_err(ctx, VTX_E_STATE, "vtx_set_barcodes must be called before vtx_submit2");
     if (!hb) return set_err(ctx, VTX_E_INVALID, "batch is NULL");
@@ -1009,7 +1020,8 @@ int vtx_submit2(vtx_ctx* ctx, const vtx_batch2* hb)
     d.read_umi = hb->read_umi_key ? P<uint64_t>(sl->read_umi) : nullptr;
     d.cand_read = hb->cand_read ? P<uint32_t>(sl->cand_read) : nullptr;
     bool shapes[kNumShapes] = {};
-    rc = scan_host_batch(ctx, hv, &d.max_read_len, &d.max_hap_len, true, &d.max_depth, shapes);
+    { Nvtx r_val("vtx: validate host batch (copies in flight)");
+      rc = scan_host_batch(ctx, hv, &d.max_read_len, &d.max_hap_len, true, &d.max_depth, shapes); }
     if (rc) { cudaStreamSynchronize(ctx->copy_stream); --ctx->trec_used; return rc; }
     d.class_mask = host_class_mask(ctx, shapes, d.max_read_len, d.max_hap_len);
     CK(cudaStreamWaitEvent(ctx->stream, sl->copy_done, 0));
@@ -1088,6 +1100,7 @@ static int finish_scalars(vtx_ctx* ctx)
 
 int vtx_finish_device(vtx_ctx* ctx, vtx_result* out)
 {
+    Nvtx nvtx_range("vtx_finish_device");
     if (!ctx || !out) return VTX_E_INVALID;
     int rc = finish_scalars(ctx);
     if (rc) return rc;
@@ -1105,18 +1118,19 @@ static int fetch_to(vtx_ctx* ctx, const vtx_result* dev, vtx_result* out, void**
 {
     const size_t n = dev->n;
     const size_t esz[7] = { 4, 4, 4, 4, 4, 8, 8 };
+    const bool values_only = (ctx->cfg.flags & VTX_F_VALUES_ONLY) != 0;
+    bool want[7] = { true, true, !values_only, !values_only, !values_only, true, !values_only || ctx->cfg.mode == VTX_MODE_COVERAGE };
     if (n > *hcap) {
         const size_t ncap = n + n / 4 + 1024;
         for (int i = 0; i < 7; ++i) {
             if (hbuf[i]) { cudaFreeHost(hbuf[i]); hbuf[i] = nullptr; }
+            if (!want[i]) continue;
             cudaError_t e = cudaHostAlloc(&hbuf[i], ncap * esz[i], cudaHostAllocDefault);
             if (e != cudaSuccess) { *hcap = 0; return set_err(ctx, VTX_E_NOMEM, "pinned result alloc failed: %s", cudaGetErrorString(e)); }
         }
         *hcap = ncap;
     }
     const void* src[7] = { dev->row, dev->col, dev->ref_cnt, dev->alt_cnt, dev->unk_cnt, dev->val, dev->val2 };
-    const bool values_only = (ctx->cfg.flags & VTX_F_VALUES_ONLY) != 0;
-    bool want[7] = { true, true, !values_only, !values_only, !values_only, true, !values_only || ctx->cfg.mode == VTX_MODE_COVERAGE };
     if (n) {
         for (int i = 0; i < 7; ++i)
             if (want[i] && src[i]) CK(cudaMemcpyAsync(hbuf[i], src[i], n * esz[i], cudaMemcpyDeviceToHost, ctx->stream));
@@ -1133,6 +1147,7 @@ static int fetch_to(vtx_ctx* ctx, const vtx_result* dev, vtx_result* out, void**
 
 int vtx_fetch(vtx_ctx* ctx, const vtx_result* device_result, vtx_result* out)
 {
+    Nvtx nvtx_range("vtx_fetch");
     if (!ctx || !device_result || !out) return VTX_E_INVALID;
     CK(cudaSetDevice(ctx->device));
     // gathered results get their own host buffers so that a local and a gathered copy can coexist
@@ -1147,8 +1162,11 @@ static int ensure_host_results(vtx_ctx* ctx, size_t n)
     if (n <= ctx->h_res_cap) return VTX_OK;
     const size_t esz[7] = { 4, 4, 4, 4, 4, 8, 8 };
     const size_t ncap = n + n / 4 + 1024;
+    const bool values_only = (ctx->cfg.flags & VTX_F_VALUES_ONLY) != 0;       // then the three count arrays never leave the device
+    const bool want[7] = { true, true, !values_only, !values_only, !values_only, true, !values_only || ctx->cfg.mode == VTX_MODE_COVERAGE };
     for (int i = 0; i < 7; ++i) {
         if (ctx->h_res[i]) { cudaFreeHost(ctx->h_res[i]); ctx->h_res[i] = nullptr; }
+        if (!want[i]) continue;
         cudaError_t e = cudaHostAlloc(&ctx->h_res[i], ncap * esz[i], cudaHostAllocDefault);
         if (e != cudaSuccess) { ctx->h_res_cap = 0; return set_err(ctx, VTX_E_NOMEM, "pinned result alloc failed: %s", cudaGetErrorString(e)); }
     }
@@ -1158,6 +1176,7 @@ static int ensure_host_results(vtx_ctx* ctx, size_t n)
 
 int vtx_finish(vtx_ctx* ctx, vtx_result* out)
 {
+    Nvtx nvtx_range("vtx_finish");
     if (!ctx || !out) return VTX_E_INVALID;
     CK(cudaSetDevice(ctx->device));
     // Stream the triplets out submit by submit: the kernels of later submits are usually still running when the
@@ -1240,6 +1259,7 @@ int vtx_last_timing(vtx_ctx* ctx, vtx_timing* t)
 int vtx_score_pairs(vtx_ctx* ctx, const vtx_batch* hb, uint64_t n_pairs, const uint32_t* pair_read,
                     const uint32_t* pair_locus, int16_t* ref_score, int16_t* alt_score)
 {
+    Nvtx nvtx_range("vtx_score_pairs");
     if (!ctx) return VTX_E_INVALID;
     if (!hb) return set_err(ctx, VTX_E_INVALID, "batch is NULL");
     const HostView hv = view_of(hb);
@@ -1386,6 +1406,7 @@ int vtx_comm_init(vtx_ctx* ctx, const uint8_t id[128], int32_t rank, int32_t n_r
 
 int vtx_gather_start(vtx_ctx* ctx, int32_t root)
 {
+    Nvtx nvtx_range("vtx_gather_start");
     if (!ctx) return VTX_E_INVALID;
     if (!ctx->finished) return set_err(ctx, VTX_E_STATE, "vtx_gather must follow vtx_finish / vtx_finish_device");
     if (ctx->gather_pending) return set_err(ctx, VTX_E_STATE, "a gather is already in flight: call vtx_gather_wait first");
@@ -1475,6 +1496,7 @@ int vtx_gather_start(vtx_ctx* ctx, int32_t root)
 
 int vtx_gather_wait(vtx_ctx* ctx, vtx_result* out)
 {
+    Nvtx nvtx_range("vtx_gather_wait");
     if (!ctx || !out) return VTX_E_INVALID;
     if (!ctx->gather_pending) return set_err(ctx, VTX_E_STATE, "no gather in flight");
     CK(cudaSetDevice(ctx->device));

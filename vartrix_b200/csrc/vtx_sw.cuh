@@ -45,6 +45,16 @@ constexpr uint32_t kBIAS2 = pack2(kBias, kBias);                    // biased 0 
 constexpr uint32_t kGOE2 = pack2(kBias + kGoe, kBias + kGoe);       // biased (0 + gap): H = 0 seen through H + go + ge
 constexpr uint32_t kNEG2 = pack2(0, 0);                             // biased -16384 ("minus infinity")
 constexpr uint32_t kGoeAdd = (uint32_t(uint16_t(int16_t(kGoe - 1))) << 16) | uint32_t(uint16_t(int16_t(kGoe)));   // + (gap, gap) incl. the carry
+// Cell update.  1 (default): the diagonal add rides inside VIADDMNMX, x = max(diag + s, F), and the floor of local
+// alignment joins the H maximum, h = VIMNMX3(x, E, 0).  0: round-1 form, tf = VIMNMX3(diag + s, F, 0), h = VIMNMX(tf, E).
+// Measured on B200 (profiles/r02_dpx_microbench.txt): 3-input DPX instructions hold the ALU pipe for 2 cycles, the 2-input
+// VIMNMX for 1, and a plain add next to a DPX instruction is free -- so form 1 costs 12 more ALU cycles per main-pass step
+// of the folded kernel (126 instead of 114) but 5 fewer issue slots (117 instead of 122), and the kernel is bound by both
+// (ncu: issue slots 81 % busy, ALU pipe 76 %).  Form 1 measured +1.9 %, with the row loop unrolled twice +3.7 %
+// (profiles/r02_fold_variants.txt).
+#ifndef VTX_SW_FUSE
+#define VTX_SW_FUSE 1
+#endif
 // The remaining plain add of a cell, H + gap.  ptxas places a plain `x + c` on the ALU pipe (VIADD), which the DPX
 // instructions already saturate; written as x * one + c with a run-time `one` it is an IMAD on the FMA pipe instead.
 // VTX_SW_HADD: 0 = plain add everywhere, 1 = IMAD everywhere, 2 = IMAD on even columns (splits the adds between the pipes).

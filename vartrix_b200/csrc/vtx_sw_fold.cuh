@@ -47,7 +47,7 @@ constexpr int kFoldCodeStride = kFoldMaxRead + 16;   // row codes per read and d
 // 256 x 2 on the config-3 shape; merging the profile rows with one IADD3 instead of IMAD + add, or unrolling the
 // row loop, does not pay at that occupancy (profiles/r01_fold_variants.txt)
 #ifndef VTX_FOLD_UNROLL
-#define VTX_FOLD_UNROLL 1
+#define VTX_FOLD_UNROLL 2
 #endif
 // 1: the reverse profile is stored in the HIGH half, so the (forward | reverse) substitution word is a plain add of the two
 // profile words (eligible for IMAD.IADD / VIADD) instead of a full IMAD b * 65536 + a (half-rate FMA-heavy pipe)
@@ -59,6 +59,10 @@ constexpr int kFoldCodeStride = kFoldMaxRead + 16;   // row codes per read and d
 #endif
 constexpr int kFoldThreads = VTX_FOLD_THREADS;
 constexpr int kFoldUnroll = VTX_FOLD_UNROLL;         // row-loop unrolling of the main pass
+#ifndef VTX_FOLD_MID_UNROLL
+#define VTX_FOLD_MID_UNROLL 1
+#endif
+constexpr int kFoldMidUnroll = VTX_FOLD_MID_UNROLL;  // column-loop unrolling of the allele pass
 
 __host__ __device__ constexpr size_t fold_warp_bytes()
 {
@@ -264,6 +268,7 @@ __global__ void __launch_bounds__(kFoldThreads, 2) vtx_k_sw_fold(const SwArgs a)
                 uint32_t hup_last = kGOE2, f_last = kNEG2;
                 const uint8_t* tab = reinterpret_cast<const uint8_t*>(midtab) - 32 * g;
                 const int steps = lmax + 7;
+#pragma unroll kFoldMidUnroll
                 for (int s = 0; s < steps; ++s) {
                     uint32_t hup = __shfl_up_sync(0xffffffffu, hup_last, 1, 8);
                     uint32_t fup = __shfl_up_sync(0xffffffffu, f_last, 1, 8);

@@ -248,3 +248,164 @@ def write_dataset(out_dir: str, n_loci: int = 200, n_barcodes: int = 50, depth: 
     bw.close()
     paths.update(n_loci=n_loci, n_barcodes=n_barcodes, n_reads=len(reads))
     return paths
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Bulk writer for the BASELINE-sized file sets (config 3: 100 k SNV loci x 50 reads): every record has the same
+# length, so the BAM body, the BGZF blocks and the BAI are built with numpy instead of one Python call per read.
+# ---------------------------------------------------------------------------------------------------------------
+def _reg2bin_vec(beg, end):
+    end = end - 1
+    out = np.zeros(len(beg), np.int64)
+    done = np.zeros(len(beg), bool)
+    for shift, base in ((14, 4681), (17, 585), (20, 73), (23, 9), (26, 1)):
+        hit = ~done & ((beg >> shift) == (end >> shift))
+        out[hit] = base + (beg[hit] >> shift)
+        done |= hit
+    return out
+
+
+def write_dataset_fast(out_dir: str, n_loci: int = 100_000, n_barcodes: int = 50_000, depth: int = 50, read_len: int = 150, seed: int = 2,
+                       umi: bool = False, spacing: int = 1200, unlisted_frac: float = 0.05, err: float = 0.005, level: int = 1, line_width: int = 60):
+    """SNV loci `spacing` apart on one contig, `depth` reads of `read_len` bases per locus (start uniform over the
+    positions that cover the variant, allele ref/alt 50/50, `err` substitution errors, CIGAR <read_len>M, mapq 60), cell tags
+    16-mer + "-1" with `unlisted_frac` of the reads carrying an unlisted one.  -> dict of paths like write_dataset."""
+    os.makedirs(out_dir, exist_ok=True)
+    rng = np.random.default_rng(seed)
+    paths = {k: os.path.join(out_dir, v) for k, v in dict(fasta="genome.fa", vcf="variants.vcf", bam="reads.bam", barcodes="barcodes.tsv").items()}
+    L = 2000 + spacing * n_loci
+    genome = rng.integers(0, 4, size=L, dtype=np.uint8)
+    with open(paths["fasta"], "wb") as fa, open(paths["fasta"] + ".fai", "w") as fai:
+        fa.write(b">chr1\n")
+        off = fa.tell()
+        seq = _ASCII[genome]
+        full = L // line_width * line_width
+        body = np.empty((full // line_width, line_width + 1), np.uint8)
+        body[:, :line_width] = seq[:full].reshape(-1, line_width); body[:, line_width] = 10
+        fa.write(body.tobytes())
+        if full < L:
+            fa.write(seq[full:].tobytes() + b"\n")
+        fai.write(f"chr1\t{L}\t{off}\t{line_width}\t{line_width + 1}\n")
+    # barcodes: 16 random bases + "-1"; listed ones go to the file
+    n_unl = max(16, n_barcodes // 20)
+    vals = rng.permutation(np.unique(rng.integers(0, 2**32, size=int((n_barcodes + n_unl) * 1.3) + 64, dtype=np.uint64)))[: n_barcodes + n_unl]
+    bases = ((vals[:, None] >> (np.arange(15, -1, -1, dtype=np.uint64) * 2)[None, :]) & 3).astype(np.uint8)
+    tags = np.empty((len(vals), 18), np.uint8)
+    tags[:, :16] = _ASCII[bases]; tags[:, 16] = ord("-"); tags[:, 17] = ord("1")
+    with open(paths["barcodes"], "wb") as f:
+        f.write(b"\n".join(bytes(t) for t in tags[:n_barcodes]) + b"\n")
+    # variants
+    pos = 1000 + spacing * np.arange(n_loci, dtype=np.int64) + rng.integers(0, 100, size=n_loci)
+    refb = genome[pos]
+    altb = (refb + rng.integers(1, 4, size=n_loci, dtype=np.uint8)) % 4
+    with open(paths["vcf"], "w") as f:
+        f.write(f"##fileformat=VCFv4.2\n##contig=<ID=chr1,length={L}>\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\n")
+        f.write("".join(f"chr1\t{p + 1}\t.\t{'ACGT'[r]}\t{'ACGT'[a]}\t.\t.\t.\n" for p, r, a in zip(pos.tolist(), refb.tolist(), altb.tolist())))
+    # BAM: fixed-length records
+    name_len = 9                                         # "r" + 7 digits + NUL  (wraps above 10 M reads: names only need to exist)
+    aux_len = 22 + (14 if umi else 0)
+    nb = (read_len + 1) // 2
+    body_len = 32 + name_len + 4 + nb + read_len + aux_len
+    rec_len = 4 + body_len
+    header_text = f"@HD\tVN:1.6\tSO:coordinate\n@SQ\tSN:chr1\tLN:{L}\n"
+    hdr = b"BAM\x01" + struct.pack("<i", len(header_text)) + header_text.encode() + struct.pack("<i", 1) + struct.pack("<i", 5) + b"chr1\x00" + struct.pack("<i", L)
+    per_block = max(1, 0xFF00 // rec_len)
+    f = open(paths["bam"], "wb")
+
+    def put_block(raw: bytes) -> int:
+        co = zlib.compressobj(level, zlib.DEFLATED, -15)
+        comp = co.compress(raw) + co.flush()
+        start = f.tell()
+        f.write(struct.pack("<BBBBIBBHBBHH", 31, 139, 8, 4, 0, 0, 255, 6, 66, 67, 2, len(comp) + 25))
+        f.write(comp)
+        f.write(struct.pack("<II", zlib.crc32(raw) & 0xFFFFFFFF, len(raw)))
+        return start
+
+    put_block(hdr)
+    rec_pos, rec_voff = [], []
+    read_no = 0
+    carry = np.zeros((0, rec_len), np.uint8); carry_pos = np.zeros(0, np.int64)
+    chunk = 4096
+    for lo in range(0, n_loci, chunk):
+        hi = min(n_loci, lo + chunk); n = (hi - lo) * depth
+        loc = np.repeat(np.arange(lo, hi), depth)
+        start = pos[loc] - rng.integers(0, read_len, size=n)
+        order = np.lexsort((start, loc)); loc, start = loc[order], start[order]
+        idx = start[:, None] + np.arange(read_len, dtype=np.int64)[None, :]
+        seq = genome[idx]
+        is_alt = rng.random(n) < 0.5
+        col = (pos[loc] - start)
+        rows = np.nonzero(is_alt)[0]
+        seq[rows, col[rows]] = altb[loc[rows]]
+        n_err = int(rng.binomial(n * read_len, err))
+        if n_err:
+            ep = rng.integers(0, n * read_len, size=n_err)
+            flat = seq.reshape(-1); flat[ep] = (flat[ep] + rng.integers(1, 4, size=n_err, dtype=np.uint8)) % 4
+        nibv = np.array([1, 2, 4, 8], np.uint8)[seq]
+        if read_len & 1:
+            nibv = np.concatenate([nibv, np.zeros((n, 1), np.uint8)], axis=1)
+        rec = np.zeros((n, rec_len), np.uint8)
+        def put32(c, v): rec[:, c:c + 4] = np.ascontiguousarray(v, dtype="<i4").view(np.uint8).reshape(-1, 4)
+        def put16(c, v): rec[:, c:c + 2] = np.ascontiguousarray(v, dtype="<u2").view(np.uint8).reshape(-1, 2)
+        put32(0, np.full(n, body_len)); put32(4, np.zeros(n)); put32(8, start)
+        rec[:, 12] = name_len; rec[:, 13] = 60
+        put16(14, _reg2bin_vec(start, start + read_len)); put16(16, np.ones(n)); put16(18, np.zeros(n))
+        put32(20, np.full(n, read_len)); put32(24, np.full(n, -1)); put32(28, np.full(n, -1)); put32(32, np.zeros(n))
+        ids = (read_no + np.arange(n)) % 10_000_000
+        rec[:, 36] = ord("r")
+        for d in range(7):
+            rec[:, 37 + d] = 48 + (ids // 10 ** (6 - d)) % 10
+        c = 36 + name_len
+        put32(c, np.full(n, (read_len << 4) | 0)); c += 4
+        rec[:, c:c + nb] = (nibv[:, 0::2] << 4) | nibv[:, 1::2]; c += nb
+        rec[:, c:c + read_len] = 0xFF; c += read_len
+        listed = rng.random(n) >= unlisted_frac
+        cbi = np.where(listed, rng.integers(0, n_barcodes, size=n), n_barcodes + rng.integers(0, n_unl, size=n))
+        rec[:, c] = ord("C"); rec[:, c + 1] = ord("B"); rec[:, c + 2] = ord("Z"); rec[:, c + 3:c + 21] = tags[cbi]; c += 22
+        if umi:
+            ub = _ASCII[rng.integers(0, 4, size=(hi - lo, max(1, depth // 3), 10), dtype=np.uint8)]
+            pick = rng.integers(0, ub.shape[1], size=n)
+            rec[:, c] = ord("U"); rec[:, c + 1] = ord("B"); rec[:, c + 2] = ord("Z"); rec[:, c + 3:c + 13] = ub[loc - lo, pick]
+        read_no += n
+        rec = np.concatenate([carry, rec]); spos = np.concatenate([carry_pos, start])
+        n_full = len(rec) // per_block * per_block if hi < n_loci else len(rec)
+        for b0 in range(0, n_full, per_block):
+            blk = rec[b0:b0 + per_block]
+            co = put_block(blk.tobytes())
+            rec_pos.append(spos[b0:b0 + len(blk)])
+            rec_voff.append((np.int64(co) << 16) + np.arange(len(blk), dtype=np.int64) * rec_len)
+        carry, carry_pos = rec[n_full:], spos[n_full:]
+    end_voff = np.int64(f.tell()) << 16
+    f.write(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))
+    f.close()
+    rpos = np.concatenate(rec_pos); voff = np.concatenate(rec_voff)
+    vend = np.concatenate([voff[1:], [end_voff]])
+    bins = _reg2bin_vec(rpos, rpos + read_len)
+    # chunks: maximal runs of consecutive records with the same bin
+    run_start = np.nonzero(np.concatenate([[True], bins[1:] != bins[:-1]]))[0]
+    run_end = np.concatenate([run_start[1:], [len(bins)]]) - 1
+    run_bin, c0, c1 = bins[run_start], voff[run_start], vend[run_end]
+    order = np.argsort(run_bin, kind="stable")
+    with open(paths["bam"] + ".bai", "wb") as b:
+        b.write(b"BAI\x01" + struct.pack("<i", 1))
+        ub_, first = np.unique(run_bin[order], return_index=True)
+        b.write(struct.pack("<i", len(ub_)))
+        bounds = np.concatenate([first, [len(order)]])
+        for k, bin_id in enumerate(ub_.tolist()):
+            sel = order[bounds[k]:bounds[k + 1]]
+            b.write(struct.pack("<Ii", bin_id, len(sel)))
+            b.write(np.stack([c0[sel], c1[sel]], axis=1).astype("<u8").tobytes())
+        # linear index: smallest record offset per 16 kb window the record overlaps
+        w0, w1 = rpos >> 14, (rpos + read_len - 1) >> 14
+        n_intv = int(w1.max()) + 1
+        lin = np.full(n_intv, np.iinfo(np.int64).max, np.int64)
+        np.minimum.at(lin, w0, voff); np.minimum.at(lin, w1, voff)
+        last = 0
+        out = np.zeros(n_intv, np.int64)
+        filled = lin != np.iinfo(np.int64).max
+        for w in range(n_intv):                      # htslib fills empty windows with the previous offset
+            if filled[w]: last = lin[w]
+            out[w] = last
+        b.write(struct.pack("<i", n_intv)); b.write(out.astype("<u8").tobytes())
+    paths.update(n_loci=n_loci, n_barcodes=n_barcodes, n_reads=int(n_loci) * depth)
+    return paths
