@@ -43,9 +43,9 @@ constexpr int kFoldMaxMid = 40;        // allele columns: n <= 2 * 96 + 40 = 232
 // (152 rows x 8 bytes put reads 0/2 and 1/3 on the same banks: a 2-way conflict on every boundary store and load)
 constexpr int kFoldRows = kFoldMaxRead + 4;
 constexpr int kFoldCodeStride = kFoldMaxRead + 16;   // row codes per read and direction (8 sentinels either side)
-// 320 threads x 2 CTAs = 20 warps/SM (96 registers, a few spills in the tile prologue only): 9.32 ms vs 9.82 ms at
-// 256 x 2 on the config-3 shape; merging the profile rows with one IADD3 instead of IMAD + add, or unrolling the
-// row loop, does not pay at that occupancy (profiles/r01_fold_variants.txt)
+// 288 threads x 2 CTAs = 18 warps/SM at 96 registers (a few spills in the tile prologue only).  Round 1 (unfused cell, no
+// unrolling): 320 x 2 beat 256 x 2 by 5 %; with the fused cell and the row loop unrolled twice 288 x 2 is the best of
+// 256 / 288 / 320 by ~1 % (profiles/r02_fold_variants.txt): the kernel is bound by issue slots and the ALU pipe, not by latency.
 #ifndef VTX_FOLD_UNROLL
 #define VTX_FOLD_UNROLL 2
 #endif
@@ -55,7 +55,7 @@ constexpr int kFoldCodeStride = kFoldMaxRead + 16;   // row codes per read and d
 #define VTX_FOLD_PRESHIFT 0
 #endif
 #ifndef VTX_FOLD_THREADS
-#define VTX_FOLD_THREADS 320
+#define VTX_FOLD_THREADS 288
 #endif
 constexpr int kFoldThreads = VTX_FOLD_THREADS;
 constexpr int kFoldUnroll = VTX_FOLD_UNROLL;         // row-loop unrolling of the main pass
