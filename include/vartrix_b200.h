@@ -67,7 +67,12 @@ typedef struct vtx_config {
     /* The reference aligns with bio 0.30.0's banded aligner, Aligner::new(GAP_OPEN, GAP_EXTEND, score, K, W) (main.rs:27-38,
      * 899).  VTX_BAND_FULL scores the whole matrix: the exact upper bound of every band, equal to the banded score
      * whenever the optimal path stays inside the band, and what reproduces the reference's 12 golden matrices.
-     * band_k / band_w: 0 = the reference's constants (6 / 20); they only matter for VTX_BAND_MODEL. */
+     * band_k / band_w: 0 = the reference's constants (6 / 20); they only matter for VTX_BAND_MODEL (K 1..8).
+     * VTX_BAND_MODEL scores every pair inside the k-mer-chain band of SURVEY Appendix B ("model B": exact k-mer hits, best
+     * chain, +-W around the chain, lazy ends; no hit -> full matrix) -- a restatement of the crate's behaviour from its
+     * documentation, NOT a port of its source (unavailable here): consistent with every golden of the reference, otherwise
+     * unverified.  It is a slow path (one warp per alignment) for users who prefer the heuristic band in low-complexity
+     * sequence; tools/band_exposure.py measures where the two differ. */
     int32_t  band_k;        /* K, main.rs:33 */
     int32_t  band_w;        /* W, main.rs:34 */
     int32_t  band_mode;     /* VTX_BAND_* */

@@ -3,6 +3,7 @@
 #include "../../include/vartrix_b200.h"
 #include "vtx_pipeline.cuh"
 #include "vtx_sw.cuh"
+#include "vtx_sw_band.cuh"
 
 #include <nvtx3/nvToolsExt.h>     // header-only; ranges cost nothing unless a profiler (nsys / ncu --nvtx) is attached
 
@@ -66,6 +67,7 @@ struct vtx_ctx {
     DBuf bck_key, bck_idx;            // the barcodes that have a vtx_pack_cb code, keyed by it
     uint32_t bck_cap = 0;
     DBuf x_read_off, x_read_len, x_units, x_off4;      // slim layout expanded to the internal read arrays
+    DBuf band_scratch;                                  // VTX_BAND_MODEL work buffers, one slice per resident warp
     uint32_t bc_cap = 0, n_barcodes = 0;
     bool have_barcodes = false;
 
@@ -290,6 +292,31 @@ int run_sw(vtx_ctx* ctx, const DevBatch& b, uint32_t n_pairs_ub, const uint32_t*
     a.max_hap = b.max_hap_len;
 
     uint64_t before = *launches;
+    if (ctx->cfg.band_mode == VTX_BAND_MODEL) {
+        // optional slow path: every pair scored inside the k-mer-chain band model, one warp per pair (vtx_sw_band.cuh)
+        BandArgs ba{};
+        ba.sw = a; ba.n_pairs_ub = n_pairs_ub; ba.k = ctx->cfg.band_k; ba.w = ctx->cfg.band_w;
+        ba.max_read = std::max<uint32_t>(b.max_read_len, 8); ba.max_hap = std::max<uint32_t>(b.max_hap_len, 8);
+        const uint64_t all_hits = uint64_t(ba.max_read) * ba.max_hap;          // every position pair can be a hit at most
+        ba.hit_cap = uint32_t(std::min<uint64_t>(all_hits, uint64_t(1) << 20));
+        ba.hit_cap = std::min<uint32_t>(ba.hit_cap, 65535u * 16u);
+        const size_t wb = band_warp_bytes(ba.max_read, ba.max_hap, ba.hit_cap);
+        size_t warps = size_t(ctx->n_sm) * 16;
+        const size_t budget = size_t(4) << 30;                                  // scratch budget: 4 GiB
+        if (warps * wb > budget) warps = std::max<size_t>(size_t(ctx->n_sm), budget / wb);
+        warps = std::max<size_t>(warps & ~size_t(3), 4);
+        ENS(ctx->band_scratch, warps * wb);
+        ba.scratch = P<uint8_t>(ctx->band_scratch);
+        if (ba.max_hap >= 65536u || ba.max_read >= 65536u) return set_err(ctx, VTX_E_UNSUPPORTED, "band model: reads and windows must be shorter than 65536");
+        ba.overflow = P<unsigned long long>(ctx->d_metrics) + 5;
+        ba.bounds_violated = P<unsigned long long>(ctx->d_metrics) + 4;
+        ba.cursor = P<uint32_t>(ctx->tile_counters);
+        vtx_k_sw_band<<<unsigned(warps / (kBandThreads / 32)), kBandThreads, 0, ctx->stream>>>(ba);
+        CK(cudaGetLastError());
+        ++*launches;
+        *sw_launches += *launches - before;
+        return VTX_OK;
+    }
     // b.class_mask: for host batches the classes the windows of this shard can select (scan_host_batch); all for device batches
     for (int c = 0; c < kNumFastClasses; ++c) {
         // a class whose narrowest window is wider than every window of this batch has no tiles: skip the empty launch
@@ -373,7 +400,7 @@ int process_batch(vtx_ctx* ctx, const DevBatch& b, TimeRec* tr)
 
     if (ctx->finished) {      // fresh result set
         CK(cudaMemsetAsync(ctx->d_res_n.p, 0, 8, st));
-        CK(cudaMemsetAsync(ctx->d_metrics.p, 0, 40, st));
+        CK(cudaMemsetAsync(ctx->d_metrics.p, 0, 48, st));
         ctx->res_ub = 0;
         ctx->finished = false;
     }
@@ -736,11 +763,8 @@ int vtx_create(const vtx_config* cfg, vtx_ctx** out)
                        kMatch, kMismatch, kGapOpen, kGapExtend);
     if (cfg->mode < 0 || cfg->mode > 2) return set_err(nullptr, VTX_E_INVALID, "unknown mode %d", cfg->mode);
     if (cfg->band_mode != VTX_BAND_FULL && cfg->band_mode != VTX_BAND_MODEL) return set_err(nullptr, VTX_E_INVALID, "unknown band_mode %d", cfg->band_mode);
-    if ((cfg->band_k != 0 && cfg->band_k != kBandK) || (cfg->band_w != 0 && cfg->band_w != kBandW))
-        return set_err(nullptr, VTX_E_UNSUPPORTED, "band constants are compiled in: K %d W %d (main.rs:33-34)", kBandK, kBandW);
-    if (cfg->band_mode == VTX_BAND_MODEL)
-        return set_err(nullptr, VTX_E_UNSUPPORTED, "band_mode VTX_BAND_MODEL is not available on the GPU: the k-mer-chain band of bio 0.30.0 is only "
-                                                   "modelled in the CPU oracle (vtxo_sw_band_model); the engine scores the full matrix");
+    if (cfg->band_k < 0 || cfg->band_k > 8 || cfg->band_w < 0 || cfg->band_w > 4096)
+        return set_err(nullptr, VTX_E_UNSUPPORTED, "band constants out of range: K %d (1..8; 0 = %d), W %d (0 = %d; main.rs:33-34)", cfg->band_k, kBandK, cfg->band_w, kBandW);
     int n_dev = 0;
     cudaError_t e = cudaGetDeviceCount(&n_dev);
     if (e != cudaSuccess || n_dev == 0)
@@ -749,6 +773,8 @@ int vtx_create(const vtx_config* cfg, vtx_ctx** out)
     CK(cudaSetDevice(cfg->device));
     ctx = new vtx_ctx();
     ctx->cfg = *cfg; ctx->device = cfg->device;
+    if (ctx->cfg.band_k == 0) ctx->cfg.band_k = kBandK;
+    if (ctx->cfg.band_w == 0) ctx->cfg.band_w = kBandW;
     cudaDeviceProp prop{};
     cudaError_t pe = cudaGetDeviceProperties(&prop, cfg->device);
     if (pe != cudaSuccess) { g_create_error = cudaGetErrorString(pe); delete ctx; return VTX_E_CUDA; }
@@ -799,7 +825,7 @@ void vtx_destroy(vtx_ctx* ctx)
         if (sl.free_ev) cudaEventDestroy(sl.free_ev);
     }
     DBuf* all[] = { &ctx->bc_slot, &ctx->bc_bytes, &ctx->bc_off, &ctx->bck_key, &ctx->bck_idx, &ctx->x_read_off, &ctx->x_read_len,
-                    &ctx->x_units, &ctx->x_off4, &ctx->read_col,
+                    &ctx->x_units, &ctx->x_off4, &ctx->band_scratch, &ctx->read_col,
                     &ctx->keep, &ctx->pidx, &ctx->scan_sums, &ctx->pair_read, &ctx->pair_col, &ctx->pair_umi, &ctx->pair_locus,
                     &ctx->pair_start, &ctx->tcount, &ctx->tstart, &ctx->pair_first, &ctx->pair_cslot, &ctx->pair_uslot, &ctx->cslot_col,
                     &ctx->cslot_locus, &ctx->uslot_cslot, &ctx->ccnt, &ctx->ucnt, &ctx->keep2, &ctx->oidx, &ctx->tile_counters,
@@ -1083,15 +1109,18 @@ static int finish_scalars(vtx_ctx* ctx)
     CK(cudaSetDevice(ctx->device));
     uint64_t* hs = static_cast<uint64_t*>(ctx->h_scalars);
     CK(cudaMemcpyAsync(hs, ctx->d_res_n.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(hs + 1, ctx->d_metrics.p, 40, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(hs + 1, ctx->d_metrics.p, 48, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    const uint64_t violated = ctx->finished ? 0 : hs[5];
+    const uint64_t violated = ctx->finished ? 0 : hs[5], band_overflow = ctx->finished ? 0 : hs[6];
     ctx->last_n = ctx->finished ? 0 : hs[0];
     ctx->last_metrics.num_not_cell_bc = ctx->finished ? 0 : hs[1];
     ctx->last_metrics.num_non_umi = ctx->finished ? 0 : hs[2];
     ctx->last_metrics.num_scored = ctx->finished ? 0 : hs[3];
     ctx->t_pairs = ctx->last_metrics.num_scored;
     ctx->finished = true;
+    if (band_overflow)
+        return set_err(ctx, VTX_E_UNSUPPORTED, "band model: %llu alignments had more k-mer hits than the work buffers hold (reads x windows too large); "
+                                               "they were scored with the full matrix", (unsigned long long)band_overflow);
     if (violated)
         return set_err(ctx, VTX_E_INVALID, "%llu loci of a device batch exceeded the bounds given to vtx_submit_device(_ex) (longest read / widest "
                                            "haplotype window); they were skipped, the result is incomplete", (unsigned long long)violated);
