@@ -244,6 +244,26 @@ int         vtx_score_pairs(vtx_ctx* ctx, const vtx_batch* host_batch, uint64_t 
  * Returns VTX_NO_UMI if the string does not fit; the caller then interns it as (1 << 61) | id. */
 uint64_t    vtx_pack_umi(const uint8_t* s, uint32_t len);
 
+/* ---- BGZF members inflated on the device (replaces htslib's bgzf_read_block -> inflate behind
+ * main.rs:822-829 for a host that only seeks and reads the compressed file) ------------------------------------------
+ * `comp` holds the raw DEFLATE payloads of n_blocks BGZF members (the bytes between the gzip header incl. its extra field
+ * and the 8-byte trailer), each starting at a multiple of 4 with at least 8 readable bytes behind it; `blocks[i]` says where
+ * member i's payload is, its ISIZE (<= 65536) and CRC-32 from the trailer, and where in `out` its bytes go.  One warp per
+ * member; VTX_BGZF_CHECK_CRC verifies the CRC-32 on the device as well.  Host pointers; synchronous.  status[i] = 0 or a
+ * decoder error code (1 bad stream, 2 bad code table, 3 input overrun, 4 size mismatch, 5 bad stored block, 6 bad distance,
+ * 7 CRC mismatch); returns VTX_E_INVALID if any member failed (the other members are still delivered).  Needs no barcodes. */
+typedef struct vtx_bgzf_block {
+    uint64_t in_off;
+    uint32_t in_len;
+    uint32_t out_len;
+    uint64_t out_off;
+    uint32_t crc32;
+    uint32_t reserved;
+} vtx_bgzf_block;
+#define VTX_BGZF_CHECK_CRC 1u
+int         vtx_bgzf_inflate(vtx_ctx* ctx, const vtx_bgzf_block* blocks, uint32_t n_blocks, const uint8_t* comp, uint64_t comp_len,
+                             uint8_t* out, uint64_t out_len, int32_t* status, uint32_t flags);
+
 /* Injective code of a cell-barcode tag of the form [ACGT]{1,24}(-N)? with N = 1..99 written without a leading zero:
  * 2 bits per base, 5 bits length, 7 bits N (0 = no suffix); < 2^60.  Returns VTX_NO_CB_KEY if the bytes have another
  * form -- the caller then lists them as an exotic tag (VTX_CB_EXOTIC | i). */

@@ -15,23 +15,40 @@ import pytest
 from conftest import ROOT
 
 
-@pytest.fixture(scope="module")
-def inflater(tmp_path_factory):
-    so = str(tmp_path_factory.mktemp("inflate") / "libinflate_shim.so")
-    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so, os.path.join(ROOT, "tests", "inflate_shim.cpp")], check=True)
-    lib = ctypes.CDLL(so)
-    lib.vtx_test_inflate.restype = ctypes.c_int
-    lib.vtx_test_inflate.argtypes = [ctypes.c_char_p, ctypes.c_ulong, ctypes.c_char_p, ctypes.c_ulong]
-    lib.vtx_test_inflate_in_pad.restype = ctypes.c_ulong
-    lib.vtx_test_inflate_out_pad.restype = ctypes.c_ulong
-    in_pad, out_pad = int(lib.vtx_test_inflate_in_pad()), int(lib.vtx_test_inflate_out_pad())
+@pytest.fixture(scope="module", params=["host", "device_logic"])
+def inflater(request, tmp_path_factory):
+    """host: csrc/host/inflate_fast.hpp (what the staging threads run).  device_logic: the bit-stream half of the device
+    decoder csrc/vtx_inflate.cuh (table builders, block headers, symbol batches) compiled for the CPU, with a serial stand-in
+    for the warp's apply step (tests/inflate_dev_shim.cpp); the kernel itself is checked on the GPU."""
+    d = tmp_path_factory.mktemp("inflate")
+    if request.param == "host":
+        so = str(d / "libinflate_shim.so")
+        subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so, os.path.join(ROOT, "tests", "inflate_shim.cpp")], check=True)
+        lib = ctypes.CDLL(so)
+        lib.vtx_test_inflate.restype = ctypes.c_int
+        lib.vtx_test_inflate.argtypes = [ctypes.c_char_p, ctypes.c_ulong, ctypes.c_char_p, ctypes.c_ulong]
+        lib.vtx_test_inflate_in_pad.restype = ctypes.c_ulong
+        lib.vtx_test_inflate_out_pad.restype = ctypes.c_ulong
+        in_pad, out_pad = int(lib.vtx_test_inflate_in_pad()), int(lib.vtx_test_inflate_out_pad())
 
-    def run(comp: bytes, n_out: int):
-        inbuf = ctypes.create_string_buffer(comp + b"\xAA" * in_pad, len(comp) + in_pad)
-        out = ctypes.create_string_buffer(n_out + out_pad)
-        ok = lib.vtx_test_inflate(inbuf, len(comp), out, n_out)
-        return bool(ok), out.raw[:n_out]
-    return run
+        def run(comp: bytes, n_out: int):
+            inbuf = ctypes.create_string_buffer(comp + b"\xAA" * in_pad, len(comp) + in_pad)
+            out = ctypes.create_string_buffer(n_out + out_pad)
+            ok = lib.vtx_test_inflate(inbuf, len(comp), out, n_out)
+            return bool(ok), out.raw[:n_out]
+        return run
+    so = str(d / "libinflate_dev_shim.so")
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I", cuda_inc, "-o", so, os.path.join(ROOT, "tests", "inflate_dev_shim.cpp")], check=True)
+    lib = ctypes.CDLL(so)
+    lib.vtx_test_inflate_dev.restype = ctypes.c_int
+    lib.vtx_test_inflate_dev.argtypes = [ctypes.c_char_p, ctypes.c_ulong, ctypes.c_char_p, ctypes.c_ulong]
+
+    def run_dev(comp: bytes, n_out: int):
+        out = ctypes.create_string_buffer(n_out + 8)
+        st = lib.vtx_test_inflate_dev(comp, len(comp), out, n_out)
+        return st == 0, out.raw[:n_out]
+    return run_dev
 
 
 def _payload(kind, n, rng, nrng):

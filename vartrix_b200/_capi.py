@@ -29,7 +29,7 @@ SYMBOLS = [
     "vtx_set_barcodes", "vtx_submit", "vtx_submit_device", "vtx_submit_device_ex", "vtx_finish",
     "vtx_finish_device", "vtx_fetch", "vtx_sync", "vtx_wait_copies", "vtx_score_pairs", "vtx_pack_umi", "vtx_last_timing", "vtx_last_tile_counts",
     "vtx_comm_unique_id", "vtx_comm_init", "vtx_gather", "vtx_gather_start", "vtx_gather_wait",
-    "vtx_submit2", "vtx_submit2_device", "vtx_pack_cb",
+    "vtx_submit2", "vtx_submit2_device", "vtx_pack_cb", "vtx_bgzf_inflate",
 ]
 NO_CB_KEY = 0xFFFFFFFFFFFFFFFF
 CB_EXOTIC = 0x8000000000000000
@@ -70,6 +70,11 @@ class Batch2(C.Structure):          # vtx_batch2: the slim staging layout
         ("read_umi_key", C.c_void_p),
         ("n_cand", C.c_uint64), ("cand_read", C.c_void_p),
     ]
+
+
+class BgzfBlock(C.Structure):      # vtx_bgzf_block
+    _fields_ = [("in_off", C.c_uint64), ("in_len", C.c_uint32), ("out_len", C.c_uint32), ("out_off", C.c_uint64),
+                ("crc32", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class Metrics(C.Structure):
@@ -136,6 +141,8 @@ def load():
     L.vtx_submit2.argtypes = [C.c_void_p, C.POINTER(Batch2)]
     L.vtx_submit2_device.restype = C.c_int
     L.vtx_submit2_device.argtypes = [C.c_void_p, C.POINTER(Batch2), C.c_uint32, C.c_uint32]
+    L.vtx_bgzf_inflate.restype = C.c_int
+    L.vtx_bgzf_inflate.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32]
     L.vtx_pack_cb.restype = C.c_uint64
     L.vtx_pack_cb.argtypes = [C.c_char_p, C.c_uint32]
     L.vtx_gather_start.restype = C.c_int

@@ -4,6 +4,7 @@
 #include "vtx_pipeline.cuh"
 #include "vtx_sw.cuh"
 #include "vtx_sw_band.cuh"
+#include "vtx_inflate.cuh"
 
 #include <nvtx3/nvToolsExt.h>     // header-only; ranges cost nothing unless a profiler (nsys / ncu --nvtx) is attached
 
@@ -68,6 +69,7 @@ struct vtx_ctx {
     uint32_t bck_cap = 0;
     DBuf x_read_off, x_read_len, x_units, x_off4;      // slim layout expanded to the internal read arrays
     DBuf band_scratch;                                  // VTX_BAND_MODEL work buffers, one slice per resident warp
+    DBuf inf_comp, inf_out, inf_desc, inf_status;       // vtx_bgzf_inflate
     uint32_t bc_cap = 0, n_barcodes = 0;
     bool have_barcodes = false;
 
@@ -825,7 +827,7 @@ void vtx_destroy(vtx_ctx* ctx)
         if (sl.free_ev) cudaEventDestroy(sl.free_ev);
     }
     DBuf* all[] = { &ctx->bc_slot, &ctx->bc_bytes, &ctx->bc_off, &ctx->bck_key, &ctx->bck_idx, &ctx->x_read_off, &ctx->x_read_len,
-                    &ctx->x_units, &ctx->x_off4, &ctx->band_scratch, &ctx->read_col,
+                    &ctx->x_units, &ctx->x_off4, &ctx->band_scratch, &ctx->inf_comp, &ctx->inf_out, &ctx->inf_desc, &ctx->inf_status, &ctx->read_col,
                     &ctx->keep, &ctx->pidx, &ctx->scan_sums, &ctx->pair_read, &ctx->pair_col, &ctx->pair_umi, &ctx->pair_locus,
                     &ctx->pair_start, &ctx->tcount, &ctx->tstart, &ctx->pair_first, &ctx->pair_cslot, &ctx->pair_uslot, &ctx->cslot_col,
                     &ctx->cslot_locus, &ctx->uslot_cslot, &ctx->ccnt, &ctx->ucnt, &ctx->keep2, &ctx->oidx, &ctx->tile_counters,
@@ -1084,6 +1086,42 @@ int vtx_submit2_device(vtx_ctx* ctx, const vtx_batch2* db, uint32_t max_read_len
     rc = expand_reads(ctx, db->n_reads, db->read_len, db->read_off4, d);
     if (rc) return rc;
     return process_batch(ctx, d, tr);
+}
+
+int vtx_bgzf_inflate(vtx_ctx* ctx, const vtx_bgzf_block* blocks, uint32_t n_blocks, const uint8_t* comp, uint64_t comp_len,
+                     uint8_t* out, uint64_t out_len, int32_t* status, uint32_t flags)
+{
+    if (!ctx) return VTX_E_INVALID;
+    Nvtx nvtx_range("vtx_bgzf_inflate");
+    if (n_blocks == 0) return VTX_OK;
+    if (!blocks || !comp || !status || (!out && out_len)) return set_err(ctx, VTX_E_INVALID, "vtx_bgzf_inflate: NULL argument");
+    static_assert(sizeof(vtx_bgzf_block) == sizeof(inflate::BlockDesc), "descriptor layouts must agree");
+    for (uint32_t i = 0; i < n_blocks; ++i) {
+        const vtx_bgzf_block& b = blocks[i];
+        if ((b.in_off & 3) || b.in_off + b.in_len + 8 > comp_len + 8 || b.in_off + b.in_len > comp_len)
+            return set_err(ctx, VTX_E_INVALID, "vtx_bgzf_inflate: member %u: payload must start on a 4-byte boundary inside comp", i);
+        if (b.out_len > 65536u || b.out_off + b.out_len > out_len) return set_err(ctx, VTX_E_INVALID, "vtx_bgzf_inflate: member %u: output outside out / ISIZE above 64 KiB", i);
+    }
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    ENS(ctx->inf_comp, size_t(comp_len) + 16); ENS(ctx->inf_out, size_t(out_len) + 16);
+    ENS(ctx->inf_desc, size_t(n_blocks) * sizeof(vtx_bgzf_block)); ENS(ctx->inf_status, size_t(n_blocks) * 4 + 16);
+    ENS(ctx->tile_counters, 64);
+    CK(cudaMemsetAsync(static_cast<uint8_t*>(ctx->inf_comp.p) + comp_len, 0, 16, st));              // the readable padding
+    CK(cudaMemcpyAsync(ctx->inf_comp.p, comp, comp_len, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->inf_desc.p, blocks, size_t(n_blocks) * sizeof(vtx_bgzf_block), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(ctx->tile_counters.p, 0, 64, st));
+    const unsigned ctas = unsigned(std::min<uint64_t>((n_blocks + inflate::kInflateWarps - 1) / inflate::kInflateWarps, uint64_t(ctx->n_sm) * 6));
+    inflate::vtx_k_bgzf_inflate<<<ctas, inflate::kInflateWarps * 32, 0, st>>>(
+        P<inflate::BlockDesc>(ctx->inf_desc), n_blocks, P<uint8_t>(ctx->inf_comp), P<uint8_t>(ctx->inf_out), P<int32_t>(ctx->inf_status),
+        P<uint32_t>(ctx->tile_counters), (flags & VTX_BGZF_CHECK_CRC) ? 1 : 0);
+    CK(cudaGetLastError());
+    if (out_len) CK(cudaMemcpyAsync(out, ctx->inf_out.p, out_len, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(status, ctx->inf_status.p, size_t(n_blocks) * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (uint32_t i = 0; i < n_blocks; ++i)
+        if (status[i] != 0) return set_err(ctx, VTX_E_INVALID, "vtx_bgzf_inflate: member %u failed with decoder status %d (corrupt data)", i, status[i]);
+    return VTX_OK;
 }
 
 uint64_t vtx_pack_cb(const uint8_t* s, uint32_t len) { return (s || len == 0) ? pack_cb(s, len) : VTX_NO_CB_KEY; }

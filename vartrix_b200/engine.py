@@ -508,6 +508,28 @@ class Engine:
         self._ck(self._L.vtx_gather_wait(self._h, C.byref(res)), "vtx_gather_wait")
         return res
 
+    def bgzf_inflate(self, members, check_crc: bool = True):
+        """members: list of (deflate payload bytes, isize, crc32) of BGZF members -> (list of inflated bytes, status array).
+        Raises nothing on corrupt members: inspect the status array (0 = ok)."""
+        n = len(members)
+        blocks = (_capi.BgzfBlock * max(n, 1))()
+        comp = bytearray(); out_len = 0
+        for i, (payload, isize, crc) in enumerate(members):
+            while len(comp) & 7:
+                comp.append(0)
+            blocks[i].in_off = len(comp); blocks[i].in_len = len(payload); blocks[i].out_len = isize
+            blocks[i].out_off = out_len; blocks[i].crc32 = crc
+            comp += payload; out_len += (isize + 7) & ~7
+        comp += b"\0" * 16
+        cbuf = (C.c_uint8 * len(comp)).from_buffer(comp)
+        out = np.zeros(max(out_len, 1), np.uint8)
+        status = np.full(max(n, 1), -1, np.int32)
+        rc = self._L.vtx_bgzf_inflate(self._h, blocks, n, cbuf, len(comp) - 16, out.ctypes.data, out_len, status.ctypes.data, 1 if check_crc else 0)
+        if rc not in (0, -1):
+            self._ck(rc, "vtx_bgzf_inflate")
+        res = [out[int(blocks[i].out_off): int(blocks[i].out_off) + int(blocks[i].out_len)].tobytes() for i in range(n)]
+        return res, status[:n]
+
     def fetch(self, dev_res: _capi.Result, copy: bool = True) -> Triplets:
         out = _capi.Result()
         self._ck(self._L.vtx_fetch(self._h, C.byref(dev_res), C.byref(out)), "vtx_fetch")
