@@ -26,6 +26,8 @@ def dataset(tmp_path_factory):
     ("coverage", False, ["--mapq", "20", "--primary-alignments", "--no-duplicates", "--padding", "70"],
      dict(mapq=20, primary_only=True, no_duplicates=True, padding=70)),
     ("consensus", True, ["--bam-tag", "CB", "--valid-chars", "ATGC"], dict(valid_chars="ATGC")),
+    ("coverage", True, ["--threads", "3", "--shard-loci", "40", "--gpu-inflate"], {}),        # BGZF members inflated on the device
+    ("alt_frac", False, ["--gpu-inflate"], {}),
 ])
 def test_cli_matrices_byte_identical_to_oracle(oracle, dataset, tmp_path, mode, umi, extra, kw):
     out, ref, var, bco = (str(tmp_path / n) for n in ("out.mtx", "ref.mtx", "variants.txt", "bcs.tsv"))

@@ -59,3 +59,14 @@ def test_reference_regression_case(tmp_path, name, argv, gold_out, gold_ref, thr
     if "gzipped" in name:                                   # main.rs:1377-1389: barcode file round trip
         want = gzip.open(f"{T}/barcodes.tsv.gz", "rt").read().split()
         assert open(bco).read().split() == want
+
+
+@pytest.mark.parametrize("name,argv,gold_out,gold_ref", [CASES[2], CASES[6]], ids=[CASES[2][0], CASES[6][0]])
+def test_reference_regression_case_with_device_inflate(tmp_path, name, argv, gold_out, gold_ref):
+    """The same goldens with --gpu-inflate: every BGZF member the loci need is inflated (and CRC-checked) on the GPU."""
+    out, ref = str(tmp_path / "result.mtx"), str(tmp_path / "result_ref.mtx")
+    r = subprocess.run([CLI, *argv, "-o", out, "--ref-matrix", ref, "--threads", "2", "--shard-loci", "9", "--gpu-inflate", "--log-level", "info"],
+                       cwd=str(tmp_path), capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert read_mtx(out) == read_mtx(f"{T}/{gold_out}") and read_mtx(ref) == read_mtx(f"{T}/{gold_ref}")
+    assert "BGZF blocks" in r.stderr

@@ -13,18 +13,20 @@
 #include <cstdio>
 #include <cstring>
 #include <fcntl.h>
+#include <functional>
 #include <string>
 #include <sys/stat.h>
 #include <unistd.h>
 #include <vector>
 
+#include "../../../include/vartrix_b200.h"
 #include "inflate_fast.hpp"
 
 namespace vtxhost {
 
 // thread-seconds the staging threads spend per phase (reported by the CLI at --log-level info)
 struct StageClock {
-    std::atomic<uint64_t> read_ns{ 0 }, inflate_ns{ 0 }, crc_ns{ 0 }, blocks{ 0 }, inflated_bytes{ 0 };
+    std::atomic<uint64_t> read_ns{ 0 }, inflate_ns{ 0 }, crc_ns{ 0 }, blocks{ 0 }, inflated_bytes{ 0 }, device_inflate_ns{ 0 };
     static uint64_t now() { return uint64_t(std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count()); }
 };
 inline StageClock& stage_clock() { static StageClock c; return c; }
@@ -82,7 +84,7 @@ public:
                 if (cur_->len == 0) { if (eof_) return false; continue; }   // empty (EOF marker) block
             }
             const size_t k = std::min<size_t>(n, cur_->len - block_pos_);
-            memcpy(d, cur_->data.data() + block_pos_, k);
+            memcpy(d, cur_->ptr + block_pos_, k);
             d += k; n -= k; block_pos_ += uint32_t(k);
         }
         return true;
@@ -92,7 +94,7 @@ public:
     {
         if (cur_ && block_pos_ == cur_->len && cur_->len > 0 && !load(cur_->next)) return nullptr;
         if (!cur_ || size_t(cur_->len - block_pos_) < n) return nullptr;
-        return cur_->data.data() + block_pos_;
+        return cur_->ptr + block_pos_;
     }
     void skip(size_t n) { block_pos_ += uint32_t(n); }     // only after a successful peek(>= n)
     bool at_eof() const { return eof_; }
@@ -105,7 +107,7 @@ private:
     // Neighbouring loci fetch overlapping file ranges (every fetch restarts at its 16 kb index window): inflated
     // blocks stay in a small cache and are used in place.  48 x 64 KiB covers the ~10 blocks of a 16 kb window of
     // a deep BAM several times over, so the cyclic re-scan pattern of consecutive loci always hits.
-    struct Slot { uint64_t coff = ~0ull, next = 0; uint32_t len = 0; std::vector<uint8_t> data; };
+    struct Slot { uint64_t coff = ~0ull, next = 0; uint32_t len = 0; const uint8_t* ptr = nullptr; std::vector<uint8_t> data; };
     static constexpr int kSlots = 48;
     Slot slots_[kSlots];
     Slot end_slot_;
@@ -121,6 +123,14 @@ private:
     {
         eof_ = false;
         if (!err_.empty()) return false;
+        if (coff >= bulk_begin_ && coff < bulk_end_) {              // inflated in bulk on the device (prefetch_bulk)
+            auto it = std::lower_bound(bulk_blocks_.begin(), bulk_blocks_.end(), coff, [](const BulkBlock& b, uint64_t c) { return b.coff < c; });
+            if (it != bulk_blocks_.end() && it->coff == coff) {
+                bulk_slot_.coff = coff; bulk_slot_.next = it->next; bulk_slot_.len = it->len; bulk_slot_.ptr = bulk_out_.data() + it->out_off;
+                cur_ = &bulk_slot_; block_pos_ = 0;
+                return true;
+            }
+        }
         for (Slot& c : slots_)
             if (c.coff == coff) { cur_ = &c; block_pos_ = 0; return true; }
         if (coff >= size_) {            // past the last block: an empty pseudo-block that the cache never serves
@@ -169,13 +179,78 @@ private:
         if (check_crc_ && uint32_t(crc32(crc32(0L, Z_NULL, 0), v->data.data(), isize)) != crc) return fail(coff, "CRC32 mismatch (corrupt data)");
         const uint64_t t_end = StageClock::now();
         clk.read_ns += t_inf - t_read; clk.inflate_ns += t_crc - t_inf; clk.crc_ns += t_end - t_crc; clk.blocks += 1; clk.inflated_bytes += isize;
-        v->coff = coff; v->next = coff + total; v->len = isize;
+        v->coff = coff; v->next = coff + total; v->len = isize; v->ptr = v->data.data();
         cur_ = v; block_pos_ = 0;
         return true;
     }
 public:
     void set_check_crc(bool on) { check_crc_ = on; }
+    // Inflate every BGZF member that starts in [coff_begin, coff_last] in one go through `fn` (the device:
+    // vtx_bgzf_inflate) and serve them from that buffer afterwards: the host only reads the compressed bytes and walks
+    // the member headers.  Returns false on error (bad() tells whether the file is at fault); a range that cannot be
+    // prefetched leaves the reader as it was and the members are inflated one by one on the host as before.
+    using BulkInflate = std::function<bool(const vtx_bgzf_block*, uint32_t, const uint8_t*, uint64_t, uint8_t*, uint64_t, std::string*)>;
+    bool prefetch_bulk(uint64_t coff_begin, uint64_t coff_last, const BulkInflate& fn)
+    {
+        if (cur_ == &bulk_slot_) cur_ = nullptr;
+        bulk_begin_ = bulk_end_ = 0; bulk_blocks_.clear();
+        if (coff_begin >= size_ || coff_last < coff_begin) return true;
+        StageClock& clk = stage_clock();
+        const uint64_t t0 = StageClock::now();
+        // read the compressed range; the last member may reach up to 64 KiB beyond coff_last
+        const uint64_t want_end = std::min<uint64_t>(size_, coff_last + (1u << 16) + 64);
+        bulk_file_.resize(size_t(want_end - coff_begin));
+        if (pread(fd_, bulk_file_.data(), bulk_file_.size(), off_t(coff_begin)) != ssize_t(bulk_file_.size())) return fail(coff_begin, "truncated file (bulk read)");
+        bulk_desc_.clear(); bulk_comp_.clear();
+        uint64_t pos = 0, out_off = 0;
+        while (coff_begin + pos <= coff_last && coff_begin + pos < size_) {
+            const uint8_t* h = bulk_file_.data() + pos;
+            const uint64_t coff = coff_begin + pos;
+            if (pos + 18 > bulk_file_.size()) return fail(coff, "truncated file (short read of the member header)");
+            if (h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4)) return fail(coff, "not a BGZF member (bad gzip magic)");
+            const uint32_t xlen = rd16(h + 10);
+            uint32_t bsize = 0; bool have_bc = false;
+            for (uint32_t q = 0; q + 4 <= xlen && pos + 12 + q + 4 <= bulk_file_.size();) {
+                const uint32_t slen = rd16(h + 12 + q + 2);
+                if (h[12 + q] == 66 && h[12 + q + 1] == 67 && slen == 2 && q + 6 <= xlen) { bsize = rd16(h + 12 + q + 4); have_bc = true; }
+                q += 4 + slen;
+            }
+            if (!have_bc) return fail(coff, "gzip member without the BGZF 'BC' field");
+            const uint32_t total = bsize + 1;
+            if (total < 12 + xlen + 8) return fail(coff, "BSIZE smaller than the member header");
+            if (pos + total > bulk_file_.size()) return fail(coff, "truncated file (short read of the member body)");
+            const uint32_t clen = total - 12 - xlen - 8;
+            const uint32_t crc = rd32(h + total - 8), isize = rd32(h + total - 4);
+            if (isize > (1u << 16)) return fail(coff, "ISIZE above 64 KiB");
+            while (bulk_comp_.size() & 7) bulk_comp_.push_back(0);
+            vtx_bgzf_block d{};
+            d.in_off = bulk_comp_.size(); d.in_len = clen; d.out_len = isize; d.out_off = out_off; d.crc32 = crc;
+            bulk_comp_.insert(bulk_comp_.end(), h + 12 + xlen, h + 12 + xlen + clen);
+            bulk_desc_.push_back(d);
+            bulk_blocks_.push_back({ coff, coff + total, out_off, isize });
+            out_off += (uint64_t(isize) + 15) & ~uint64_t(15);
+            pos += total;
+        }
+        bulk_comp_.resize(bulk_comp_.size() + 16, 0);                                   // readable padding behind the last payload
+        bulk_out_.resize(size_t(out_off) + 16);
+        const uint64_t t1 = StageClock::now();
+        std::string e;
+        if (!bulk_desc_.empty() && !fn(bulk_desc_.data(), uint32_t(bulk_desc_.size()), bulk_comp_.data(), bulk_comp_.size() - 16, bulk_out_.data(), out_off, &e)) {
+            bulk_blocks_.clear();
+            if (err_.empty()) err_ = "device BGZF inflate: " + e;
+            return false;
+        }
+        clk.read_ns += t1 - t0; clk.device_inflate_ns += StageClock::now() - t1; clk.blocks += bulk_desc_.size(); clk.inflated_bytes += out_off;
+        if (!bulk_blocks_.empty()) { bulk_begin_ = bulk_blocks_.front().coff; bulk_end_ = bulk_blocks_.back().next; }
+        return true;
+    }
 private:
+    struct BulkBlock { uint64_t coff, next, out_off; uint32_t len; };
+    std::vector<BulkBlock> bulk_blocks_;
+    std::vector<uint8_t> bulk_file_, bulk_comp_, bulk_out_;
+    std::vector<vtx_bgzf_block> bulk_desc_;
+    uint64_t bulk_begin_ = 0, bulk_end_ = 0;
+    Slot bulk_slot_;
     std::string err_;
     bool check_crc_ = true;
     int fd_ = -1;
@@ -405,6 +480,38 @@ public:
     bool bad() const { return !err_.empty(); }
     const std::string& error() const { return err_; }
     void set_check_crc(bool on) { bg_.set_check_crc(on); }
+    // Compressed-offset span [first, last] of the BGZF members a fetch(tid, beg, end) may touch (index chunks, before any
+    // resume hint).  false when the index has nothing for the region.
+    bool region_span(int tid, int64_t beg, int64_t end, uint64_t* c_first, uint64_t* c_last) const
+    {
+        if (tid < 0 || size_t(tid) >= refs_.size() || end <= beg) return false;
+        if (beg < 0) beg = 0;
+        const BaiRef& r = refs_[size_t(tid)];
+        uint64_t min_off = 0;
+        if (!r.linear.empty()) { size_t w = size_t(beg >> 14); if (w >= r.linear.size()) w = r.linear.size() - 1; min_off = r.linear[w]; }
+        const int64_t e1 = end - 1;
+        uint64_t lo = ~0ull, hi = 0;
+        auto add_bin = [&](uint32_t bin) {
+            auto it = std::lower_bound(r.bin_ids.begin(), r.bin_ids.end(), bin);
+            if (it == r.bin_ids.end() || *it != bin) return;
+            for (const BaiChunk& c : r.bin_chunks[size_t(it - r.bin_ids.begin())])
+                if (c.end > min_off) { lo = std::min(lo, std::max(c.beg, min_off)); hi = std::max(hi, c.end); }
+        };
+        add_bin(0);
+        for (int64_t k = 1 + (beg >> 26); k <= 1 + (e1 >> 26); ++k) add_bin(uint32_t(k));
+        for (int64_t k = 9 + (beg >> 23); k <= 9 + (e1 >> 23); ++k) add_bin(uint32_t(k));
+        for (int64_t k = 73 + (beg >> 20); k <= 73 + (e1 >> 20); ++k) add_bin(uint32_t(k));
+        for (int64_t k = 585 + (beg >> 17); k <= 585 + (e1 >> 17); ++k) add_bin(uint32_t(k));
+        for (int64_t k = 4681 + (beg >> 14); k <= 4681 + (e1 >> 14); ++k) add_bin(uint32_t(k));
+        if (lo == ~0ull) return false;
+        *c_first = lo >> 16; *c_last = hi >> 16;
+        return true;
+    }
+    bool prefetch_bulk(uint64_t c_first, uint64_t c_last, const Bgzf::BulkInflate& fn)
+    {
+        if (!bg_.prefetch_bulk(c_first, c_last, fn)) { if (bg_.bad()) fail(bg_.error()); return false; }
+        return true;
+    }
     // compressed file offset where the 16 kb window of `pos` starts (BAI linear index; monotone within a contig).
     // Differences of it estimate how much BAM a range of loci spans -- used to balance loci over GPUs before any decode.
     uint64_t linear_offset(int tid, int64_t pos) const

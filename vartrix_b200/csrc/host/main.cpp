@@ -48,7 +48,7 @@ struct Opts {
     std::string scoring = "consensus", bam_tag = "CB", valid_chars = "ATGCatgc", dump_staged;
     long padding = 100, threads = 1, mapq = 0, device = 0, shard_loci = 0;      // 0: chosen from the number of loci and threads
     std::vector<int> devices;          // --devices: the loci are sharded over these GPUs (contiguous ranges, main.rs:250-254)
-    bool primary = false, no_dups = false, umi = false, ref_matrix_given = false;
+    bool primary = false, no_dups = false, umi = false, ref_matrix_given = false, gpu_inflate = false;
 };
 
 void usage()
@@ -76,6 +76,8 @@ void usage()
          "      --device INT            CUDA device ordinal [0]\n"
          "      --devices LIST          Shard the loci over several GPUs: e.g. 0-7 or 0,2,5 (one NCCL gather at the end)\n"
          "      --shard-loci INT        VCF records per staged shard [up to 2048, fewer for short VCFs]\n"
+         "      --gpu-inflate           Inflate the BGZF members of every shard on the GPU (one call per shard) instead of on\n"
+         "                              the staging threads; for hosts with few cores per GPU\n"
          "      --dump-staged FILE      Stage only, write the shards to FILE (no GPU)");
 }
 
@@ -131,6 +133,7 @@ bool parse(int argc, char** argv, Opts* o)
         else if (a == "--devices") { if (!parse_devices(v(), &o->devices)) { fprintf(stderr, "error: bad --devices list\n"); return false; } }
         else if (a == "--shard-loci") o->shard_loci = atol(v().c_str());
         else if (a == "--dump-staged") o->dump_staged = v();
+        else if (a == "--gpu-inflate") o->gpu_inflate = true;
         else if (a == "-h" || a == "--help") { usage(); exit(0); }
         else if (a == "-V" || a == "--version") { puts("vartrix_b200 0.1 (vartrix 1.1.22 surface)"); exit(0); }
         else { fprintf(stderr, "error: unknown argument %s\n", argv[i]); return false; }
@@ -387,9 +390,25 @@ int main(int argc, char** argv)
     UmiInterner umis;
     std::vector<std::unique_ptr<StagedShard>> recycled;      // guarded by mu
     std::atomic<uint64_t> stage_ns{ 0 }, arena_ns{ 0 }, staged_bytes{ 0 };
+    std::atomic<int> worker_no{ 0 };
     auto worker = [&]() {
         Fasta fa; BamFile bam; std::string e;
         if (!fa.open(o.fasta, &e) || !bam.open(o.bam, &e)) { std::lock_guard<std::mutex> g(mu); failed = true; fail_msg = e; cv.notify_all(); return; }
+        StageArgs sa_w = sa;
+        vtx_ctx* ictx = nullptr;                 // --gpu-inflate: this worker's own context for vtx_bgzf_inflate
+        std::vector<int32_t> istatus;
+        if (o.gpu_inflate) {
+            vtx_config c{};
+            c.device = o.devices[size_t(worker_no.fetch_add(1)) % o.devices.size()];
+            c.mode = VTX_MODE_CONSENSUS; c.match = 1; c.mismatch = -5; c.gap_open = -5; c.gap_extend = -1; c.min_score = 25;
+            if (vtx_create(&c, &ictx) != VTX_OK) { std::lock_guard<std::mutex> g(mu); failed = true; fail_msg = vtx_last_error(nullptr); cv.notify_all(); return; }
+            sa_w.bulk_inflate = [&istatus, ictx](const vtx_bgzf_block* b, uint32_t n, const uint8_t* comp, uint64_t comp_len, uint8_t* out, uint64_t out_len, std::string* err) {
+                istatus.resize(n);
+                if (vtx_bgzf_inflate(ictx, b, n, comp, comp_len, out, out_len, istatus.data(), VTX_BGZF_CHECK_CRC) == VTX_OK) return true;
+                *err = vtx_last_error(ictx);
+                return false;
+            };
+        }
         for (;;) {
             const size_t i = next.fetch_add(1);
             if (i >= n_shards) break;
@@ -401,7 +420,7 @@ int main(int argc, char** argv)
             if (!sh) sh = std::make_unique<StagedShard>();
             const size_t lo = k * size_t(o.shard_loci), hi = std::min(recs.size(), lo + size_t(o.shard_loci));
             const uint64_t t_stage = StageClock::now();
-            const bool staged_ok = stage_loci(recs, lo, hi, fa, bam, sa, umis, sh.get(), &e);
+            const bool staged_ok = stage_loci(recs, lo, hi, fa, bam, sa_w, umis, sh.get(), &e);
             stage_ns += StageClock::now() - t_stage;
             if (!staged_ok) { std::lock_guard<std::mutex> g(mu); failed = true; fail_msg = e; cv.notify_all(); return; }
             { std::lock_guard<std::mutex> g(mu); ready[k] = std::move(sh); }
@@ -482,8 +501,8 @@ int main(int argc, char** argv)
     {   // where the time went: thread-seconds of the staging pool, device milliseconds of the last finish
         const StageClock& c = stage_clock();
         LOG_INFO("Staging thread-seconds: total %.3f = file read %.3f + inflate %.3f + crc32 %.3f + record scan / filters / packing %.3f; %llu BGZF blocks, %.1f MB inflated; copy into pinned arenas %.3f s (%.1f MB)",
-                 stage_ns.load() * 1e-9, c.read_ns.load() * 1e-9, c.inflate_ns.load() * 1e-9, c.crc_ns.load() * 1e-9,
-                 (double(stage_ns.load()) - double(c.read_ns.load()) - double(c.inflate_ns.load()) - double(c.crc_ns.load())) * 1e-9,
+                 stage_ns.load() * 1e-9, c.read_ns.load() * 1e-9, (c.inflate_ns.load() + c.device_inflate_ns.load()) * 1e-9, c.crc_ns.load() * 1e-9,
+                 (double(stage_ns.load()) - double(c.read_ns.load()) - double(c.inflate_ns.load()) - double(c.device_inflate_ns.load()) - double(c.crc_ns.load())) * 1e-9,
                  (unsigned long long)c.blocks.load(), c.inflated_bytes.load() * 1e-6, arena_ns.load() * 1e-9, staged_bytes.load() * 1e-6);
         for (Lane& ln : lanes) {
             vtx_timing t{};

@@ -34,6 +34,9 @@ struct StageArgs {
     char bam_tag[2] = { 'C', 'B' };
     bool valid[256] = {};        // --valid-chars
     bool with_umi = true;        // stage the UB keys (--umi, or a dump for the tests); without --umi nobody reads them
+    // --gpu-inflate: the BGZF members of a shard's loci are inflated in one device call (vtx_bgzf_inflate) instead of one
+    // by one on the staging thread; empty = host inflate
+    Bgzf::BulkInflate bulk_inflate;
 };
 
 // vtx_pack_cb (include/vartrix_b200.h), kept local so that staging can run without the CUDA library: an injective code of
@@ -213,6 +216,23 @@ inline bool stage_loci(const std::vector<VcfRecord>& recs, size_t lo, size_t hi,
 {
     out->with_umi = a.with_umi;
     out->cb_off.push_back(0);
+    if (a.bulk_inflate && hi > lo) {
+        // one compressed range for the whole shard when its loci sit on one contig (the usual case: sorted VCF)
+        uint64_t c0 = ~0ull, c1 = 0;
+        bool one_contig = true;
+        for (size_t i = lo; i < hi && one_contig; ++i) one_contig = recs[i].chrom == recs[lo].chrom;
+        if (one_contig) {
+            const int tid = bam.tid_of(recs[lo].chrom);
+            for (size_t i = lo; i < hi; ++i) {
+                uint64_t f = 0, l = 0;
+                const int64_t start = recs[i].pos0, end = recs[i].pos0 + int64_t(recs[i].alleles[0].size());
+                if (bam.region_span(tid, start, end, &f, &l)) { c0 = std::min(c0, f); c1 = std::max(c1, l); }
+            }
+            if (c0 != ~0ull && c1 - c0 < (uint64_t(1) << 30)) {
+                if (!bam.prefetch_bulk(c0, c1, a.bulk_inflate)) { *err = bam.error().empty() ? "device BGZF inflate failed" : bam.error(); return false; }
+            }
+        }
+    }
     static thread_local ReadIndex read_index;               // record virtual offset -> staged read id (table reused across shards)
     read_index.clear();
     BamRecord rec;
