@@ -211,3 +211,30 @@ def test_cpp_staging_with_long_spliced_records_across_index_bins(oracle, tmp_pat
             _same_staging(sb, ob)
             assert met == {m: ob.host_metrics[m] for m in met}, (threads, k)
         assert sum(int(m["num_not_useful"]) for _, m in shards) > 0        # spliced records that skip their locus
+
+
+@pytest.mark.parametrize("shard", ["7", "1000000"])
+def test_bulk_inflate_path_stages_the_same_shards(tmp_path, shard):
+    """--gpu-inflate reads one compressed range per shard, walks the BGZF member headers and serves the records out of one
+    bulk buffer (inflated by the device in the product; by the host decoder under --dump-staged): same staging, byte for byte."""
+    outs = []
+    for extra in ([], ["--gpu-inflate"]):
+        out = tmp_path / f"d{len(outs)}.staged"
+        subprocess.run([CLI, "-v", f"{REF_TEST_DIR}/test_dna.vcf", "-b", f"{REF_TEST_DIR}/test_dna.bam", "-f", f"{REF_TEST_DIR}/test_dna.fa",
+                        "-c", f"{REF_TEST_DIR}/dna_barcodes.tsv", "--dump-staged", str(out), "--shard-loci", shard, "--threads", "2", *extra],
+                       check=True, cwd=str(tmp_path))
+        outs.append(open(out, "rb").read())
+    assert outs[0] == outs[1] and len(outs[0]) > 100_000
+
+
+def test_bulk_inflate_path_reports_corruption(tmp_path):
+    import shutil
+    raw = bytearray(open(f"{REF_TEST_DIR}/test.bam", "rb").read())
+    bsize0 = int.from_bytes(raw[16:18], "little") + 1
+    for k in range(bsize0 + 40, bsize0 + 440):
+        raw[k] ^= 0x5A
+    bam = tmp_path / "bad.bam"
+    bam.write_bytes(bytes(raw)); shutil.copy(f"{REF_TEST_DIR}/test.bam.bai", str(bam) + ".bai")
+    r = subprocess.run([CLI, "-v", f"{REF_TEST_DIR}/test.vcf", "-b", str(bam), "-f", f"{REF_TEST_DIR}/test.fa", "-c", f"{REF_TEST_DIR}/barcodes.tsv",
+                        "--dump-staged", str(tmp_path / "d.staged"), "--gpu-inflate"], cwd=str(tmp_path), capture_output=True, text=True)
+    assert r.returncode != 0 and "inflate" in (r.stdout + r.stderr)

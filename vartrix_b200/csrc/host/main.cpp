@@ -397,7 +397,17 @@ int main(int argc, char** argv)
         StageArgs sa_w = sa;
         vtx_ctx* ictx = nullptr;                 // --gpu-inflate: this worker's own context for vtx_bgzf_inflate
         std::vector<int32_t> istatus;
-        if (o.gpu_inflate) {
+        if (o.gpu_inflate && dumping) {
+            // --dump-staged never touches a GPU: the bulk path (one compressed range per shard, member walk, serving records out
+            // of the bulk buffer) is exercised with the host decoder standing in for vtx_bgzf_inflate (CPU tests)
+            sa_w.bulk_inflate = [](const vtx_bgzf_block* b, uint32_t n, const uint8_t* comp, uint64_t, uint8_t* out, uint64_t, std::string* err) {
+                for (uint32_t i = 0; i < n; ++i) {
+                    if (b[i].out_len && !vtx_inflate_raw(comp + b[i].in_off, b[i].in_len, out + b[i].out_off, b[i].out_len)) { *err = "member " + std::to_string(i) + ": inflate failed"; return false; }
+                    if (uint32_t(crc32(crc32(0L, Z_NULL, 0), out + b[i].out_off, b[i].out_len)) != b[i].crc32) { *err = "member " + std::to_string(i) + ": CRC32 mismatch"; return false; }
+                }
+                return true;
+            };
+        } else if (o.gpu_inflate) {
             vtx_config c{};
             c.device = o.devices[size_t(worker_no.fetch_add(1)) % o.devices.size()];
             c.mode = VTX_MODE_CONSENSUS; c.match = 1; c.mismatch = -5; c.gap_open = -5; c.gap_extend = -1; c.min_score = 25;
