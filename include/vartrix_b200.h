@@ -264,6 +264,52 @@ typedef struct vtx_bgzf_block {
 int         vtx_bgzf_inflate(vtx_ctx* ctx, const vtx_bgzf_block* blocks, uint32_t n_blocks, const uint8_t* comp, uint64_t comp_len,
                              uint8_t* out, uint64_t out_len, int32_t* status, uint32_t flags);
 
+/* ---- a shard of loci straight from the BAM: inflate, record scan, fetch, record filters and tag extraction on the
+ * device.  The host's part shrinks to what needs the file system and the index: it reads the compressed
+ * byte range the loci's index chunks span, walks the BGZF member headers, lists the chunk starts that fall into the range
+ * (record boundaries), builds the haplotype windows from the FASTA -- and hands all of it over.  The device then does what
+ * csrc/host/stager.hpp does on staging threads and the reference does through rust-htslib: every record of contig `tid`
+ * with pos < end and bam_endpos > start per locus, in file order (main.rs:822-829); mapq / primary / duplicate /
+ * useful_alignment filters in that order (main.rs:833-865); CB (`bam_tag`) and UB as the first Z-typed aux field of that
+ * name (main.rs:737-757); then the same pipeline as vtx_submit.  Loci must be ascending on one contig of a
+ * coordinate-sorted BAM.  Asynchronous like vtx_submit (two short waits on the staging stream for sizes).
+ *   members / comp : as for vtx_bgzf_inflate, in file order, out_off = running sum of out_len (one contiguous stream)
+ *   entry_off      : ascending offsets into that stream; [0] = first record to look at, [n_entry - 1] = end of the
+ *                    records to look at; every entry is a record boundary (BAI chunk starts / ends)
+ * Returns VTX_E_UNSUPPORTED when the shard needs the host path (a UB string that vtx_pack_umi cannot express, a read
+ * above 16 000 bases) and VTX_E_INVALID for corrupt members / records; nothing of the shard has been counted then and
+ * the caller may stage it on the host instead (vtx_submit2). */
+typedef struct vtx_bam_shard {
+    uint32_t        n_loci;
+    const uint32_t* locus_row;       /* [n_loci] */
+    const int64_t*  locus_start;     /* [n_loci] rec.pos(), 0-based            (main.rs:619-623) */
+    const int64_t*  locus_end;       /* [n_loci] start + len(REF) */
+    const uint8_t*  hap_bytes;       /* windows as in vtx_batch */
+    uint64_t        hap_bytes_len;
+    const uint32_t* ref_off;
+    const uint32_t* ref_len;
+    const uint32_t* alt_off;
+    const uint32_t* alt_len;
+    int32_t         tid;             /* BAM reference id of the contig */
+    uint32_t        n_members;
+    const vtx_bgzf_block* members;
+    const uint8_t*  comp;
+    uint64_t        comp_len;
+    uint32_t        n_entry;
+    const uint64_t* entry_off;
+    uint32_t        mapq;            /* --mapq */
+    int32_t         primary_only;    /* --primary-alignments */
+    int32_t         no_duplicates;   /* --no-duplicates */
+    char            bam_tag[2];      /* --bam-tag */
+} vtx_bam_shard;
+/* the host-side share of main.rs:449-459, counted on the device for shards that came through vtx_submit_bam */
+typedef struct vtx_bam_metrics {
+    uint64_t num_reads, num_low_mapq, num_non_primary, num_duplicates, num_not_useful;
+} vtx_bam_metrics;
+int         vtx_submit_bam(vtx_ctx* ctx, const vtx_bam_shard* shard);
+/* Counters of every vtx_submit_bam since the ctx was created (waits for the staging stream). */
+int         vtx_bam_metrics_get(vtx_ctx* ctx, vtx_bam_metrics* out);
+
 /* Injective code of a cell-barcode tag of the form [ACGT]{1,24}(-N)? with N = 1..99 written without a leading zero:
  * 2 bits per base, 5 bits length, 7 bits N (0 = no suffix); < 2^60.  Returns VTX_NO_CB_KEY if the bytes have another
  * form -- the caller then lists them as an exotic tag (VTX_CB_EXOTIC | i). */

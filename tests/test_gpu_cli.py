@@ -28,6 +28,11 @@ def dataset(tmp_path_factory):
     ("consensus", True, ["--bam-tag", "CB", "--valid-chars", "ATGC"], dict(valid_chars="ATGC")),
     ("coverage", True, ["--threads", "3", "--shard-loci", "40", "--gpu-inflate"], {}),        # BGZF members inflated on the device
     ("alt_frac", False, ["--gpu-inflate"], {}),
+    # the BAM decoded on the device: inflate, record walk, fetch, record filters, tags (vtx_submit_bam)
+    ("coverage", True, ["--threads", "3", "--shard-loci", "40", "--gpu-stage"], {}),
+    ("consensus", False, ["--gpu-stage", "--shard-loci", "7", "--threads", "2"], {}),
+    ("coverage", False, ["--gpu-stage", "--mapq", "20", "--primary-alignments", "--no-duplicates", "--padding", "70"],
+     dict(mapq=20, primary_only=True, no_duplicates=True, padding=70)),
 ])
 def test_cli_matrices_byte_identical_to_oracle(oracle, dataset, tmp_path, mode, umi, extra, kw):
     out, ref, var, bco = (str(tmp_path / n) for n in ("out.mtx", "ref.mtx", "variants.txt", "bcs.tsv"))

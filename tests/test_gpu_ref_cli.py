@@ -70,3 +70,14 @@ def test_reference_regression_case_with_device_inflate(tmp_path, name, argv, gol
     assert r.returncode == 0, r.stdout + r.stderr
     assert read_mtx(out) == read_mtx(f"{T}/{gold_out}") and read_mtx(ref) == read_mtx(f"{T}/{gold_ref}")
     assert "BGZF blocks" in r.stderr
+
+
+@pytest.mark.parametrize("name,argv,gold_out,gold_ref", [CASES[2], CASES[3], CASES[5], CASES[6]], ids=[CASES[i][0] for i in (2, 3, 5, 6)])
+def test_reference_regression_case_with_device_staging(tmp_path, name, argv, gold_out, gold_ref):
+    """The same goldens with --gpu-stage: the host reads compressed ranges and the index; the BAM is decoded on the GPU."""
+    out, ref = str(tmp_path / "result.mtx"), str(tmp_path / "result_ref.mtx")
+    r = subprocess.run([CLI, *argv, "-o", out, "--ref-matrix", ref, "--threads", "2", "--shard-loci", "9", "--gpu-stage", "--log-level", "info"],
+                       cwd=str(tmp_path), capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert read_mtx(out) == read_mtx(f"{T}/{gold_out}") and read_mtx(ref) == read_mtx(f"{T}/{gold_ref}")
+    assert "staged on the host after the device declined" not in r.stderr

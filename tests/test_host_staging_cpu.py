@@ -238,3 +238,64 @@ def test_bulk_inflate_path_reports_corruption(tmp_path):
     r = subprocess.run([CLI, "-v", f"{REF_TEST_DIR}/test.vcf", "-b", str(bam), "-f", f"{REF_TEST_DIR}/test.fa", "-c", f"{REF_TEST_DIR}/barcodes.tsv",
                         "--dump-staged", str(tmp_path / "d.staged"), "--gpu-inflate"], cwd=str(tmp_path), capture_output=True, text=True)
     assert r.returncode != 0 and "inflate" in (r.stdout + r.stderr)
+
+
+def _read_vtxd(path):
+    """shards dumped by `--gpu-stage --dump-staged`: the host's share of device staging"""
+    import struct
+    data = open(path, "rb").read()
+    p, out = 16, []
+    def take():
+        nonlocal p
+        (nb,) = struct.unpack_from("<Q", data, p); p += 8
+        b = data[p:p + nb]; p += nb
+        return b
+    while p < len(data):
+        assert data[p:p + 4] == b"VTXD"; p += 4
+        tid = struct.unpack("<q", take())[0]
+        row = np.frombuffer(take(), np.uint32); start = np.frombuffer(take(), np.int64); end = np.frombuffer(take(), np.int64)
+        members = np.frombuffer(take(), np.dtype([("in_off", "<u8"), ("in_len", "<u4"), ("out_len", "<u4"), ("out_off", "<u8"), ("crc", "<u4"), ("pad", "<u4")]))
+        comp = take(); entry = np.frombuffer(take(), np.uint64)
+        out.append(dict(tid=tid, row=row, start=start, end=end, members=members, comp=comp, entry=entry))
+    return out
+
+
+@pytest.mark.parametrize("pre,bcs,shard", [("test_dna", "dna_barcodes.tsv", "7"), ("test_dna", "dna_barcodes.tsv", "1000"), ("test", "barcodes.tsv", "1")])
+def test_device_staging_host_share(tmp_path, pre, bcs, shard):
+    """--gpu-stage: the host hands the device a member table, the compressed bytes and the record boundaries the index knows.
+    Emulated here: the members inflate (zlib) to one stream with matching CRCs; walking the BAM records from the first entry
+    hits every later entry exactly and ends on the last one; the records that overlap the loci are as many as the host stager
+    fetches (its num_reads), i.e. the range is complete."""
+    import struct, zlib
+    base = [CLI, "-v", f"{REF_TEST_DIR}/{pre}.vcf", "-b", f"{REF_TEST_DIR}/{pre}.bam", "-f", f"{REF_TEST_DIR}/{pre}.fa", "-c", f"{REF_TEST_DIR}/{bcs}",
+            "--shard-loci", shard, "--threads", "2"]
+    subprocess.run([*base, "--dump-staged", str(tmp_path / "dev.staged"), "--gpu-stage"], check=True, cwd=str(tmp_path))
+    subprocess.run([*base, "--dump-staged", str(tmp_path / "host.staged")], check=True, cwd=str(tmp_path))
+    from vartrix_b200.staged_io import read_dump
+    _, _, host = read_dump(str(tmp_path / "host.staged"))
+    dev = _read_vtxd(str(tmp_path / "dev.staged"))
+    assert len(dev) == len(host)
+    for d, (hb, hmet) in zip(dev, host):
+        assert np.array_equal(d["row"], hb.locus_row)
+        stream = bytearray()
+        for m in d["members"]:
+            raw = zlib.decompress(d["comp"][int(m["in_off"]): int(m["in_off"]) + int(m["in_len"])], -15)
+            assert len(raw) == m["out_len"] and int(m["out_off"]) == len(stream) and (zlib.crc32(raw) & 0xFFFFFFFF) == m["crc"] and m["in_off"] % 4 == 0
+            stream += raw
+        entry = [int(x) for x in d["entry"]]
+        fetched = 0
+        if entry:
+            assert entry == sorted(set(entry)) and entry[-1] <= len(stream)
+            p, hit, recs = entry[0], set(), []
+            while p < entry[-1]:
+                if p in entry: hit.add(p)
+                bs = struct.unpack_from("<I", stream, p)[0]
+                refid, pos, l_name, mapq, _bin, n_cig, flag, l_seq = struct.unpack_from("<iiBBHHHi", stream, p + 4)
+                cig = struct.unpack_from(f"<{n_cig}I", stream, p + 36 + l_name)
+                rlen = 0 if flag & 4 else sum(c >> 4 for c in cig if (c & 15) in (0, 2, 3, 7, 8))
+                recs.append((refid, pos, pos + (rlen if rlen > 0 else 1)))
+                p += 4 + bs
+            assert p == entry[-1] and hit == set(entry[:-1])
+            for s0, e0 in zip(d["start"], d["end"]):
+                fetched += sum(1 for (t, a, b) in recs if t == d["tid"] and a < e0 and b > s0)
+        assert fetched == hmet["num_reads"]

@@ -29,7 +29,7 @@ SYMBOLS = [
     "vtx_set_barcodes", "vtx_submit", "vtx_submit_device", "vtx_submit_device_ex", "vtx_finish",
     "vtx_finish_device", "vtx_fetch", "vtx_sync", "vtx_wait_copies", "vtx_score_pairs", "vtx_pack_umi", "vtx_last_timing", "vtx_last_tile_counts",
     "vtx_comm_unique_id", "vtx_comm_init", "vtx_gather", "vtx_gather_start", "vtx_gather_wait",
-    "vtx_submit2", "vtx_submit2_device", "vtx_pack_cb", "vtx_bgzf_inflate",
+    "vtx_submit2", "vtx_submit2_device", "vtx_pack_cb", "vtx_bgzf_inflate", "vtx_submit_bam", "vtx_bam_metrics_get",
 ]
 NO_CB_KEY = 0xFFFFFFFFFFFFFFFF
 CB_EXOTIC = 0x8000000000000000

@@ -244,6 +244,53 @@ public:
         if (!bulk_blocks_.empty()) { bulk_begin_ = bulk_blocks_.front().coff; bulk_end_ = bulk_blocks_.back().next; }
         return true;
     }
+    // The members that start in [coff_begin, coff_last], NOT inflated: descriptors with out_off = running sum of ISIZE (one
+    // contiguous stream), payloads packed on 8-byte boundaries into `comp` (16 readable bytes behind the last one), and for
+    // every member its file offset -> stream offset (`index`, ascending; the last entry is (end of the last member, total)).
+    struct MemberRef { uint64_t coff, stream_off; };
+    bool read_members(uint64_t coff_begin, uint64_t coff_last, std::vector<vtx_bgzf_block>* desc, std::vector<uint8_t>* comp, std::vector<MemberRef>* index)
+    {
+        desc->clear(); comp->clear(); index->clear();
+        if (coff_begin >= size_ || coff_last < coff_begin) { index->push_back({ coff_begin, 0 }); comp->resize(16, 0); return true; }
+        const uint64_t t0 = StageClock::now();
+        const uint64_t want_end = std::min<uint64_t>(size_, coff_last + (1u << 16) + 64);
+        bulk_file_.resize(size_t(want_end - coff_begin));
+        if (pread(fd_, bulk_file_.data(), bulk_file_.size(), off_t(coff_begin)) != ssize_t(bulk_file_.size())) return fail(coff_begin, "truncated file (bulk read)");
+        uint64_t pos = 0, out_off = 0;
+        while (coff_begin + pos <= coff_last && coff_begin + pos < size_) {
+            const uint8_t* h = bulk_file_.data() + pos;
+            const uint64_t coff = coff_begin + pos;
+            if (pos + 18 > bulk_file_.size()) return fail(coff, "truncated file (short read of the member header)");
+            if (h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4)) return fail(coff, "not a BGZF member (bad gzip magic)");
+            const uint32_t xlen = rd16(h + 10);
+            uint32_t bsize = 0; bool have_bc = false;
+            for (uint32_t q = 0; q + 4 <= xlen && pos + 12 + q + 4 <= bulk_file_.size();) {
+                const uint32_t slen = rd16(h + 12 + q + 2);
+                if (h[12 + q] == 66 && h[12 + q + 1] == 67 && slen == 2 && q + 6 <= xlen) { bsize = rd16(h + 12 + q + 4); have_bc = true; }
+                q += 4 + slen;
+            }
+            if (!have_bc) return fail(coff, "gzip member without the BGZF 'BC' field");
+            const uint32_t total = bsize + 1;
+            if (total < 12 + xlen + 8) return fail(coff, "BSIZE smaller than the member header");
+            if (pos + total > bulk_file_.size()) return fail(coff, "truncated file (short read of the member body)");
+            const uint32_t clen = total - 12 - xlen - 8;
+            const uint32_t crc = rd32(h + total - 8), isize = rd32(h + total - 4);
+            if (isize > (1u << 16)) return fail(coff, "ISIZE above 64 KiB");
+            while (comp->size() & 7) comp->push_back(0);
+            vtx_bgzf_block d{};
+            d.in_off = comp->size(); d.in_len = clen; d.out_len = isize; d.out_off = out_off; d.crc32 = crc;
+            comp->insert(comp->end(), h + 12 + xlen, h + 12 + xlen + clen);
+            desc->push_back(d);
+            index->push_back({ coff, out_off });
+            out_off += isize;
+            pos += total;
+        }
+        index->push_back({ coff_begin + pos, out_off });
+        comp->resize(comp->size() + 16, 0);
+        StageClock& clk = stage_clock();
+        clk.read_ns += StageClock::now() - t0; clk.blocks += desc->size(); clk.inflated_bytes += out_off;
+        return true;
+    }
 private:
     struct BulkBlock { uint64_t coff, next, out_off; uint32_t len; };
     std::vector<BulkBlock> bulk_blocks_;
@@ -505,6 +552,34 @@ public:
         for (int64_t k = 4681 + (beg >> 14); k <= 4681 + (e1 >> 14); ++k) add_bin(uint32_t(k));
         if (lo == ~0ull) return false;
         *c_first = lo >> 16; *c_last = hi >> 16;
+        return true;
+    }
+    // The index chunks a fetch(tid, beg, end) walks, as virtual-offset pairs (starts clamped to the linear index like fetch
+    // does); every start and end is a record boundary.  Appends to `out`.
+    void region_chunks(int tid, int64_t beg, int64_t end, std::vector<BaiChunk>* out) const
+    {
+        if (tid < 0 || size_t(tid) >= refs_.size() || end <= beg) return;
+        if (beg < 0) beg = 0;
+        const BaiRef& r = refs_[size_t(tid)];
+        uint64_t min_off = 0;
+        if (!r.linear.empty()) { size_t w = size_t(beg >> 14); if (w >= r.linear.size()) w = r.linear.size() - 1; min_off = r.linear[w]; }
+        const int64_t e1 = end - 1;
+        auto add_bin = [&](uint32_t bin) {
+            auto it = std::lower_bound(r.bin_ids.begin(), r.bin_ids.end(), bin);
+            if (it == r.bin_ids.end() || *it != bin) return;
+            for (const BaiChunk& c : r.bin_chunks[size_t(it - r.bin_ids.begin())])
+                if (c.end > min_off) out->push_back({ std::max(c.beg, min_off), c.end });
+        };
+        add_bin(0);
+        for (int64_t k = 1 + (beg >> 26); k <= 1 + (e1 >> 26); ++k) add_bin(uint32_t(k));
+        for (int64_t k = 9 + (beg >> 23); k <= 9 + (e1 >> 23); ++k) add_bin(uint32_t(k));
+        for (int64_t k = 73 + (beg >> 20); k <= 73 + (e1 >> 20); ++k) add_bin(uint32_t(k));
+        for (int64_t k = 585 + (beg >> 17); k <= 585 + (e1 >> 17); ++k) add_bin(uint32_t(k));
+        for (int64_t k = 4681 + (beg >> 14); k <= 4681 + (e1 >> 14); ++k) add_bin(uint32_t(k));
+    }
+    bool read_members(uint64_t c_first, uint64_t c_last, std::vector<vtx_bgzf_block>* desc, std::vector<uint8_t>* comp, std::vector<Bgzf::MemberRef>* index)
+    {
+        if (!bg_.read_members(c_first, c_last, desc, comp, index)) { if (bg_.bad()) fail(bg_.error()); return false; }
         return true;
     }
     bool prefetch_bulk(uint64_t c_first, uint64_t c_last, const Bgzf::BulkInflate& fn)

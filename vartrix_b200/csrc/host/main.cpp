@@ -48,7 +48,7 @@ struct Opts {
     std::string scoring = "consensus", bam_tag = "CB", valid_chars = "ATGCatgc", dump_staged;
     long padding = 100, threads = 1, mapq = 0, device = 0, shard_loci = 0;      // 0: chosen from the number of loci and threads
     std::vector<int> devices;          // --devices: the loci are sharded over these GPUs (contiguous ranges, main.rs:250-254)
-    bool primary = false, no_dups = false, umi = false, ref_matrix_given = false, gpu_inflate = false;
+    bool primary = false, no_dups = false, umi = false, ref_matrix_given = false, gpu_inflate = false, gpu_stage = false;
 };
 
 void usage()
@@ -76,6 +76,8 @@ void usage()
          "      --device INT            CUDA device ordinal [0]\n"
          "      --devices LIST          Shard the loci over several GPUs: e.g. 0-7 or 0,2,5 (one NCCL gather at the end)\n"
          "      --shard-loci INT        VCF records per staged shard [up to 2048, fewer for short VCFs]\n"
+         "      --gpu-stage             Decode the BAM on the GPU: the host only reads the compressed ranges the loci's index chunks\n"
+         "                              span; inflate, record scan, fetch, record filters and tag extraction run on the device\n"
          "      --gpu-inflate           Inflate the BGZF members of every shard on the GPU (one call per shard) instead of on\n"
          "                              the staging threads; for hosts with few cores per GPU\n"
          "      --dump-staged FILE      Stage only, write the shards to FILE (no GPU)");
@@ -134,6 +136,7 @@ bool parse(int argc, char** argv, Opts* o)
         else if (a == "--shard-loci") o->shard_loci = atol(v().c_str());
         else if (a == "--dump-staged") o->dump_staged = v();
         else if (a == "--gpu-inflate") o->gpu_inflate = true;
+        else if (a == "--gpu-stage") o->gpu_stage = true;
         else if (a == "-h" || a == "--help") { usage(); exit(0); }
         else if (a == "-V" || a == "--version") { puts("vartrix_b200 0.1 (vartrix 1.1.22 surface)"); exit(0); }
         else { fprintf(stderr, "error: unknown argument %s\n", argv[i]); return false; }
@@ -272,6 +275,7 @@ struct Lane {
     std::string err;
     int rc = 0;
     vtx_result dev{};                   // this lane's triplets on its device
+    Fasta fb_fa; BamFile fb_bam; bool fb_open = false; size_t host_fallbacks = 0;    // --gpu-stage: shards the device sent back
 };
 
 int main(int argc, char** argv)
@@ -383,6 +387,8 @@ int main(int argc, char** argv)
             if (lanes[d].lo + i < lanes[d].hi) { order.push_back(lanes[d].lo + i); lane_of[lanes[d].lo + i] = d; --left; }
 
     std::vector<std::unique_ptr<StagedShard>> ready(n_shards);
+    std::vector<std::unique_ptr<DeviceShard>> ready_dev(n_shards);         // --gpu-stage: the host's share of a device-staged shard
+    const bool gpu_stage = o.gpu_stage;          // with --dump-staged: the host's share of device-staged shards is dumped ("VTXD")
     std::mutex mu; std::condition_variable cv;
     std::atomic<size_t> next{ 0 };
     const size_t window = std::max<size_t>(2, (size_t(o.threads) * 2 + 2 + n_dev - 1) / n_dev);
@@ -425,10 +431,23 @@ int main(int argc, char** argv)
             const size_t k = order[i];
             Lane& ln = lanes[lane_of[k]];
             { std::unique_lock<std::mutex> g(mu); cv.wait(g, [&] { return failed || k - ln.lo < ln.consumed + window; }); if (failed) return; }
+            const size_t lo = k * size_t(o.shard_loci), hi = std::min(recs.size(), lo + size_t(o.shard_loci));
+            if (gpu_stage) {
+                auto ds = std::make_unique<DeviceShard>();
+                bool supported = true;
+                const uint64_t t_stage = StageClock::now();
+                const bool ok = stage_loci_device(recs, lo, hi, fa, bam, sa_w, ds.get(), &supported, &e);
+                stage_ns += StageClock::now() - t_stage;
+                if (!ok) { std::lock_guard<std::mutex> g(mu); failed = true; fail_msg = e; cv.notify_all(); return; }
+                if (supported) {
+                    { std::lock_guard<std::mutex> g(mu); ready_dev[k] = std::move(ds); }
+                    cv.notify_all();
+                    continue;
+                }
+            }
             std::unique_ptr<StagedShard> sh;
             { std::lock_guard<std::mutex> g(mu); if (!recycled.empty()) { sh = std::move(recycled.back()); recycled.pop_back(); } }
             if (!sh) sh = std::make_unique<StagedShard>();
-            const size_t lo = k * size_t(o.shard_loci), hi = std::min(recs.size(), lo + size_t(o.shard_loci));
             const uint64_t t_stage = StageClock::now();
             const bool staged_ok = stage_loci(recs, lo, hi, fa, bam, sa_w, umis, sh.get(), &e);
             stage_ns += StageClock::now() - t_stage;
@@ -453,14 +472,42 @@ int main(int argc, char** argv)
         if (!dumping && engine_ready[size_t(ln.rank)].get() != 0) { ln.rc = 1; std::lock_guard<std::mutex> g(mu); failed = true; cv.notify_all(); return; }
         for (size_t k = ln.lo; k < ln.hi && ln.rc == 0; ++k) {
             std::unique_ptr<StagedShard> sh;
+            std::unique_ptr<DeviceShard> ds;
             {
                 std::unique_lock<std::mutex> g(mu);
-                cv.wait(g, [&] { return failed || ready[k]; });
+                cv.wait(g, [&] { return failed || ready[k] || ready_dev[k]; });
                 if (failed) { ln.rc = 1; break; }
-                sh = std::move(ready[k]);
+                sh = std::move(ready[k]); ds = std::move(ready_dev[k]);
                 ln.consumed = k - ln.lo + 1;
             }
             cv.notify_all();
+            if (ds && dump) {                   // test dump of the host's share: loci, member table, compressed bytes, record boundaries
+                auto put = [&](const void* p, size_t bytes) { uint64_t n = bytes; fwrite(&n, 8, 1, dump); if (bytes) fwrite(p, 1, bytes, dump); };
+                fwrite("VTXD", 1, 4, dump);
+                const int64_t tid64 = ds->tid;
+                put(&tid64, 8);
+                put(ds->locus_row.data(), ds->locus_row.size() * 4); put(ds->locus_start.data(), ds->locus_start.size() * 8); put(ds->locus_end.data(), ds->locus_end.size() * 8);
+                put(ds->members.data(), ds->members.size() * sizeof(vtx_bgzf_block)); put(ds->comp.data(), ds->comp.size()); put(ds->entry_off.data(), ds->entry_off.size() * 8);
+                continue;
+            }
+            if (ds) {
+                vtx_bam_shard bs;
+                ds->fill(&bs, sa);
+                const int brc = vtx_submit_bam(ln.ctx, &bs);
+                if (brc == VTX_OK) { ln.hm.add(ds->met); continue; }
+                if (brc != VTX_E_UNSUPPORTED) { ln.err = vtx_last_error(ln.ctx); ln.rc = 1; break; }
+                // a shard the device cannot key (e.g. a UB string outside vtx_pack_umi's alphabet): stage it here, on the host
+                if (!ln.fb_open) {
+                    std::string e;
+                    if (!ln.fb_fa.open(o.fasta, &e) || !ln.fb_bam.open(o.bam, &e)) { ln.err = e; ln.rc = 1; break; }
+                    ln.fb_open = true;
+                }
+                sh = std::make_unique<StagedShard>();
+                std::string e;
+                const size_t lo = k * size_t(o.shard_loci), hi = std::min(recs.size(), lo + size_t(o.shard_loci));
+                if (!stage_loci(recs, lo, hi, ln.fb_fa, ln.fb_bam, sa, umis, sh.get(), &e)) { ln.err = e; ln.rc = 1; break; }
+                ++ln.host_fallbacks;
+            }
             ln.hm.add(sh->met);
             auto recycle = [&]() { sh->clear(); std::lock_guard<std::mutex> g(mu); recycled.push_back(std::move(sh)); };
             if (dump) { dump_shard(dump, *sh); recycle(); continue; }
@@ -492,7 +539,18 @@ int main(int argc, char** argv)
     }
     int rc = 0;
     HostMetrics hm;
-    for (Lane& ln : lanes) { hm.add(ln.hm); if (ln.rc) rc = 1; }
+    for (Lane& ln : lanes) {
+        hm.add(ln.hm);
+        if (ln.rc) rc = 1;
+        if (gpu_stage && ln.ctx && !ln.rc) {          // the record-filter counters of the shards the device staged
+            vtx_bam_metrics bm{};
+            if (vtx_bam_metrics_get(ln.ctx, &bm) == VTX_OK) {
+                hm.num_reads += bm.num_reads; hm.num_low_mapq += bm.num_low_mapq; hm.num_non_primary += bm.num_non_primary;
+                hm.num_duplicates += bm.num_duplicates; hm.num_not_useful += bm.num_not_useful;
+            }
+            if (ln.host_fallbacks) LOG_INFO("GPU %d: %zu shard(s) staged on the host after the device declined them", ln.device, ln.host_fallbacks);
+        }
+    }
     if (rc) { std::lock_guard<std::mutex> g(mu); failed = true; }
     cv.notify_all();
     for (auto& t : pool) t.join();

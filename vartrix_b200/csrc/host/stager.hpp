@@ -210,6 +210,93 @@ private:
     size_t n_ = 0;
 };
 
+// What the host keeps doing when the device stages the reads itself (vtx_submit_bam): windows from the FASTA, the compressed
+// byte range of the loci's index chunks, the BGZF member table, the record boundaries the index knows.
+struct DeviceShard {
+    std::vector<uint32_t> locus_row, ref_off, ref_len, alt_off, alt_len;
+    std::vector<int64_t> locus_start, locus_end;
+    std::vector<uint8_t> hap_bytes, comp;
+    std::vector<vtx_bgzf_block> members;
+    std::vector<uint64_t> entry_off;
+    int32_t tid = -1;
+    HostMetrics met;             // only the per-record counters the host still owns: multi-allelic / invalid records
+    void fill(vtx_bam_shard* b, const StageArgs& a) const
+    {
+        memset(b, 0, sizeof(*b));
+        b->n_loci = uint32_t(locus_row.size()); b->locus_row = locus_row.data(); b->locus_start = locus_start.data(); b->locus_end = locus_end.data();
+        b->hap_bytes = hap_bytes.data(); b->hap_bytes_len = hap_bytes.size();
+        b->ref_off = ref_off.data(); b->ref_len = ref_len.data(); b->alt_off = alt_off.data(); b->alt_len = alt_len.data();
+        b->tid = tid; b->n_members = uint32_t(members.size()); b->members = members.data(); b->comp = comp.data(); b->comp_len = comp.empty() ? 0 : comp.size() - 16;
+        b->n_entry = uint32_t(entry_off.size()); b->entry_off = entry_off.data();
+        b->mapq = a.mapq; b->primary_only = a.primary_only; b->no_duplicates = a.no_duplicates; b->bam_tag[0] = a.bam_tag[0]; b->bam_tag[1] = a.bam_tag[1];
+    }
+};
+
+// Records [lo, hi) of the VCF -> the host's share of a device-staged shard.  `*supported` = false (and nothing else done) when
+// the loci are not ascending on one contig: such shards are staged on the host.
+inline bool stage_loci_device(const std::vector<VcfRecord>& recs, size_t lo, size_t hi, const Fasta& fa, BamFile& bam,
+                              const StageArgs& a, DeviceShard* out, bool* supported, std::string* err)
+{
+    *supported = true;
+    for (size_t i = lo + 1; i < hi; ++i)
+        if (recs[i].chrom != recs[lo].chrom || recs[i].pos0 < recs[i - 1].pos0) { *supported = false; return true; }
+    *out = DeviceShard();
+    if (hi <= lo) return true;
+    out->tid = bam.tid_of(recs[lo].chrom);
+    std::string ref_hap, alt_hap;
+    std::vector<BaiChunk> chunks;
+    for (size_t i = lo; i < hi; ++i) {
+        const VcfRecord& v = recs[i];
+        const int64_t start = v.pos0, end = v.pos0 + int64_t(v.alleles[0].size());      // main.rs:619-623
+        if (v.alleles.size() > 2) { out->met.num_multiallelic_recs++; continue; }       // main.rs:646-653
+        const std::string alt = v.alleles.size() == 2 ? v.alleles[1] : std::string();   // main.rs:656-659
+        const int64_t L = fa.length(v.chrom);
+        if (L < 0) { *err = "Requested chromosome " + v.chrom + " was not found in fasta"; return false; }
+        const int64_t w0 = std::max<int64_t>(start - a.padding, 0), w1 = std::min(end + a.padding, L);
+        if (end > L || !fa.fetch_upper(v.chrom, w0, w1, &ref_hap)) { *err = "FASTA fetch failed at " + v.chrom + ":" + std::to_string(v.pos0); return false; }
+        alt_hap.assign(ref_hap, 0, size_t(start - w0));
+        alt_hap += alt;
+        alt_hap.append(ref_hap, size_t(end - w0), std::string::npos);
+        bool ok = true;
+        for (unsigned char c : alt_hap) if (!a.valid[c]) { ok = false; break; }         // main.rs:675-684
+        if (!ok) { out->met.num_invalid_recs++; continue; }
+        out->locus_row.push_back(uint32_t(i)); out->locus_start.push_back(start); out->locus_end.push_back(end);
+        pad16(out->hap_bytes); out->ref_off.push_back(uint32_t(out->hap_bytes.size())); out->ref_len.push_back(uint32_t(ref_hap.size()));
+        out->hap_bytes.insert(out->hap_bytes.end(), ref_hap.begin(), ref_hap.end());
+        pad16(out->hap_bytes); out->alt_off.push_back(uint32_t(out->hap_bytes.size())); out->alt_len.push_back(uint32_t(alt_hap.size()));
+        out->hap_bytes.insert(out->hap_bytes.end(), alt_hap.begin(), alt_hap.end());
+        bam.region_chunks(out->tid, start, end, &chunks);
+    }
+    pad16(out->hap_bytes);
+    if (chunks.empty()) return true;                                  // no locus has any indexed read: nothing to inflate
+    uint64_t v_first = ~0ull, v_last = 0;
+    for (const BaiChunk& c : chunks) { v_first = std::min(v_first, c.beg); v_last = std::max(v_last, c.end); }
+    std::vector<Bgzf::MemberRef> index;
+    if (!bam.read_members(v_first >> 16, v_last >> 16, &out->members, &out->comp, &index)) { *err = bam.error(); return false; }
+    // virtual offset -> offset in the inflated stream
+    auto stream_of = [&](uint64_t voff, uint64_t* so) -> bool {
+        const uint64_t coff = voff >> 16, uoff = voff & 0xFFFF;
+        auto it = std::lower_bound(index.begin(), index.end(), coff, [](const Bgzf::MemberRef& m, uint64_t c) { return m.coff < c; });
+        if (it == index.end() || it->coff != coff) return false;
+        *so = it->stream_off + uoff;
+        return *so <= index.back().stream_off;
+    };
+    std::vector<uint64_t>& e = out->entry_off;
+    for (const BaiChunk& c : chunks) {
+        uint64_t so;
+        if (!stream_of(c.beg, &so)) { *err = "BAM index points outside a BGZF member (index and file do not match)"; return false; }
+        e.push_back(so);
+    }
+    uint64_t s_end;
+    if (!stream_of(v_last, &s_end)) { *err = "BAM index points outside a BGZF member (index and file do not match)"; return false; }
+    e.push_back(s_end);
+    std::sort(e.begin(), e.end());
+    e.erase(std::unique(e.begin(), e.end()), e.end());
+    while (!e.empty() && e.back() > s_end) e.pop_back();
+    if (e.size() < 2) e.clear();
+    return true;
+}
+
 // Records [lo, hi) of the VCF -> one shard.  Mirrors evaluate_rec + the head of evaluate_alns.
 inline bool stage_loci(const std::vector<VcfRecord>& recs, size_t lo, size_t hi, const Fasta& fa, BamFile& bam,
                        const StageArgs& a, UmiInterner& umis, StagedShard* out, std::string* err)

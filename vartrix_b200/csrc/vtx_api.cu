@@ -5,6 +5,7 @@
 #include "vtx_sw.cuh"
 #include "vtx_sw_band.cuh"
 #include "vtx_inflate.cuh"
+#include "vtx_stage.cuh"
 
 #include <nvtx3/nvToolsExt.h>     // header-only; ranges cost nothing unless a profiler (nsys / ncu --nvtx) is attached
 
@@ -53,6 +54,16 @@ struct InSlot {
     bool used = false;
 };
 
+// device buffers of one shard staged on the device (vtx_submit_bam); two slots: shard k+1 is inflated and scanned while the
+// Smith-Waterman kernels of shard k still read shard k's stream
+struct StageSlot {
+    DBuf comp, desc, status, stream, entry, seg_count, seg_first, rec_off, rec_tid, rec_pos, rec_end, rec_fm, l_start, l_end,
+        locus_row, hap, ref_off, ref_len, alt_off, alt_len, cand_count, cand_first, cand_rec, used, read_off, read_len,
+        read_cb_off, read_cb_len, read_umi, cand_start, scalars;
+    cudaEvent_t staged = nullptr, free_ev = nullptr;
+    bool used_once = false;
+};
+
 }  // namespace
 
 struct vtx_ctx {
@@ -70,6 +81,12 @@ struct vtx_ctx {
     DBuf x_read_off, x_read_len, x_units, x_off4;      // slim layout expanded to the internal read arrays
     DBuf band_scratch;                                  // VTX_BAND_MODEL work buffers, one slice per resident warp
     DBuf inf_comp, inf_out, inf_desc, inf_status;       // vtx_bgzf_inflate
+    StageSlot sslot[2];                                 // vtx_submit_bam
+    uint64_t n_bam_submits = 0;
+    cudaStream_t stage_stream = nullptr;
+    DBuf bam_metrics;                                   // stage::LocusMetrics, cumulative
+    DBuf stage_sums;                                    // block sums of the scans on the staging stream
+    uint64_t* h_stage = nullptr;                        // pinned scalars read back between the staging phases
     uint32_t bc_cap = 0, n_barcodes = 0;
     bool have_barcodes = false;
 
@@ -835,6 +852,18 @@ void vtx_destroy(vtx_ctx* ctx)
                     &ctx->r_alt, &ctx->r_unk, &ctx->r_val, &ctx->r_val2, &ctx->g_counts };
     for (DBuf* b : all) if (b->p) cudaFree(b->p);
     for (auto& b : ctx->g_dev) if (b.p) cudaFree(b.p);
+    if (ctx->stage_stream) { cudaStreamSynchronize(ctx->stage_stream); cudaStreamDestroy(ctx->stage_stream); }
+    for (auto& ss : ctx->sslot) {
+        DBuf* sb[] = { &ss.comp, &ss.desc, &ss.status, &ss.stream, &ss.entry, &ss.seg_count, &ss.seg_first, &ss.rec_off, &ss.rec_tid, &ss.rec_pos, &ss.rec_end,
+                       &ss.rec_fm, &ss.l_start, &ss.l_end, &ss.locus_row, &ss.hap, &ss.ref_off, &ss.ref_len, &ss.alt_off, &ss.alt_len, &ss.cand_count,
+                       &ss.cand_first, &ss.cand_rec, &ss.used, &ss.read_off, &ss.read_len, &ss.read_cb_off, &ss.read_cb_len, &ss.read_umi, &ss.cand_start, &ss.scalars };
+        for (DBuf* b : sb) if (b->p) cudaFree(b->p);
+        if (ss.staged) cudaEventDestroy(ss.staged);
+        if (ss.free_ev) cudaEventDestroy(ss.free_ev);
+    }
+    if (ctx->bam_metrics.p) cudaFree(ctx->bam_metrics.p);
+    if (ctx->stage_sums.p) cudaFree(ctx->stage_sums.p);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     for (void* h : ctx->h_res) if (h) cudaFreeHost(h);
     for (void* h : ctx->g_host) if (h) cudaFreeHost(h);
     if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
@@ -1121,6 +1150,205 @@ int vtx_bgzf_inflate(vtx_ctx* ctx, const vtx_bgzf_block* blocks, uint32_t n_bloc
     CK(cudaStreamSynchronize(st));
     for (uint32_t i = 0; i < n_blocks; ++i)
         if (status[i] != 0) return set_err(ctx, VTX_E_INVALID, "vtx_bgzf_inflate: member %u failed with decoder status %d (corrupt data)", i, status[i]);
+    return VTX_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// vtx_submit_bam: inflate + record scan + fetch + filters + tags on the device (vtx_inflate.cuh, vtx_stage.cuh)
+// -------------------------------------------------------------------------------------------------
+namespace {
+int scan_u32_on(vtx_ctx* ctx, cudaStream_t st, const uint32_t* in, uint64_t n, uint32_t* out, DBuf& sums)
+{
+    const unsigned nb = std::max(1u, blocks_for(n, kScanTile));
+    int rc = ensure(ctx, sums, size_t(nb) * 4);
+    if (rc) return rc;
+    vtx_k_scan_tiles<<<nb, kScanThreads, 0, st>>>(in, n, out, P<uint32_t>(sums));
+    vtx_k_scan_sums<<<1, kScanThreads, 0, st>>>(P<uint32_t>(sums), nb, out + n);
+    vtx_k_scan_add<<<nb, kScanThreads, 0, st>>>(out, n, P<uint32_t>(sums));
+    CK(cudaGetLastError());
+    return VTX_OK;
+}
+}  // namespace
+
+int vtx_submit_bam(vtx_ctx* ctx, const vtx_bam_shard* sh)
+{
+    if (!ctx) return VTX_E_INVALID;
+    Nvtx nvtx_range("vtx_submit_bam");
+    if (!ctx->have_barcodes) return set_err(ctx, VTX_E_STATE, "vtx_set_barcodes must be called before vtx_submit_bam");
+    if (!sh) return set_err(ctx, VTX_E_INVALID, "shard is NULL");
+    const uint32_t nl = sh->n_loci, nm = sh->n_members, ne = sh->n_entry;
+    if (nl && (!sh->locus_row || !sh->locus_start || !sh->locus_end || !sh->ref_off || !sh->ref_len || !sh->alt_off || !sh->alt_len))
+        return set_err(ctx, VTX_E_INVALID, "vtx_submit_bam: locus arrays missing");
+    if (nm && (!sh->members || !sh->comp)) return set_err(ctx, VTX_E_INVALID, "vtx_submit_bam: members missing");
+    if ((ne == 1) || (ne && !sh->entry_off)) return set_err(ctx, VTX_E_INVALID, "vtx_submit_bam: entry_off needs at least a start and an end");
+    if (sh->hap_bytes_len >= 0xFFFFFFFFull) return set_err(ctx, VTX_E_INVALID, "haplotype pool exceeds 4 GiB; split the shard");
+    uint64_t stream_len = 0;
+    uint32_t max_hap = 0;
+    for (uint32_t i = 0; i < nm; ++i) {
+        const vtx_bgzf_block& b = sh->members[i];
+        if ((b.in_off & 3) || b.in_off + b.in_len > sh->comp_len || b.out_len > 65536u || b.out_off != stream_len)
+            return set_err(ctx, VTX_E_INVALID, "vtx_submit_bam: member %u: payload on a 4-byte boundary inside comp, out_off = running sum of out_len", i);
+        stream_len += b.out_len;
+    }
+    if (stream_len >= 0xFFFFFFFFull) return set_err(ctx, VTX_E_INVALID, "vtx_submit_bam: more than 4 GiB of records in one shard; split the shard");
+    for (uint32_t i = 0; i < ne; ++i)
+        if (sh->entry_off[i] > stream_len || (i && sh->entry_off[i] <= sh->entry_off[i - 1])) return set_err(ctx, VTX_E_INVALID, "vtx_submit_bam: entry_off must ascend inside the stream");
+    for (uint32_t l = 0; l < nl; ++l) {
+        if ((sh->ref_off[l] & 15) || (sh->alt_off[l] & 15) || uint64_t(sh->ref_off[l]) + sh->ref_len[l] > sh->hap_bytes_len ||
+            uint64_t(sh->alt_off[l]) + sh->alt_len[l] > sh->hap_bytes_len) return set_err(ctx, VTX_E_INVALID, "vtx_submit_bam: locus %u: bad haplotype window", l);
+        if (l && (sh->locus_row[l] <= sh->locus_row[l - 1])) return set_err(ctx, VTX_E_INVALID, "locus_row must be strictly ascending (locus %u)", l);
+        max_hap = std::max(max_hap, std::max(sh->ref_len[l], sh->alt_len[l]));
+    }
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->stage_stream) {
+        CK(cudaStreamCreateWithFlags(&ctx->stage_stream, cudaStreamNonBlocking));
+        for (auto& ss : ctx->sslot) { CK(cudaEventCreateWithFlags(&ss.staged, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ss.free_ev, cudaEventDisableTiming)); }
+        ENS(ctx->bam_metrics, sizeof(stage::LocusMetrics));
+        CK(cudaMemsetAsync(ctx->bam_metrics.p, 0, sizeof(stage::LocusMetrics), ctx->stage_stream));
+        CK(cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_stage), 256, cudaHostAllocDefault));
+    }
+    cudaStream_t ss = ctx->stage_stream;
+    StageSlot& sl = ctx->sslot[ctx->n_bam_submits & 1];
+    ++ctx->n_bam_submits;
+    if (sl.used_once) CK(cudaEventSynchronize(sl.free_ev));       // the kernels that read this slot's stream two shards ago are done
+    sl.used_once = true;
+    TimeRec* tr = new_trec(ctx);
+    if (!tr) return set_err(ctx, VTX_E_CUDA, "cudaEventCreate failed");
+    auto fail_out = [&](int code) { --ctx->trec_used; sl.used_once = false; return code; };
+
+    // ---- copies (staging stream) ----
+    auto up = [&](DBuf& d, const void* h, size_t bytes) -> int {
+        int rc = ensure(ctx, d, bytes ? bytes + 16 : 16);
+        if (rc) return rc;
+        if (bytes && cudaMemcpyAsync(d.p, h, bytes, cudaMemcpyHostToDevice, ss) != cudaSuccess) return set_err(ctx, VTX_E_CUDA, "cudaMemcpyAsync failed in vtx_submit_bam");
+        return VTX_OK;
+    };
+    CK(cudaEventRecord(tr->ev[EV_START], ss));
+    int rc;
+    if ((rc = up(sl.comp, sh->comp, sh->comp_len)) || (rc = up(sl.desc, sh->members, size_t(nm) * sizeof(vtx_bgzf_block))) ||
+        (rc = up(sl.entry, sh->entry_off, size_t(ne) * 8)) || (rc = up(sl.l_start, sh->locus_start, size_t(nl) * 8)) ||
+        (rc = up(sl.l_end, sh->locus_end, size_t(nl) * 8)) || (rc = up(sl.locus_row, sh->locus_row, size_t(nl) * 4)) ||
+        (rc = up(sl.hap, sh->hap_bytes, sh->hap_bytes_len)) || (rc = up(sl.ref_off, sh->ref_off, size_t(nl) * 4)) ||
+        (rc = up(sl.ref_len, sh->ref_len, size_t(nl) * 4)) || (rc = up(sl.alt_off, sh->alt_off, size_t(nl) * 4)) ||
+        (rc = up(sl.alt_len, sh->alt_len, size_t(nl) * 4))) return fail_out(rc);
+    CK(cudaMemsetAsync(static_cast<uint8_t*>(sl.comp.p) + sh->comp_len, 0, 16, ss));
+    CK(cudaEventRecord(tr->ev[EV_H2D], ss));
+    tr->had_h2d = true;
+    // ---- inflate into one contiguous stream ----
+    ENS(sl.stream, size_t(stream_len) + 64); ENS(sl.status, size_t(nm) * 4 + 16); ENS(sl.scalars, 256);
+    uint32_t* d_sc = P<uint32_t>(sl.scalars);       // [0] walk cursor / inflate cursor, [1] err, [2] max_span, [3] max read, [4..] spare
+    CK(cudaMemsetAsync(sl.scalars.p, 0, 256, ss));
+    if (nm) {
+        const unsigned ctas = unsigned(std::min<uint64_t>((nm + inflate::kInflateWarps - 1) / inflate::kInflateWarps, uint64_t(ctx->n_sm) * 6));
+        inflate::vtx_k_bgzf_inflate<<<ctas, inflate::kInflateWarps * 32, 0, ss>>>(P<inflate::BlockDesc>(sl.desc), nm, P<uint8_t>(sl.comp), P<uint8_t>(sl.stream),
+                                                                                 P<int32_t>(sl.status), d_sc, 1);
+        CK(cudaGetLastError());
+    }
+    stage::Params sp{};
+    sp.s = P<uint8_t>(sl.stream); sp.s_len = stream_len; sp.tid = sh->tid; sp.mapq_min = sh->mapq; sp.primary_only = sh->primary_only;
+    sp.no_duplicates = sh->no_duplicates; sp.want_umi = ctx->cfg.use_umi ? 1 : 0; sp.tag0 = uint8_t(sh->bam_tag[0]); sp.tag1 = uint8_t(sh->bam_tag[1]);
+    // ---- record boundaries ----
+    const uint32_t n_seg = ne ? ne - 1 : 0;
+    ENS(sl.seg_count, size_t(n_seg + 1) * 4); ENS(sl.seg_first, size_t(n_seg + 2) * 4);
+    uint32_t n_rec = 0;
+    std::vector<int32_t> h_status(nm);
+    if (n_seg) {
+        stage::vtx_k_walk<<<blocks_for(n_seg, 64), 64, 0, ss>>>(sp, n_seg, P<uint64_t>(sl.entry), 0, P<uint32_t>(sl.seg_count), nullptr, nullptr, d_sc + 1);
+        rc = scan_u32_on(ctx, ss, P<uint32_t>(sl.seg_count), n_seg, P<uint32_t>(sl.seg_first), ctx->stage_sums);
+        if (rc) return fail_out(rc);
+    }
+    // wait #1 (staging stream only): inflate status, walk errors, number of records
+    uint32_t* hs = reinterpret_cast<uint32_t*>(ctx->h_stage);
+    if (n_seg) CK(cudaMemcpyAsync(hs, P<uint32_t>(sl.seg_first) + n_seg, 4, cudaMemcpyDeviceToHost, ss)); else hs[0] = 0;
+    CK(cudaMemcpyAsync(hs + 1, d_sc + 1, 4, cudaMemcpyDeviceToHost, ss));
+    if (nm) CK(cudaMemcpyAsync(h_status.data(), sl.status.p, size_t(nm) * 4, cudaMemcpyDeviceToHost, ss));
+    CK(cudaStreamSynchronize(ss));
+    for (uint32_t i = 0; i < nm; ++i)
+        if (h_status[i] != 0) return fail_out(set_err(ctx, VTX_E_INVALID, "vtx_submit_bam: BGZF member %u failed with decoder status %d (corrupt data)", i, h_status[i]));
+    if (hs[1] & (stage::kErrWalk | stage::kErrRecord))
+        return fail_out(set_err(ctx, VTX_E_INVALID, "vtx_submit_bam: the record walk did not land on the index's record boundaries (corrupt BAM record or index; flags %u)", hs[1]));
+    n_rec = hs[0];
+    const size_t nrp = size_t(n_rec) + 1;
+    ENS(sl.rec_off, nrp * 8); ENS(sl.rec_tid, nrp * 4); ENS(sl.rec_pos, nrp * 4); ENS(sl.rec_end, nrp * 4); ENS(sl.rec_fm, nrp * 4); ENS(sl.used, nrp * 4);
+    ENS(sl.cand_count, size_t(nl + 1) * 4); ENS(sl.cand_first, size_t(nl + 2) * 4); ENS(sl.cand_start, size_t(nl + 2) * 8);
+    stage::LocusMetrics* d_met = P<stage::LocusMetrics>(ctx->bam_metrics);
+    uint64_t n_cand = 0;
+    uint32_t max_read = 0;
+    if (n_rec) {
+        stage::vtx_k_walk<<<blocks_for(n_seg, 64), 64, 0, ss>>>(sp, n_seg, P<uint64_t>(sl.entry), 1, nullptr, P<uint32_t>(sl.seg_first), P<uint64_t>(sl.rec_off), d_sc + 1);
+        stage::vtx_k_parse<<<blocks_for(n_rec, 256), 256, 0, ss>>>(sp, n_rec, P<uint64_t>(sl.rec_off), P<int32_t>(sl.rec_tid), P<int32_t>(sl.rec_pos),
+                                                                   P<int32_t>(sl.rec_end), P<uint32_t>(sl.rec_fm), d_sc + 2);
+        CK(cudaMemsetAsync(sl.used.p, 0, nrp * 4, ss));
+    }
+    if (nl) {
+        // counts first; the per-locus metric counters of this pass only become final if the shard is accepted, so they go to a scratch copy
+        ENS(sl.status, std::max<size_t>(size_t(nm) * 4 + 16, sizeof(stage::LocusMetrics) + 16));
+        stage::LocusMetrics* d_tmp = reinterpret_cast<stage::LocusMetrics*>(sl.status.p);
+        CK(cudaMemsetAsync(d_tmp, 0, sizeof(stage::LocusMetrics), ss));
+        stage::vtx_k_locus_cands<<<blocks_for(nl, 64), 64, 0, ss>>>(sp, nl, P<int64_t>(sl.l_start), P<int64_t>(sl.l_end), n_rec, P<uint64_t>(sl.rec_off),
+                                                                   P<int32_t>(sl.rec_tid), P<int32_t>(sl.rec_pos), P<int32_t>(sl.rec_end), P<uint32_t>(sl.rec_fm),
+                                                                   d_sc + 2, 0, P<uint32_t>(sl.cand_count), nullptr, nullptr, nullptr, d_tmp);
+        rc = scan_u32_on(ctx, ss, P<uint32_t>(sl.cand_count), nl, P<uint32_t>(sl.cand_first), ctx->stage_sums);
+        if (rc) return fail_out(rc);
+        CK(cudaMemcpyAsync(hs, P<uint32_t>(sl.cand_first) + nl, 4, cudaMemcpyDeviceToHost, ss));
+    } else hs[0] = 0;
+    CK(cudaMemcpyAsync(hs + 1, d_sc + 1, 12, cudaMemcpyDeviceToHost, ss));      // err, max_span, max read
+    CK(cudaStreamSynchronize(ss));                                               // wait #2: number of candidates, longest read
+    n_cand = hs[0]; max_read = hs[3];
+    if (hs[1] & (stage::kErrWalk | stage::kErrRecord)) return fail_out(set_err(ctx, VTX_E_INVALID, "vtx_submit_bam: corrupt BAM record (flags %u)", hs[1]));
+    if (max_read > uint32_t(kMaxRead)) return fail_out(set_err(ctx, VTX_E_UNSUPPORTED, "reads longer than %d bases (biased int16 DP) are not supported (%u)", kMaxRead, max_read));
+    if (n_cand >= 0xFFFFFFF0ull) return fail_out(set_err(ctx, VTX_E_INVALID, "n_cand exceeds 2^32 per shard; split the shard"));
+    const size_t ncp = size_t(n_cand) + 1;
+    ENS(sl.cand_rec, ncp * 4); ENS(sl.read_off, nrp * 8); ENS(sl.read_len, nrp * 4); ENS(sl.read_cb_off, nrp * 4); ENS(sl.read_cb_len, nrp * 2 + 2);
+    if (ctx->cfg.use_umi) ENS(sl.read_umi, nrp * 8);
+    if (nl) {
+        stage::LocusMetrics* d_tmp = reinterpret_cast<stage::LocusMetrics*>(sl.status.p);
+        stage::vtx_k_locus_cands<<<blocks_for(nl, 64), 64, 0, ss>>>(sp, nl, P<int64_t>(sl.l_start), P<int64_t>(sl.l_end), n_rec, P<uint64_t>(sl.rec_off),
+                                                                   P<int32_t>(sl.rec_tid), P<int32_t>(sl.rec_pos), P<int32_t>(sl.rec_end), P<uint32_t>(sl.rec_fm),
+                                                                   d_sc + 2, 1, nullptr, P<uint32_t>(sl.cand_first), P<uint32_t>(sl.cand_rec), P<uint32_t>(sl.used), d_tmp);
+        stage::vtx_k_widen<<<blocks_for(nl + 1, 256), 256, 0, ss>>>(nl + 1, P<uint32_t>(sl.cand_first), P<uint64_t>(sl.cand_start));
+    }
+    if (n_rec)
+        stage::vtx_k_read_emit<<<blocks_for(n_rec, 128), 128, 0, ss>>>(sp, n_rec, P<uint64_t>(sl.rec_off), P<uint32_t>(sl.used), P<uint64_t>(sl.read_off),
+                                                                       P<uint32_t>(sl.read_len), P<uint32_t>(sl.read_cb_off), P<uint16_t>(sl.read_cb_len),
+                                                                       P<uint64_t>(sl.read_umi), d_sc + 1);
+    CK(cudaGetLastError());
+    if (ctx->cfg.use_umi && n_rec) {      // wait #3 only with --umi: a UB string the device cannot key sends the shard back to the host
+        CK(cudaMemcpyAsync(hs + 1, d_sc + 1, 4, cudaMemcpyDeviceToHost, ss));
+        CK(cudaStreamSynchronize(ss));
+        if (hs[1] & stage::kErrExoticUmi) return fail_out(set_err(ctx, VTX_E_UNSUPPORTED, "vtx_submit_bam: a UB tag outside vtx_pack_umi's alphabet needs the host's interner; stage this shard on the host"));
+    }
+    if (nl) {                             // the shard is accepted: its filter counters join the running totals
+        stage::LocusMetrics* d_tmp = reinterpret_cast<stage::LocusMetrics*>(sl.status.p);
+        vtx_k_add_u64<<<1, 32, 0, ss>>>(reinterpret_cast<unsigned long long*>(d_met), reinterpret_cast<const unsigned long long*>(d_tmp), 5);
+    }
+    CK(cudaEventRecord(sl.staged, ss));
+    // ---- the usual pipeline, on the engine stream, reading reads and tags inside the stream ----
+    DevBatch d{};
+    d.n_loci = nl; d.n_reads = n_rec; d.n_cand = n_cand;
+    d.locus_row = P<uint32_t>(sl.locus_row); d.hap = P<uint8_t>(sl.hap); d.ref_off = P<uint32_t>(sl.ref_off); d.ref_len = P<uint32_t>(sl.ref_len);
+    d.alt_off = P<uint32_t>(sl.alt_off); d.alt_len = P<uint32_t>(sl.alt_len); d.cand_start = P<uint64_t>(sl.cand_start);
+    d.read_nib = P<uint8_t>(sl.stream); d.read_off = P<uint64_t>(sl.read_off); d.read_len = P<uint32_t>(sl.read_len);
+    d.cb_bytes = P<uint8_t>(sl.stream); d.read_cb_off = P<uint32_t>(sl.read_cb_off); d.read_cb_len = P<uint16_t>(sl.read_cb_len);
+    d.read_umi = ctx->cfg.use_umi ? P<uint64_t>(sl.read_umi) : nullptr; d.cand_read = P<uint32_t>(sl.cand_rec);
+    d.max_read_len = max_read; d.max_hap_len = max_hap;
+    CK(cudaStreamWaitEvent(ctx->stream, sl.staged, 0));
+    CK(cudaEventRecord(tr->ev[EV_C0], ctx->stream));
+    rc = process_batch(ctx, d, tr);
+    if (rc) return rc;
+    CK(cudaEventRecord(sl.free_ev, ctx->stream));
+    return VTX_OK;
+}
+
+int vtx_bam_metrics_get(vtx_ctx* ctx, vtx_bam_metrics* out)
+{
+    if (!ctx || !out) return VTX_E_INVALID;
+    memset(out, 0, sizeof(*out));
+    if (!ctx->stage_stream) return VTX_OK;
+    CK(cudaSetDevice(ctx->device));
+    static_assert(sizeof(vtx_bam_metrics) == sizeof(stage::LocusMetrics), "metric layouts must agree");
+    CK(cudaMemcpyAsync(out, ctx->bam_metrics.p, sizeof(*out), cudaMemcpyDeviceToHost, ctx->stage_stream));
+    CK(cudaStreamSynchronize(ctx->stage_stream));
     return VTX_OK;
 }
 

@@ -535,6 +535,11 @@ __global__ void vtx_k_emit(uint32_t n_slots_ub, int mode, const uint32_t* __rest
     out.val[o] = v; out.val2[o] = v2;
 }
 
+__global__ void vtx_k_add_u64(unsigned long long* dst, const unsigned long long* __restrict__ src, int n)
+{
+    if (blockIdx.x == 0 && int(threadIdx.x) < n) dst[threadIdx.x] += src[threadIdx.x];
+}
+
 // res_n += total; the running count also goes to a host-mapped slot so that vtx_finish can start copying the
 // triplets of this submit while later submits are still computing
 __global__ void vtx_k_bump(unsigned long long* res_n, const uint32_t* __restrict__ total, unsigned long long* cum_host)
