@@ -156,10 +156,7 @@ def test_cpp_staging_with_dense_overlapping_loci(oracle, dataset, tmp_path):
     assert sb.n_cand > 1.5 * len(sb.read_len)        # reads are shared between neighbouring loci
 
 
-def test_cpp_staging_with_long_spliced_records_across_index_bins(oracle, tmp_path):
-    """Spliced records of up to 150 kb live in high-level BAI bins, far ahead (in file order) of the short reads around the
-    loci they cover: the region iterator (chunk merging, linear-index lower bound, resumed scans) must still hand out
-    exactly the records htslib would, in file order."""
+def _spliced_dataset(tmp_path):
     from vartrix_b200.synth_files import BamWriter
     rng = np.random.default_rng(11)
     contigs = [("chrA", 400_000), ("chrB", 120_000)]
@@ -200,6 +197,14 @@ def test_cpp_staging_with_long_spliced_records_across_index_bins(oracle, tmp_pat
                 ref = "ACGT"[genome[ci][p0]]
                 f.write(f"{name}\t{p0 + 1}\t.\t{ref}\t{'ACGT'[(genome[ci][p0] + 1) % 4]}\t.\t.\t.\n")
     bcs = tmp_path / "b.tsv"; bcs.write_text("ACGTACGTACGTACGT-1\n")
+    return vcf, bam, fa, bcs
+
+
+def test_cpp_staging_with_long_spliced_records_across_index_bins(oracle, tmp_path):
+    """Spliced records of up to 150 kb live in high-level BAI bins, far ahead (in file order) of the short reads around the
+    loci they cover: the region iterator (chunk merging, linear-index lower bound, resumed scans) must still hand out
+    exactly the records htslib would, in file order."""
+    vcf, bam, fa, bcs = _spliced_dataset(tmp_path)
     for threads, shard in ((1, 1000000), (3, 41)):
         out = tmp_path / f"s{threads}.staged"
         subprocess.run([CLI, "-v", str(vcf), "-b", str(bam), "-f", str(fa), "-c", str(bcs), "--dump-staged", str(out),
@@ -251,6 +256,12 @@ def _read_vtxd(path):
         b = data[p:p + nb]; p += nb
         return b
     while p < len(data):
+        if data[p:p + 4] == b"VTXS":            # a shard the device path declined (several contigs): staged on the host
+            p += 4
+            for _ in range(15): take()
+            p += 56
+            out.append(None)
+            continue
         assert data[p:p + 4] == b"VTXD"; p += 4
         tid = struct.unpack("<q", take())[0]
         row = np.frombuffer(take(), np.uint32); start = np.frombuffer(take(), np.int64); end = np.frombuffer(take(), np.int64)
@@ -276,7 +287,7 @@ def test_device_staging_host_share(tmp_path, pre, bcs, shard):
     dev = _read_vtxd(str(tmp_path / "dev.staged"))
     assert len(dev) == len(host)
     for d, (hb, hmet) in zip(dev, host):
-        assert np.array_equal(d["row"], hb.locus_row)
+        assert d is not None and np.array_equal(d["row"], hb.locus_row)
         stream = bytearray()
         for m in d["members"]:
             raw = zlib.decompress(d["comp"][int(m["in_off"]): int(m["in_off"]) + int(m["in_len"])], -15)
@@ -299,3 +310,108 @@ def test_device_staging_host_share(tmp_path, pre, bcs, shard):
             for s0, e0 in zip(d["start"], d["end"]):
                 fetched += sum(1 for (t, a, b) in recs if t == d["tid"] and a < e0 and b > s0)
         assert fetched == hmet["num_reads"]
+
+
+@pytest.fixture(scope="module")
+def stage_dev(tmp_path_factory):
+    import ctypes
+    so = str(tmp_path_factory.mktemp("stageshim") / "libstage_dev_shim.so")
+    cuda_inc = "/usr/local/cuda/include"
+    if not os.path.isdir(cuda_inc):
+        pytest.skip("CUDA headers not found")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I", cuda_inc, "-o", so, os.path.join(ROOT, "tests", "stage_dev_shim.cpp")], check=True)
+    return ctypes.CDLL(so)
+
+
+def _run_stage_dev(lib, stream, d, mapq, primary, nodup, umi, tag):
+    import ctypes
+
+    class StageOut(ctypes.Structure):
+        _fields_ = [("n_rec", ctypes.c_uint32), ("err", ctypes.c_uint32), ("max_span", ctypes.c_uint32), ("max_read", ctypes.c_uint32),
+                    ("n_cand", ctypes.c_uint64), ("metrics", ctypes.c_uint64 * 5)]
+    nl = len(d["row"])
+    rec_cap, cand_cap = len(stream) // 36 + 16, 1 << 22
+    out = StageOut()
+    sbuf = np.frombuffer(bytes(stream) + b"\0" * 8, np.uint8)
+    entry = np.ascontiguousarray(d["entry"], np.uint64)
+    ls, le = np.ascontiguousarray(d["start"], np.int64), np.ascontiguousarray(d["end"], np.int64)
+    cand_first = np.zeros(nl + 1, np.uint32); cand_rec = np.zeros(cand_cap, np.uint32)
+    read_off = np.zeros(rec_cap, np.uint64); read_len = np.zeros(rec_cap, np.uint32); cb_off = np.zeros(rec_cap, np.uint32)
+    cb_len = np.zeros(rec_cap, np.uint16); umi_k = np.zeros(rec_cap, np.uint64); used = np.zeros(rec_cap, np.uint32)
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    rc = lib.vtx_test_stage_dev(P(sbuf), ctypes.c_uint64(len(stream)), ctypes.c_int32(int(d["tid"])), ctypes.c_uint32(mapq), primary, nodup, umi,
+                                tag.encode(), ctypes.c_uint32(len(entry)), P(entry), ctypes.c_uint32(nl), P(ls), P(le), ctypes.c_uint32(rec_cap),
+                                ctypes.c_uint64(cand_cap), ctypes.byref(out), P(cand_first), P(cand_rec), P(read_off), P(read_len), P(cb_off),
+                                P(cb_len), P(umi_k), P(used))
+    assert rc == 0, (rc, out.err)
+    return out, cand_first, cand_rec, read_off, read_len, cb_off, cb_len, umi_k, used
+
+
+@pytest.mark.parametrize("pre,bcs,shard,extra", [
+    ("test_dna", "dna_barcodes.tsv", "7", []), ("test_dna", "dna_barcodes.tsv", "1000", ["--mapq", "30", "--primary-alignments"]),
+    ("test", "barcodes.tsv", "1", ["--umi"]), ("test", "barcodes.tsv", "1", ["--umi", "--no-duplicates", "--mapq", "4"]),
+    ("test_dna", "dna_barcodes.tsv", "5", ["--bam-tag", "CB", "--mapq", "1"])])
+def test_device_staging_logic_matches_host_stager(tmp_path, stage_dev, pre, bcs, shard, extra):
+    """The bodies of the staging kernels (csrc/vtx_stage.cuh), run serially on the CPU over the shard the CLI hands to
+    vtx_submit_bam, produce per locus exactly the candidates the host stager produces: same reads (bases, length), same cell tag
+    bytes, same UMI keys, in the same order, and the same five filter counters (main.rs:831-865)."""
+    _check_device_logic(tmp_path, stage_dev, f"{REF_TEST_DIR}/{pre}.vcf", f"{REF_TEST_DIR}/{pre}.bam", f"{REF_TEST_DIR}/{pre}.fa",
+                        f"{REF_TEST_DIR}/{bcs}", shard, extra)
+
+
+@pytest.mark.parametrize("shard,extra", [("40", []), ("13", ["--mapq", "20", "--primary-alignments", "--no-duplicates", "--padding", "80", "--umi"])])
+def test_device_staging_logic_on_synthetic_files(tmp_path, stage_dev, dataset, shard, extra):
+    """... on files with multi-allelic / invalid records, reads without a cell tag, duplicates, secondary alignments"""
+    n = _check_device_logic(tmp_path, stage_dev, dataset["vcf"], dataset["bam"], dataset["fasta"], dataset["barcodes"], shard, extra)
+    assert n > 1000
+
+
+@pytest.mark.parametrize("shard", ["41", "220"])
+def test_device_staging_logic_with_long_spliced_records(tmp_path, stage_dev, shard):
+    """... and with 150 kb spliced records in high-level index bins: the compressed range of a shard starts far ahead of its
+    loci, and the per-locus window search (longest reference span) must still find them"""
+    vcf, bam, fa, bcs = _spliced_dataset(tmp_path)
+    n = _check_device_logic(tmp_path, stage_dev, str(vcf), str(bam), str(fa), str(bcs), shard, ["--umi"])
+    assert n > 100
+
+
+def _check_device_logic(tmp_path, stage_dev, vcf, bam, fa, bcs, shard, extra):
+    import zlib
+    from vartrix_b200.staged_io import read_dump
+    base = [CLI, "-v", vcf, "-b", bam, "-f", fa, "-c", bcs, "--shard-loci", shard, "--threads", "2", *extra]
+    subprocess.run([*base, "--dump-staged", str(tmp_path / "dev.staged"), "--gpu-stage"], check=True, cwd=str(tmp_path))
+    subprocess.run([*base, "--dump-staged", str(tmp_path / "host.staged")], check=True, cwd=str(tmp_path))
+    _, _, host = read_dump(str(tmp_path / "host.staged"))
+    dev = _read_vtxd(str(tmp_path / "dev.staged"))
+    assert len(dev) == len(host)
+    mapq = int(extra[extra.index("--mapq") + 1]) if "--mapq" in extra else 0
+    umi = 1 if "--umi" in extra else 0
+    n_checked = 0
+    for d, (hb, hmet) in zip(dev, host):
+        if d is None:
+            continue
+        assert np.array_equal(d["row"], hb.locus_row)
+        stream = b"".join(zlib.decompress(d["comp"][int(m["in_off"]): int(m["in_off"]) + int(m["in_len"])], -15) for m in d["members"])
+        out, cand_first, cand_rec, read_off, read_len, cb_off, cb_len, umi_k, used = _run_stage_dev(
+            stage_dev, stream, d, mapq, int("--primary-alignments" in extra), int("--no-duplicates" in extra), umi, "CB")
+        assert [out.metrics[i] for i in range(5)] == [hmet[k] for k in ("num_reads", "num_low_mapq", "num_non_primary", "num_duplicates", "num_not_useful")]
+        assert out.n_cand == len(hb.cand_read) and np.array_equal(cand_first.astype(np.uint64), hb.cand_start)
+        assert out.max_read == (int(hb.read_len[hb.cand_read].max()) if len(hb.cand_read) else 0)
+        sb = np.frombuffer(stream, np.uint8)
+        for c in range(int(out.n_cand)):
+            r, hr = int(cand_rec[c]), int(hb.cand_read[c])
+            assert used[r] == 1 and read_len[r] == hb.read_len[hr]
+            nb = (int(read_len[r]) + 1) // 2
+            assert np.array_equal(sb[int(read_off[r]): int(read_off[r]) + nb], hb.read_nib[int(hb.read_off[hr]): int(hb.read_off[hr]) + nb])
+            h_has_cb = hb.read_cb_off[hr] != 0xFFFFFFFF
+            assert (cb_off[r] != 0xFFFFFFFF) == h_has_cb
+            if h_has_cb:
+                assert cb_len[r] == hb.read_cb_len[hr]
+                assert bytes(sb[int(cb_off[r]): int(cb_off[r]) + int(cb_len[r])]) == bytes(hb.cb_bytes[int(hb.read_cb_off[hr]): int(hb.read_cb_off[hr]) + int(hb.read_cb_len[hr])])
+            if umi:
+                assert umi_k[r] == hb.read_umi_key[hr]
+            n_checked += 1
+        # records that serve several loci are one read on both sides
+        assert len(set(cand_rec[:int(out.n_cand)].tolist())) == len(set(hb.cand_read.tolist()))
+    assert n_checked > 0
+    return n_checked

@@ -1287,7 +1287,7 @@ int vtx_submit_bam(vtx_ctx* ctx, const vtx_bam_shard* sh)
         CK(cudaMemsetAsync(d_tmp, 0, sizeof(stage::LocusMetrics), ss));
         stage::vtx_k_locus_cands<<<blocks_for(nl, 64), 64, 0, ss>>>(sp, nl, P<int64_t>(sl.l_start), P<int64_t>(sl.l_end), n_rec, P<uint64_t>(sl.rec_off),
                                                                    P<int32_t>(sl.rec_tid), P<int32_t>(sl.rec_pos), P<int32_t>(sl.rec_end), P<uint32_t>(sl.rec_fm),
-                                                                   d_sc + 2, 0, P<uint32_t>(sl.cand_count), nullptr, nullptr, nullptr, d_tmp);
+                                                                   d_sc + 2, d_sc + 3, 0, P<uint32_t>(sl.cand_count), nullptr, nullptr, nullptr, d_tmp);
         rc = scan_u32_on(ctx, ss, P<uint32_t>(sl.cand_count), nl, P<uint32_t>(sl.cand_first), ctx->stage_sums);
         if (rc) return fail_out(rc);
         CK(cudaMemcpyAsync(hs, P<uint32_t>(sl.cand_first) + nl, 4, cudaMemcpyDeviceToHost, ss));
@@ -1305,7 +1305,7 @@ int vtx_submit_bam(vtx_ctx* ctx, const vtx_bam_shard* sh)
         stage::LocusMetrics* d_tmp = reinterpret_cast<stage::LocusMetrics*>(sl.status.p);
         stage::vtx_k_locus_cands<<<blocks_for(nl, 64), 64, 0, ss>>>(sp, nl, P<int64_t>(sl.l_start), P<int64_t>(sl.l_end), n_rec, P<uint64_t>(sl.rec_off),
                                                                    P<int32_t>(sl.rec_tid), P<int32_t>(sl.rec_pos), P<int32_t>(sl.rec_end), P<uint32_t>(sl.rec_fm),
-                                                                   d_sc + 2, 1, nullptr, P<uint32_t>(sl.cand_first), P<uint32_t>(sl.cand_rec), P<uint32_t>(sl.used), d_tmp);
+                                                                   d_sc + 2, d_sc + 3, 1, nullptr, P<uint32_t>(sl.cand_first), P<uint32_t>(sl.cand_rec), P<uint32_t>(sl.used), d_tmp);
         stage::vtx_k_widen<<<blocks_for(nl + 1, 256), 256, 0, ss>>>(nl + 1, P<uint32_t>(sl.cand_first), P<uint64_t>(sl.cand_start));
     }
     if (n_rec)

@@ -31,42 +31,64 @@ struct Params {
 // error bits (first word of `err`): the shard is then re-staged on the host, which produces the message
 enum : uint32_t { kErrWalk = 1, kErrRecord = 2, kErrExoticUmi = 4, kErrLongRead = 8 };
 
-__device__ __forceinline__ uint32_t ld32(const uint8_t* p) { return uint32_t(p[0]) | (uint32_t(p[1]) << 8) | (uint32_t(p[2]) << 16) | (uint32_t(p[3]) << 24); }
-__device__ __forceinline__ uint32_t ld16(const uint8_t* p) { return uint32_t(p[0]) | (uint32_t(p[1]) << 8); }
+__host__ __device__ inline uint32_t ld32(const uint8_t* p) { return uint32_t(p[0]) | (uint32_t(p[1]) << 8) | (uint32_t(p[2]) << 16) | (uint32_t(p[3]) << 24); }
+__host__ __device__ inline uint32_t ld16(const uint8_t* p) { return uint32_t(p[0]) | (uint32_t(p[1]) << 8); }
+
+// The per-item bodies below are __host__ __device__: the kernels at the end of the file are one-line wrappers, and
+// tests/stage_dev_shim.cpp runs the same bodies serially on the CPU against the host stager (tests/test_host_staging_cpu.py).
+__host__ __device__ inline void flag_or(uint32_t* p, uint32_t v)
+{
+#ifdef __CUDA_ARCH__
+    atomicOr(p, v);
+#else
+    *p |= v;
+#endif
+}
+__host__ __device__ inline void take_max(uint32_t* p, uint32_t v)
+{
+#ifdef __CUDA_ARCH__
+    atomicMax(p, v);
+#else
+    if (v > *p) *p = v;
+#endif
+}
+__host__ __device__ inline void add_u64(unsigned long long* p, unsigned long long v)
+{
+#ifdef __CUDA_ARCH__
+    atomicAdd(p, v);
+#else
+    *p += v;
+#endif
+}
 
 // ---- 1. record boundaries: one thread per segment [seg_off[k], seg_off[k + 1]) of the stream ---------------------------
 // pass 0 counts the records of the segment, pass 1 writes their offsets at rec_first[k]..
-__global__ void vtx_k_walk(Params P, uint32_t n_seg, const uint64_t* __restrict__ seg_off, int pass, uint32_t* __restrict__ seg_count,
-                           const uint32_t* __restrict__ rec_first, uint64_t* __restrict__ rec_off, uint32_t* __restrict__ err)
+__host__ __device__ inline void walk_segment(const Params& P, uint32_t k, const uint64_t* seg_off, int pass, uint32_t* seg_count,
+                                             const uint32_t* rec_first, uint64_t* rec_off, uint32_t* err)
 {
-    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_seg) return;
     uint64_t p = seg_off[k];
     const uint64_t end = seg_off[k + 1];
     uint32_t n = 0;
     const uint32_t base = pass ? rec_first[k] : 0;
     while (p < end) {
-        if (p + 36 > P.s_len) { atomicOr(err, kErrWalk); break; }
+        if (p + 36 > P.s_len) { flag_or(err, kErrWalk); break; }
         const uint32_t bs = ld32(P.s + p);
         const uint8_t* b = P.s + p + 4;
         const int64_t l_seq = int32_t(ld32(b + 16));
         const uint64_t need = 32ull + b[8] + 4ull * ld16(b + 12) + (l_seq < 0 ? 0 : uint64_t(l_seq + 1) / 2 + uint64_t(l_seq));
-        if (bs < 32 || bs > (1u << 28) || l_seq < 0 || need > bs || p + 4 + bs > P.s_len) { atomicOr(err, kErrRecord); break; }
+        if (bs < 32 || bs > (1u << 28) || l_seq < 0 || need > bs || p + 4 + bs > P.s_len) { flag_or(err, kErrRecord); break; }
         if (pass) rec_off[base + n] = p;
         ++n;
         p += 4 + uint64_t(bs);
     }
-    if (p > end) atomicOr(err, kErrWalk);                  // the walk must land exactly on the next entry point
+    if (p > end) flag_or(err, kErrWalk);                  // the walk must land exactly on the next entry point
     if (!pass) seg_count[k] = n;
 }
 
 // ---- 2. one thread per record: position, end position (htslib bam_endpos), flag | mapq, longest reference span ---------
-__global__ void vtx_k_parse(Params P, uint32_t n_rec, const uint64_t* __restrict__ rec_off, int32_t* __restrict__ rec_tid,
-                            int32_t* __restrict__ rec_pos, int32_t* __restrict__ rec_end, uint32_t* __restrict__ rec_fm,
-                            uint32_t* __restrict__ max_span /* [0] longest reference span, [1] longest read */)
+__host__ __device__ inline void parse_record(const Params& P, uint32_t i, const uint64_t* rec_off, int32_t* rec_tid, int32_t* rec_pos,
+                                             int32_t* rec_end, uint32_t* rec_fm, uint32_t* max_span /* longest reference span of a record */)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_rec) return;
     const uint8_t* b = P.s + rec_off[i] + 4;
     const int32_t pos = int32_t(ld32(b + 4));
     const uint32_t flag = ld16(b + 14), nc = ld16(b + 12);
@@ -79,17 +101,19 @@ __global__ void vtx_k_parse(Params P, uint32_t n_rec, const uint64_t* __restrict
         }
     }
     const int64_t e = int64_t(pos) + (rlen > 0 ? rlen : 1);
-    rec_tid[i] = int32_t(ld32(b));
-    rec_pos[i] = pos;
+    const int32_t tid = int32_t(ld32(b));
+    rec_tid[i] = tid;
+    // a range of the shard's contig holds only its records; should the index ever hand out a tail of the next contig (or of
+    // unplaced reads), those sort last and keep the position array monotone for the per-locus binary searches
+    rec_pos[i] = tid == P.tid ? pos : 0x7fffffff;
     rec_end[i] = int32_t(e > 0x7fffffff ? 0x7fffffff : e);
     rec_fm[i] = (flag << 8) | b[9];
-    atomicMax(max_span, uint32_t(e - pos > 0xFFFFFFFFll ? 0xFFFFFFFFu : uint32_t(e - pos)));
-    atomicMax(max_span + 1, ld32(b + 16));
+    if (tid == P.tid) take_max(max_span, uint32_t(e - pos > 0xFFFFFFFFll ? 0xFFFFFFFFu : uint32_t(e - pos)));
 }
 
 // rust-htslib 0.36 CigarStringView::read_pos(p, include_softclips = false, include_dels = true) folded into
 // useful_alignment (main.rs:790-806): is there a p in start..=end with an aligned base or a deletion?
-__device__ inline bool useful_alignment(const uint8_t* b, int64_t start, int64_t end)
+__host__ __device__ inline bool useful_alignment(const uint8_t* b, int64_t start, int64_t end)
 {
     const uint8_t* cg = b + 32 + b[8];
     const uint32_t nc = ld16(b + 12);
@@ -118,15 +142,11 @@ __device__ inline bool useful_alignment(const uint8_t* b, int64_t start, int64_t
 struct LocusMetrics { unsigned long long num_reads, num_low_mapq, num_non_primary, num_duplicates, num_not_useful; };
 
 // ---- 3. one thread per locus: the records it fetches, the four filters; pass 0 counts, pass 1 lists ---------------------
-__global__ void vtx_k_locus_cands(Params P, uint32_t n_loci, const int64_t* __restrict__ l_start, const int64_t* __restrict__ l_end,
-                                  uint32_t n_rec, const uint64_t* __restrict__ rec_off, const int32_t* __restrict__ rec_tid,
-                                  const int32_t* __restrict__ rec_pos, const int32_t* __restrict__ rec_end, const uint32_t* __restrict__ rec_fm,
-                                  const uint32_t* __restrict__ max_span, int pass, uint32_t* __restrict__ cand_count,
-                                  const uint32_t* __restrict__ cand_first, uint32_t* __restrict__ cand_rec, uint32_t* __restrict__ used,
-                                  LocusMetrics* __restrict__ met)
+__host__ __device__ inline void locus_cands(const Params& P, uint32_t l, const int64_t* l_start, const int64_t* l_end, uint32_t n_rec,
+                                            const uint64_t* rec_off, const int32_t* rec_tid, const int32_t* rec_pos, const int32_t* rec_end,
+                                            const uint32_t* rec_fm, const uint32_t* max_span, uint32_t* max_read, int pass, uint32_t* cand_count,
+                                            const uint32_t* cand_first, uint32_t* cand_rec, uint32_t* used, LocusMetrics* met)
 {
-    const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
-    if (l >= n_loci) return;
     const int64_t start = l_start[l], end = l_end[l];
     // records are coordinate-sorted: candidates lie in [first pos > start - max_span, first pos >= end)
     const int64_t lo_pos = start - int64_t(*max_span);
@@ -136,7 +156,7 @@ __global__ void vtx_k_locus_cands(Params P, uint32_t n_loci, const int64_t* __re
     hi = n_rec;
     while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (int64_t(rec_pos[mid]) < end) lo = mid + 1; else hi = mid; }
     const uint32_t last = lo;
-    uint32_t n = 0;
+    uint32_t n = 0, longest = 0;
     unsigned long long fetched = 0, low = 0, nonprim = 0, dup = 0, notuse = 0;
     const uint32_t base = pass ? cand_first[l] : 0;
     for (uint32_t i = first; i < last; ++i) {
@@ -148,20 +168,22 @@ __global__ void vtx_k_locus_cands(Params P, uint32_t n_loci, const int64_t* __re
         if (P.no_duplicates && (fl & 0x400)) { ++dup; continue; }                         // 849
         if (!useful_alignment(P.s + rec_off[i] + 4, start, end)) { ++notuse; continue; }  // 857
         if (pass) { cand_rec[base + n] = i; used[i] = 1u; }
+        else { const uint32_t ls = ld32(P.s + rec_off[i] + 4 + 16); if (ls > longest) longest = ls; }                       // l_seq of a read that will be scored
         ++n;
     }
     if (!pass) {
         cand_count[l] = n;
-        if (fetched) atomicAdd(&met->num_reads, fetched);
-        if (low) atomicAdd(&met->num_low_mapq, low);
-        if (nonprim) atomicAdd(&met->num_non_primary, nonprim);
-        if (dup) atomicAdd(&met->num_duplicates, dup);
-        if (notuse) atomicAdd(&met->num_not_useful, notuse);
+        if (longest) take_max(max_read, longest);
+        if (fetched) add_u64(&met->num_reads, fetched);
+        if (low) add_u64(&met->num_low_mapq, low);
+        if (nonprim) add_u64(&met->num_non_primary, nonprim);
+        if (dup) add_u64(&met->num_duplicates, dup);
+        if (notuse) add_u64(&met->num_not_useful, notuse);
     }
 }
 
 // first aux field named (t0, t1): its value bytes when the type is Z (Record::aux -> Aux::String), else nothing
-__device__ inline bool aux_z(const uint8_t* p, const uint8_t* e, uint8_t t0, uint8_t t1, uint32_t* off_from_p, uint32_t* len)
+__host__ __device__ inline bool aux_z(const uint8_t* p, const uint8_t* e, uint8_t t0, uint8_t t1, uint32_t* off_from_p, uint32_t* len)
 {
     const uint8_t* base = p;
     while (p + 3 <= e) {
@@ -196,7 +218,7 @@ __device__ inline bool aux_z(const uint8_t* p, const uint8_t* e, uint8_t t0, uin
 }
 
 // vtx_pack_umi on the device: strings over {A,C,G,T,N} up to 18 bases; anything else cannot be keyed here
-__device__ inline uint64_t pack_umi(const uint8_t* s, uint32_t len)
+__host__ __device__ inline uint64_t pack_umi(const uint8_t* s, uint32_t len)
 {
     if (len > 18) return kNoUmi;
     uint64_t k = 0;
@@ -211,13 +233,9 @@ __device__ inline uint64_t pack_umi(const uint8_t* s, uint32_t len)
 // ---- 4. one thread per record: the read arrays of the engine -----------------------------------------------------------------
 // read id = record index (nothing is copied or compacted: bases and tag bytes stay where they are in the stream); records
 // that are no locus's candidate get an empty entry
-__global__ void vtx_k_read_emit(Params P, uint32_t n_rec, const uint64_t* __restrict__ rec_off, const uint32_t* __restrict__ used,
-                                uint64_t* __restrict__ read_off, uint32_t* __restrict__ read_len,
-                                uint32_t* __restrict__ read_cb_off, uint16_t* __restrict__ read_cb_len, uint64_t* __restrict__ read_umi,
-                                uint32_t* __restrict__ err)
+__host__ __device__ inline void read_emit(const Params& P, uint32_t i, const uint64_t* rec_off, const uint32_t* used, uint64_t* read_off,
+                                          uint32_t* read_len, uint32_t* read_cb_off, uint16_t* read_cb_len, uint64_t* read_umi, uint32_t* err)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_rec) return;
     const uint32_t r = i;
     if (!used[i]) { read_off[r] = 0; read_len[r] = 0; read_cb_off[r] = kNoCb; read_cb_len[r] = 0; if (P.want_umi) read_umi[r] = kNoUmi; return; }
     const uint64_t ro = rec_off[i];
@@ -225,7 +243,7 @@ __global__ void vtx_k_read_emit(Params P, uint32_t n_rec, const uint64_t* __rest
     const uint32_t bs = ld32(P.s + ro);
     const int32_t l_seq = int32_t(ld32(b + 16));
     const uint64_t seq_off = ro + 4 + 32 + b[8] + 4ull * ld16(b + 12);
-    if (l_seq > 16000) atomicOr(err, kErrLongRead);
+    if (l_seq > 16000) flag_or(err, kErrLongRead);
     read_off[r] = seq_off;
     read_len[r] = uint32_t(l_seq);
     const uint8_t* aux = P.s + seq_off + uint64_t(l_seq + 1) / 2 + uint64_t(l_seq);
@@ -238,10 +256,44 @@ __global__ void vtx_k_read_emit(Params P, uint32_t n_rec, const uint64_t* __rest
         uint64_t key = kNoUmi;
         if (aux_z(aux, e, 'U', 'B', &off, &len)) {                                                                        // main.rs:752-757
             key = pack_umi(aux + off, len);
-            if (key == kNoUmi) atomicOr(err, kErrExoticUmi);          // needs the host's interner: the shard goes back to the host path
+            if (key == kNoUmi) flag_or(err, kErrExoticUmi);          // needs the host's interner: the shard goes back to the host path
         }
         read_umi[r] = key;
     }
+}
+
+#ifdef __CUDACC__
+__global__ void vtx_k_walk(Params P, uint32_t n_seg, const uint64_t* __restrict__ seg_off, int pass, uint32_t* __restrict__ seg_count,
+                           const uint32_t* __restrict__ rec_first, uint64_t* __restrict__ rec_off, uint32_t* __restrict__ err)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n_seg) walk_segment(P, k, seg_off, pass, seg_count, rec_first, rec_off, err);
+}
+__global__ void vtx_k_parse(Params P, uint32_t n_rec, const uint64_t* __restrict__ rec_off, int32_t* __restrict__ rec_tid,
+                            int32_t* __restrict__ rec_pos, int32_t* __restrict__ rec_end, uint32_t* __restrict__ rec_fm,
+                            uint32_t* __restrict__ max_span)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_rec) parse_record(P, i, rec_off, rec_tid, rec_pos, rec_end, rec_fm, max_span);
+}
+__global__ void vtx_k_locus_cands(Params P, uint32_t n_loci, const int64_t* __restrict__ l_start, const int64_t* __restrict__ l_end,
+                                  uint32_t n_rec, const uint64_t* __restrict__ rec_off, const int32_t* __restrict__ rec_tid,
+                                  const int32_t* __restrict__ rec_pos, const int32_t* __restrict__ rec_end, const uint32_t* __restrict__ rec_fm,
+                                  const uint32_t* __restrict__ max_span, uint32_t* __restrict__ max_read, int pass, uint32_t* __restrict__ cand_count,
+                                  const uint32_t* __restrict__ cand_first, uint32_t* __restrict__ cand_rec, uint32_t* __restrict__ used,
+                                  LocusMetrics* __restrict__ met)
+{
+    const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l < n_loci) locus_cands(P, l, l_start, l_end, n_rec, rec_off, rec_tid, rec_pos, rec_end, rec_fm, max_span, max_read, pass, cand_count,
+                                cand_first, cand_rec, used, met);
+}
+__global__ void vtx_k_read_emit(Params P, uint32_t n_rec, const uint64_t* __restrict__ rec_off, const uint32_t* __restrict__ used,
+                                uint64_t* __restrict__ read_off, uint32_t* __restrict__ read_len,
+                                uint32_t* __restrict__ read_cb_off, uint16_t* __restrict__ read_cb_len, uint64_t* __restrict__ read_umi,
+                                uint32_t* __restrict__ err)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_rec) read_emit(P, i, rec_off, used, read_off, read_len, read_cb_off, read_cb_len, read_umi, err);
 }
 
 // cand_start (u64, what the pipeline expects) from the u32 exclusive scan of the per-locus counts
@@ -250,6 +302,7 @@ __global__ void vtx_k_widen(uint32_t n, const uint32_t* __restrict__ in, uint64_
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = in[i];
 }
+#endif   // __CUDACC__
 
 }  // namespace stage
 }  // namespace vtx
