@@ -35,6 +35,8 @@ def main():
     ap.add_argument("--threads", type=int, nargs="+", default=[16, 64, 128])
     ap.add_argument("--devices", nargs="+", default=["0"])
     ap.add_argument("--mode", default="consensus")
+    ap.add_argument("--stage", nargs="+", default=["host"], choices=["host", "gpu-inflate", "gpu-stage"],
+                    help="who decodes the BAM: staging threads, staging threads with device inflate, or the device")
     ap.add_argument("--keep", default="")
     a = ap.parse_args()
     from vartrix_b200 import synth_files
@@ -48,14 +50,15 @@ def main():
     gen_s = time.time() - t0
     cli = os.path.join(ROOT, "vartrix_b200", "bin", "vartrix_b200")
     runs = []
-    for dev in a.devices:
+    import hashlib
+    for dev, stage in [(dv, sg) for dv in a.devices for sg in a.stage]:
         for th in a.threads:
-            o = os.path.join(d, f"out_{dev}_{th}.mtx")
+            o = os.path.join(d, f"out_{dev}_{th}_{stage}.mtx")
             for p in (o, os.path.join(d, "ref_matrix.mtx")):
                 if os.path.exists(p):
                     os.remove(p)
             cmd = [cli, "-v", ds["vcf"], "-b", ds["bam"], "-f", ds["fasta"], "-c", ds["barcodes"], "-o", o, "-s", a.mode, "--threads", str(th),
-                   "--log-level", "info", "--devices", dev]
+                   "--log-level", "info", "--devices", dev] + ([] if stage == "host" else ["--" + stage])
             t0 = time.time()
             p = subprocess.run(cmd, capture_output=True, text=True, cwd=d)
             wall = time.time() - t0
@@ -70,7 +73,8 @@ def main():
             st = re.search(r"Staging thread-seconds: total ([\d.]+) = file read ([\d.]+) \+ inflate ([\d.]+) \+ crc32 ([\d.]+) \+ record scan / filters / packing ([\d.]+); (\d+) BGZF blocks, ([\d.]+) MB inflated; copy into pinned arenas ([\d.]+) s \(([\d.]+) MB\)", err)
             gpu = [dict(device=int(m.group(1)), h2d_ms=float(m.group(2)), prep_ms=float(m.group(3)), sw_ms=float(m.group(4)), post_ms=float(m.group(5)), pairs=int(m.group(6)))
                    for m in re.finditer(r"GPU (\d+) device ms: h2d ([\d.]+), prep ([\d.]+), Smith-Waterman ([\d.]+), post ([\d.]+) \((\d+) pairs", err)]
-            run = dict(devices=dev, threads=th, rc=p.returncode, wall_s=round(wall, 3), reads_fetched=reads, pairs_scored=pairs, marks_s=marks, gpu=gpu,
+            run = dict(devices=dev, threads=th, stage=stage, mtx_sha1=hashlib.sha1(open(o, "rb").read()).hexdigest()[:12] if os.path.exists(o) else None,
+                       rc=p.returncode, wall_s=round(wall, 3), reads_fetched=reads, pairs_scored=pairs, marks_s=marks, gpu=gpu,
                        mtx_bytes=os.path.getsize(o) if os.path.exists(o) else None)
             if st and reads:
                 tot, rd, inf, crc, scan = (float(st.group(i)) for i in range(1, 6))
