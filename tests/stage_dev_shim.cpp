@@ -24,7 +24,8 @@ extern "C" int vtx_test_stage_dev(const uint8_t* stream, uint64_t stream_len, in
     memset(out, 0, sizeof(*out));
     const uint32_t n_seg = n_entry ? n_entry - 1 : 0;
     std::vector<uint32_t> seg_count(n_seg + 1, 0), seg_first(n_seg + 2, 0);
-    for (uint32_t k = 0; k < n_seg; ++k) walk_segment(P, k, entry, 0, seg_count.data(), nullptr, nullptr, &out->err);
+    DirectFetch F{ stream };
+    for (uint32_t k = 0; k < n_seg; ++k) walk_segment(P, k, entry, 0, seg_count.data(), nullptr, nullptr, &out->err, F);
     for (uint32_t k = 0; k < n_seg; ++k) seg_first[k + 1] = seg_first[k] + seg_count[k];
     if (out->err & (kErrWalk | kErrRecord)) return 1;
     const uint32_t n_rec = seg_first[n_seg];
@@ -33,7 +34,7 @@ extern "C" int vtx_test_stage_dev(const uint8_t* stream, uint64_t stream_len, in
     std::vector<uint64_t> rec_off(n_rec + 1);
     std::vector<int32_t> rec_tid(n_rec + 1), rec_pos(n_rec + 1), rec_end(n_rec + 1);
     std::vector<uint32_t> rec_fm(n_rec + 1);
-    for (uint32_t k = 0; k < n_seg; ++k) walk_segment(P, k, entry, 1, nullptr, seg_first.data(), rec_off.data(), &out->err);
+    for (uint32_t k = 0; k < n_seg; ++k) walk_segment(P, k, entry, 1, nullptr, seg_first.data(), rec_off.data(), &out->err, F);
     for (uint32_t i = 0; i < n_rec; ++i) parse_record(P, i, rec_off.data(), rec_tid.data(), rec_pos.data(), rec_end.data(), rec_fm.data(), &out->max_span);
     memset(used, 0, size_t(n_rec) * 4);
     std::vector<uint32_t> cand_count(n_loci + 1, 0);

@@ -11,6 +11,7 @@
 #include <chrono>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fcntl.h>
 #include <functional>
@@ -40,7 +41,7 @@ inline uint64_t rd64(const uint8_t* p) { return uint64_t(rd32(p)) | (uint64_t(rd
 // ---------------------------------------------------------------------------------------------
 class Bgzf {
 public:
-    ~Bgzf() { close(); }
+    ~Bgzf() { close(); release_bulk_out(); }
     bool open(const std::string& path, std::string* err)
     {
         close();
@@ -126,7 +127,7 @@ private:
         if (coff >= bulk_begin_ && coff < bulk_end_) {              // inflated in bulk on the device (prefetch_bulk)
             auto it = std::lower_bound(bulk_blocks_.begin(), bulk_blocks_.end(), coff, [](const BulkBlock& b, uint64_t c) { return b.coff < c; });
             if (it != bulk_blocks_.end() && it->coff == coff) {
-                bulk_slot_.coff = coff; bulk_slot_.next = it->next; bulk_slot_.len = it->len; bulk_slot_.ptr = bulk_out_.data() + it->out_off;
+                bulk_slot_.coff = coff; bulk_slot_.next = it->next; bulk_slot_.len = it->len; bulk_slot_.ptr = bulk_out_ + it->out_off;
                 cur_ = &bulk_slot_; block_pos_ = 0;
                 return true;
             }
@@ -185,6 +186,8 @@ private:
     }
 public:
     void set_check_crc(bool on) { check_crc_ = on; }
+    // page-locked memory for the bulk buffer (the device copies straight into it): e.g. vtx_host_alloc / vtx_host_free
+    void set_bulk_allocator(std::function<bool(void**, size_t)> a, std::function<void(void*)> f) { release_bulk_out(); bulk_alloc_ = std::move(a); bulk_free_ = std::move(f); }
     // Inflate every BGZF member that starts in [coff_begin, coff_last] in one go through `fn` (the device:
     // vtx_bgzf_inflate) and serve them from that buffer afterwards: the host only reads the compressed bytes and walks
     // the member headers.  Returns false on error (bad() tells whether the file is at fault); a range that cannot be
@@ -232,10 +235,17 @@ public:
             pos += total;
         }
         bulk_comp_.resize(bulk_comp_.size() + 16, 0);                                   // readable padding behind the last payload
-        bulk_out_.resize(size_t(out_off) + 16);
+        if (size_t(out_off) + 16 > bulk_out_cap_) {          // grown geometrically; page-locked when the owner supplied such an allocator
+            release_bulk_out();
+            const size_t want = (size_t(out_off) + 16) * 5 / 4 + (1u << 20);
+            if (bulk_alloc_) { void* q = nullptr; if (bulk_alloc_(&q, want)) bulk_out_ = static_cast<uint8_t*>(q); bulk_out_pinned_ = bulk_out_ != nullptr; }
+            if (!bulk_out_) { bulk_out_ = static_cast<uint8_t*>(malloc(want)); bulk_out_pinned_ = false; }
+            if (!bulk_out_) return fail(coff_begin, "out of memory (bulk inflate buffer)");
+            bulk_out_cap_ = want;
+        }
         const uint64_t t1 = StageClock::now();
         std::string e;
-        if (!bulk_desc_.empty() && !fn(bulk_desc_.data(), uint32_t(bulk_desc_.size()), bulk_comp_.data(), bulk_comp_.size() - 16, bulk_out_.data(), out_off, &e)) {
+        if (!bulk_desc_.empty() && !fn(bulk_desc_.data(), uint32_t(bulk_desc_.size()), bulk_comp_.data(), bulk_comp_.size() - 16, bulk_out_, out_off, &e)) {
             bulk_blocks_.clear();
             if (err_.empty()) err_ = "device BGZF inflate: " + e;
             return false;
@@ -294,7 +304,17 @@ public:
 private:
     struct BulkBlock { uint64_t coff, next, out_off; uint32_t len; };
     std::vector<BulkBlock> bulk_blocks_;
-    std::vector<uint8_t> bulk_file_, bulk_comp_, bulk_out_;
+    std::vector<uint8_t> bulk_file_, bulk_comp_;
+    uint8_t* bulk_out_ = nullptr;
+    size_t bulk_out_cap_ = 0;
+    bool bulk_out_pinned_ = false;
+    std::function<bool(void**, size_t)> bulk_alloc_;
+    std::function<void(void*)> bulk_free_;
+    void release_bulk_out()
+    {
+        if (bulk_out_) { if (bulk_out_pinned_ && bulk_free_) bulk_free_(bulk_out_); else free(bulk_out_); }
+        bulk_out_ = nullptr; bulk_out_cap_ = 0;
+    }
     std::vector<vtx_bgzf_block> bulk_desc_;
     uint64_t bulk_begin_ = 0, bulk_end_ = 0;
     Slot bulk_slot_;
@@ -527,6 +547,34 @@ public:
     bool bad() const { return !err_.empty(); }
     const std::string& error() const { return err_; }
     void set_check_crc(bool on) { bg_.set_check_crc(on); }
+    // A virtual offset at or before which every record with pos < end lies (sorted file): the first record the index files under
+    // a 16 kb bin whose window starts behind `end` -- that record, and everything after it, starts at or behind `end`.  Chunks of
+    // the wide bins (reads that cross 16 kb ... 64 Mb boundaries) reach far beyond a region; a sequential reader stops at the
+    // first record with pos >= end, a bulk reader needs this bound instead.  ~0 when the index knows no later 16 kb bin.
+    uint64_t upper_clip(int tid, int64_t end) const
+    {
+        if (tid < 0 || size_t(tid) >= refs_.size() || end <= 0) return ~0ull;
+        const BaiRef& r = refs_[size_t(tid)];
+        const uint32_t first_bin = 4681u + uint32_t(((end - 1) >> 14) + 1);
+        for (auto it = std::lower_bound(r.bin_ids.begin(), r.bin_ids.end(), first_bin); it != r.bin_ids.end(); ++it) {
+            const std::vector<BaiChunk>& cs = r.bin_chunks[size_t(it - r.bin_ids.begin())];
+            if (cs.empty()) continue;
+            uint64_t lo = ~0ull;
+            for (const BaiChunk& c : cs) lo = std::min(lo, c.beg);
+            return lo;
+        }
+        return ~0ull;
+    }
+    // Record boundaries the linear index knows inside (lo, hi): the first record overlapping each 16 kb window of [beg, end).
+    // Entry points for a parallel record walk.  Appends to `out`.
+    void linear_entries(int tid, int64_t beg, int64_t end, uint64_t lo, uint64_t hi, std::vector<uint64_t>* out) const
+    {
+        if (tid < 0 || size_t(tid) >= refs_.size() || end <= beg) return;
+        const std::vector<uint64_t>& lin = refs_[size_t(tid)].linear;
+        if (beg < 0) beg = 0;
+        for (size_t w = size_t(beg >> 14); w < lin.size() && int64_t(w) <= ((end - 1) >> 14) + 1; ++w)
+            if (lin[w] > lo && lin[w] < hi) out->push_back(lin[w]);
+    }
     // Compressed-offset span [first, last] of the BGZF members a fetch(tid, beg, end) may touch (index chunks, before any
     // resume hint).  false when the index has nothing for the region.
     bool region_span(int tid, int64_t beg, int64_t end, uint64_t* c_first, uint64_t* c_last) const
@@ -537,12 +585,13 @@ public:
         uint64_t min_off = 0;
         if (!r.linear.empty()) { size_t w = size_t(beg >> 14); if (w >= r.linear.size()) w = r.linear.size() - 1; min_off = r.linear[w]; }
         const int64_t e1 = end - 1;
+        const uint64_t max_off = upper_clip(tid, end);
         uint64_t lo = ~0ull, hi = 0;
         auto add_bin = [&](uint32_t bin) {
             auto it = std::lower_bound(r.bin_ids.begin(), r.bin_ids.end(), bin);
             if (it == r.bin_ids.end() || *it != bin) return;
             for (const BaiChunk& c : r.bin_chunks[size_t(it - r.bin_ids.begin())])
-                if (c.end > min_off) { lo = std::min(lo, std::max(c.beg, min_off)); hi = std::max(hi, c.end); }
+                if (c.end > min_off && c.beg < max_off) { lo = std::min(lo, std::max(c.beg, min_off)); hi = std::max(hi, std::min(c.end, max_off)); }
         };
         add_bin(0);
         for (int64_t k = 1 + (beg >> 26); k <= 1 + (e1 >> 26); ++k) add_bin(uint32_t(k));
@@ -555,7 +604,7 @@ public:
         return true;
     }
     // The index chunks a fetch(tid, beg, end) walks, as virtual-offset pairs (starts clamped to the linear index like fetch
-    // does); every start and end is a record boundary.  Appends to `out`.
+    // does, ends clamped to upper_clip); every start and end is a record boundary.  Appends to `out`.
     void region_chunks(int tid, int64_t beg, int64_t end, std::vector<BaiChunk>* out) const
     {
         if (tid < 0 || size_t(tid) >= refs_.size() || end <= beg) return;
@@ -564,11 +613,12 @@ public:
         uint64_t min_off = 0;
         if (!r.linear.empty()) { size_t w = size_t(beg >> 14); if (w >= r.linear.size()) w = r.linear.size() - 1; min_off = r.linear[w]; }
         const int64_t e1 = end - 1;
+        const uint64_t max_off = upper_clip(tid, end);
         auto add_bin = [&](uint32_t bin) {
             auto it = std::lower_bound(r.bin_ids.begin(), r.bin_ids.end(), bin);
             if (it == r.bin_ids.end() || *it != bin) return;
             for (const BaiChunk& c : r.bin_chunks[size_t(it - r.bin_ids.begin())])
-                if (c.end > min_off) out->push_back({ std::max(c.beg, min_off), c.end });
+                if (c.end > min_off && c.beg < max_off) out->push_back({ std::max(c.beg, min_off), std::min(c.end, max_off) });
         };
         add_bin(0);
         for (int64_t k = 1 + (beg >> 26); k <= 1 + (e1 >> 26); ++k) add_bin(uint32_t(k));
@@ -582,6 +632,7 @@ public:
         if (!bg_.read_members(c_first, c_last, desc, comp, index)) { if (bg_.bad()) fail(bg_.error()); return false; }
         return true;
     }
+    void set_bulk_allocator(std::function<bool(void**, size_t)> a, std::function<void(void*)> f) { bg_.set_bulk_allocator(std::move(a), std::move(f)); }
     bool prefetch_bulk(uint64_t c_first, uint64_t c_last, const Bgzf::BulkInflate& fn)
     {
         if (!bg_.prefetch_bulk(c_first, c_last, fn)) { if (bg_.bad()) fail(bg_.error()); return false; }

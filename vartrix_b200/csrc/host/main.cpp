@@ -418,6 +418,7 @@ int main(int argc, char** argv)
             c.device = o.devices[size_t(worker_no.fetch_add(1)) % o.devices.size()];
             c.mode = VTX_MODE_CONSENSUS; c.match = 1; c.mismatch = -5; c.gap_open = -5; c.gap_extend = -1; c.min_score = 25;
             if (vtx_create(&c, &ictx) != VTX_OK) { std::lock_guard<std::mutex> g(mu); failed = true; fail_msg = vtx_last_error(nullptr); cv.notify_all(); return; }
+            bam.set_bulk_allocator([](void** q, size_t n) { return vtx_host_alloc(q, n) == VTX_OK; }, [](void* q) { vtx_host_free(q); });
             sa_w.bulk_inflate = [&istatus, ictx](const vtx_bgzf_block* b, uint32_t n, const uint8_t* comp, uint64_t comp_len, uint8_t* out, uint64_t out_len, std::string* err) {
                 istatus.resize(n);
                 if (vtx_bgzf_inflate(ictx, b, n, comp, comp_len, out, out_len, istatus.data(), VTX_BGZF_CHECK_CRC) == VTX_OK) return true;

@@ -282,6 +282,10 @@ inline bool stage_loci_device(const std::vector<VcfRecord>& recs, size_t lo, siz
         return *so <= index.back().stream_off;
     };
     std::vector<uint64_t>& e = out->entry_off;
+    // more places to start walking from: the first record of every 16 kb window (linear index) -- one walker per entry point
+    std::vector<uint64_t> lin;
+    bam.linear_entries(out->tid, out->locus_start.front(), *std::max_element(out->locus_end.begin(), out->locus_end.end()), v_first, v_last, &lin);
+    for (uint64_t v : lin) chunks.push_back({ v, v });
     for (const BaiChunk& c : chunks) {
         uint64_t so;
         if (!stream_of(c.beg, &so)) { *err = "BAM index points outside a BGZF member (index and file do not match)"; return false; }

@@ -1235,7 +1235,7 @@ int vtx_submit_bam(vtx_ctx* ctx, const vtx_bam_shard* sh)
     CK(cudaEventRecord(tr->ev[EV_H2D], ss));
     tr->had_h2d = true;
     // ---- inflate into one contiguous stream ----
-    ENS(sl.stream, size_t(stream_len) + 64); ENS(sl.status, size_t(nm) * 4 + 16); ENS(sl.scalars, 256);
+    ENS(sl.stream, size_t(stream_len) + stage::kWalkWindow + 64);      // the walkers read whole windows ENS(sl.status, size_t(nm) * 4 + 16); ENS(sl.scalars, 256);
     uint32_t* d_sc = P<uint32_t>(sl.scalars);       // [0] walk cursor / inflate cursor, [1] err, [2] max_span, [3] max read, [4..] spare
     CK(cudaMemsetAsync(sl.scalars.p, 0, 256, ss));
     if (nm) {
@@ -1253,7 +1253,7 @@ int vtx_submit_bam(vtx_ctx* ctx, const vtx_bam_shard* sh)
     uint32_t n_rec = 0;
     std::vector<int32_t> h_status(nm);
     if (n_seg) {
-        stage::vtx_k_walk<<<blocks_for(n_seg, 64), 64, 0, ss>>>(sp, n_seg, P<uint64_t>(sl.entry), 0, P<uint32_t>(sl.seg_count), nullptr, nullptr, d_sc + 1);
+        stage::vtx_k_walk<<<blocks_for(n_seg, stage::kWalkWarps), stage::kWalkWarps * 32, 0, ss>>>(sp, n_seg, P<uint64_t>(sl.entry), 0, P<uint32_t>(sl.seg_count), nullptr, nullptr, d_sc + 1);
         rc = scan_u32_on(ctx, ss, P<uint32_t>(sl.seg_count), n_seg, P<uint32_t>(sl.seg_first), ctx->stage_sums);
         if (rc) return fail_out(rc);
     }
@@ -1275,7 +1275,7 @@ int vtx_submit_bam(vtx_ctx* ctx, const vtx_bam_shard* sh)
     uint64_t n_cand = 0;
     uint32_t max_read = 0;
     if (n_rec) {
-        stage::vtx_k_walk<<<blocks_for(n_seg, 64), 64, 0, ss>>>(sp, n_seg, P<uint64_t>(sl.entry), 1, nullptr, P<uint32_t>(sl.seg_first), P<uint64_t>(sl.rec_off), d_sc + 1);
+        stage::vtx_k_walk<<<blocks_for(n_seg, stage::kWalkWarps), stage::kWalkWarps * 32, 0, ss>>>(sp, n_seg, P<uint64_t>(sl.entry), 1, nullptr, P<uint32_t>(sl.seg_first), P<uint64_t>(sl.rec_off), d_sc + 1);
         stage::vtx_k_parse<<<blocks_for(n_rec, 256), 256, 0, ss>>>(sp, n_rec, P<uint64_t>(sl.rec_off), P<int32_t>(sl.rec_tid), P<int32_t>(sl.rec_pos),
                                                                    P<int32_t>(sl.rec_end), P<uint32_t>(sl.rec_fm), d_sc + 2);
         CK(cudaMemsetAsync(sl.used.p, 0, nrp * 4, ss));
