@@ -38,6 +38,7 @@ def main():
     ap.add_argument("--stage", nargs="+", default=["host"], choices=["host", "gpu-inflate", "gpu-stage"],
                     help="who decodes the BAM: staging threads, staging threads with device inflate, or the device")
     ap.add_argument("--keep", default="")
+    ap.add_argument("--reps", type=int, default=1, help="runs per configuration; the fastest is reported (the others' wall times are listed)")
     a = ap.parse_args()
     from vartrix_b200 import synth_files
     d = a.keep or tempfile.mkdtemp(prefix="vtx_scale_")
@@ -59,9 +60,17 @@ def main():
                     os.remove(p)
             cmd = [cli, "-v", ds["vcf"], "-b", ds["bam"], "-f", ds["fasta"], "-c", ds["barcodes"], "-o", o, "-s", a.mode, "--threads", str(th),
                    "--log-level", "info", "--devices", dev] + ([] if stage == "host" else ["--" + stage])
-            t0 = time.time()
-            p = subprocess.run(cmd, capture_output=True, text=True, cwd=d)
-            wall = time.time() - t0
+            walls, best = [], None
+            for _ in range(max(1, a.reps)):
+                for q in (o, os.path.join(d, "ref_matrix.mtx")):
+                    if os.path.exists(q):
+                        os.remove(q)
+                t0 = time.time()
+                pr = subprocess.run(cmd, capture_output=True, text=True, cwd=d)
+                walls.append(round(time.time() - t0, 3))
+                if best is None or walls[-1] == min(walls):
+                    best = pr
+            p, wall = best, min(walls)
             err = p.stderr
             def grab(pat, cast=float):
                 m = re.search(pat, err)
@@ -74,7 +83,7 @@ def main():
             gpu = [dict(device=int(m.group(1)), h2d_ms=float(m.group(2)), prep_ms=float(m.group(3)), sw_ms=float(m.group(4)), post_ms=float(m.group(5)), pairs=int(m.group(6)))
                    for m in re.finditer(r"GPU (\d+) device ms: h2d ([\d.]+), prep ([\d.]+), Smith-Waterman ([\d.]+), post ([\d.]+) \((\d+) pairs", err)]
             run = dict(devices=dev, threads=th, stage=stage, mtx_sha1=hashlib.sha1(open(o, "rb").read()).hexdigest()[:12] if os.path.exists(o) else None,
-                       rc=p.returncode, wall_s=round(wall, 3), reads_fetched=reads, pairs_scored=pairs, marks_s=marks, gpu=gpu,
+                       rc=p.returncode, wall_s=round(wall, 3), wall_s_all_reps=walls, reads_fetched=reads, pairs_scored=pairs, marks_s=marks, gpu=gpu,
                        mtx_bytes=os.path.getsize(o) if os.path.exists(o) else None)
             if st and reads:
                 tot, rd, inf, crc, scan = (float(st.group(i)) for i in range(1, 6))

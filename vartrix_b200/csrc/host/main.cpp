@@ -48,7 +48,7 @@ struct Opts {
     std::string scoring = "consensus", bam_tag = "CB", valid_chars = "ATGCatgc", dump_staged;
     long padding = 100, threads = 1, mapq = 0, device = 0, shard_loci = 0;      // 0: chosen from the number of loci and threads
     std::vector<int> devices;          // --devices: the loci are sharded over these GPUs (contiguous ranges, main.rs:250-254)
-    bool primary = false, no_dups = false, umi = false, ref_matrix_given = false, gpu_inflate = false, gpu_stage = false;
+    bool primary = false, no_dups = false, umi = false, ref_matrix_given = false, gpu_inflate = false, gpu_stage = false, cut_at_contigs = false;
 };
 
 void usage()
@@ -78,6 +78,7 @@ void usage()
          "      --shard-loci INT        VCF records per staged shard [up to 2048, fewer for short VCFs]\n"
          "      --gpu-stage             Decode the BAM on the GPU: the host only reads the compressed ranges the loci's index chunks\n"
          "                              span; inflate, record scan, fetch, record filters and tag extraction run on the device\n"
+         "      --cut-at-contigs        End a staged shard where the contig changes (implied by --gpu-stage)\n"
          "      --gpu-inflate           Inflate the BGZF members of every shard on the GPU (one call per shard) instead of on\n"
          "                              the staging threads; for hosts with few cores per GPU\n"
          "      --dump-staged FILE      Stage only, write the shards to FILE (no GPU)");
@@ -136,7 +137,8 @@ bool parse(int argc, char** argv, Opts* o)
         else if (a == "--shard-loci") o->shard_loci = atol(v().c_str());
         else if (a == "--dump-staged") o->dump_staged = v();
         else if (a == "--gpu-inflate") o->gpu_inflate = true;
-        else if (a == "--gpu-stage") o->gpu_stage = true;
+        else if (a == "--gpu-stage") { o->gpu_stage = true; o->cut_at_contigs = true; }
+        else if (a == "--cut-at-contigs") o->cut_at_contigs = true;
         else if (a == "-h" || a == "--help") { usage(); exit(0); }
         else if (a == "-V" || a == "--version") { puts("vartrix_b200 0.1 (vartrix 1.1.22 surface)"); exit(0); }
         else { fprintf(stderr, "error: unknown argument %s\n", argv[i]); return false; }
@@ -352,7 +354,14 @@ int main(int argc, char** argv)
     // default shard size: 2048 loci (~100 k candidates at 50x, enough to fill the GPU), smaller when the VCF is short so that
     // every staging thread still gets ~10 shards (load balance; the GPU is idle most of the time anyway)
     if (o.shard_loci == 0) o.shard_loci = long(std::min<size_t>(2048, std::max<size_t>(128, recs.size() / (size_t(o.threads) * 10 + 1))));
-    const size_t n_shards = (recs.size() + size_t(o.shard_loci) - 1) / size_t(o.shard_loci);
+    // shard k = records [shard_lo[k], shard_lo[k + 1]).  With --gpu-stage (or --cut-at-contigs) a shard also ends where the contig
+    // changes, so that every shard of a sorted VCF can be staged on the device (one contig, ascending positions).
+    std::vector<size_t> shard_lo;
+    for (size_t i = 0, in_shard = 0; i < recs.size(); ++i, ++in_shard) {
+        if (i == 0 || in_shard == size_t(o.shard_loci) || (o.cut_at_contigs && recs[i].chrom != recs[i - 1].chrom)) { shard_lo.push_back(i); in_shard = 0; }
+    }
+    const size_t n_shards = shard_lo.size();
+    shard_lo.push_back(recs.size());
 
     // Loci -> GPUs: contiguous ranges like the reference's static chunks (main.rs:250-254), balanced by the compressed
     // bytes of BAM each shard spans (BAI linear index) -- a cheap stand-in for the candidate count, known before any decode.
@@ -360,8 +369,8 @@ int main(int argc, char** argv)
         std::vector<double> w(n_shards, 1.0);
         double total = 0;
         for (size_t k = 0; k < n_shards; ++k) {
-            const VcfRecord& a = recs[k * size_t(o.shard_loci)];
-            const VcfRecord& z = recs[std::min(recs.size(), (k + 1) * size_t(o.shard_loci)) - 1];
+            const VcfRecord& a = recs[shard_lo[k]];
+            const VcfRecord& z = recs[shard_lo[k + 1] - 1];
             if (a.chrom == z.chrom) {
                 const int tid = b0.tid_of(a.chrom);
                 const uint64_t f0 = b0.linear_offset(tid, a.pos0), f1 = b0.linear_offset(tid, z.pos0 + int64_t(z.alleles[0].size()) + (1 << 14));
@@ -432,7 +441,7 @@ int main(int argc, char** argv)
             const size_t k = order[i];
             Lane& ln = lanes[lane_of[k]];
             { std::unique_lock<std::mutex> g(mu); cv.wait(g, [&] { return failed || k - ln.lo < ln.consumed + window; }); if (failed) return; }
-            const size_t lo = k * size_t(o.shard_loci), hi = std::min(recs.size(), lo + size_t(o.shard_loci));
+            const size_t lo = shard_lo[k], hi = shard_lo[k + 1];
             if (gpu_stage) {
                 auto ds = std::make_unique<DeviceShard>();
                 bool supported = true;
@@ -505,7 +514,7 @@ int main(int argc, char** argv)
                 }
                 sh = std::make_unique<StagedShard>();
                 std::string e;
-                const size_t lo = k * size_t(o.shard_loci), hi = std::min(recs.size(), lo + size_t(o.shard_loci));
+                const size_t lo = shard_lo[k], hi = shard_lo[k + 1];
                 if (!stage_loci(recs, lo, hi, ln.fb_fa, ln.fb_bam, sa, umis, sh.get(), &e)) { ln.err = e; ln.rc = 1; break; }
                 ++ln.host_fallbacks;
             }
@@ -531,7 +540,7 @@ int main(int argc, char** argv)
         }
         ln.dev = tmp;
     };
-    LOG_INFO("[%.3f s] staging on %ld thread(s) for %zu GPU(s), %zu shards of %ld records", now_s(), o.threads, n_dev, n_shards, o.shard_loci);
+    LOG_INFO("[%.3f s] staging on %ld thread(s) for %zu GPU(s), %zu shards of up to %ld records", now_s(), o.threads, n_dev, n_shards, o.shard_loci);
     {
         std::vector<std::thread> lane_threads;
         for (size_t d = 1; d < n_dev; ++d) lane_threads.emplace_back(consume, std::ref(lanes[d]));

@@ -1235,7 +1235,8 @@ int vtx_submit_bam(vtx_ctx* ctx, const vtx_bam_shard* sh)
     CK(cudaEventRecord(tr->ev[EV_H2D], ss));
     tr->had_h2d = true;
     // ---- inflate into one contiguous stream ----
-    ENS(sl.stream, size_t(stream_len) + stage::kWalkWindow + 64);      // the walkers read whole windows ENS(sl.status, size_t(nm) * 4 + 16); ENS(sl.scalars, 256);
+    ENS(sl.stream, size_t(stream_len) + stage::kWalkWindow + 64);      // the walkers read whole windows
+    ENS(sl.status, size_t(nm) * 4 + 16); ENS(sl.scalars, 256);
     uint32_t* d_sc = P<uint32_t>(sl.scalars);       // [0] walk cursor / inflate cursor, [1] err, [2] max_span, [3] max read, [4..] spare
     CK(cudaMemsetAsync(sl.scalars.p, 0, 256, ss));
     if (nm) {
