@@ -96,7 +96,8 @@ def test_cli_shards_loci_over_two_gpus(tmp_path):
     ds = synth_files.write_dataset(str(tmp_path / "files"), n_loci=600, n_barcodes=80, depth=25, read_len=100, seed=13)
     cli = os.path.join(ROOT, "vartrix_b200", "bin", "vartrix_b200")
     outs = {}
-    for name, dev in (("one", ["--device", "0"]), ("two", ["--devices", "0,1"]), ("two_rev", ["--devices", "1,0"])):
+    for name, dev in (("one", ["--device", "0"]), ("two", ["--devices", "0,1"]), ("two_rev", ["--devices", "1,0"]),
+                      ("two_dev_staged", ["--devices", "0,1", "--gpu-stage"])):          # each GPU decodes the BAM ranges of its own loci
         d = tmp_path / name; d.mkdir()
         cmd = [cli, "-v", ds["vcf"], "-b", ds["bam"], "-f", ds["fasta"], "-c", ds["barcodes"], "-o", str(d / "out.mtx"), "--ref-matrix", str(d / "ref.mtx"),
                "-s", "coverage", "--umi", "--threads", "4", "--shard-loci", "37", "--log-level", "info", *dev]
@@ -105,4 +106,4 @@ def test_cli_shards_loci_over_two_gpus(tmp_path):
         outs[name] = (open(d / "out.mtx").read(), open(d / "ref.mtx").read(),
                       [ln for ln in r.stderr.splitlines() if "Number of" in ln])
     assert outs["one"][0].count("\n") > 1000
-    assert outs["two"] == outs["one"] and outs["two_rev"] == outs["one"]
+    assert outs["two"] == outs["one"] and outs["two_rev"] == outs["one"] and outs["two_dev_staged"] == outs["one"]
