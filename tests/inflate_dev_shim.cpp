@@ -15,7 +15,10 @@ extern "C" int vtx_test_inflate_dev(const unsigned char* in, unsigned long in_le
     Sym batch[32];
     size_t op = 0;
     while (st.status == kOk && st.phase != 3) {
+        const uint32_t word0 = st.word; const int phase0 = st.phase, cnt0 = st.bitcnt; const uint32_t left0 = st.stored_left;
         const int n = decode_batch(st, T, lens, batch, 32);
+        // what the kernel relies on: a call reads less than kMaxInputPerCall bytes beyond where it started
+        if (st.phase != 2 && st.word > word0 + kMaxInputPerCall / 4 + 2) return -2;
         for (int k = 0; k < n; ++k) {
             const Sym& sy = batch[k];
             if (op + sy.len > out_len) return kBadSize;
@@ -24,7 +27,8 @@ extern "C" int vtx_test_inflate_dev(const unsigned char* in, unsigned long in_le
             else memcpy(out + op, reinterpret_cast<const uint8_t*>(buf.data()) + sy.arg, sy.len);
             op += sy.len;
         }
-        if (n == 0 && st.status == kOk && st.phase != 3) return -1;      // no progress: would loop forever
+        if (n == 0 && st.status == kOk && st.phase != 3 && st.word == word0 && st.phase == phase0 && st.bitcnt == cnt0 && st.stored_left == left0)
+            return -1;                                                   // no progress: would loop forever
     }
     return st.status;
 }

@@ -82,7 +82,9 @@ def main():
             st = re.search(r"Staging thread-seconds: total ([\d.]+) = file read ([\d.]+) \+ inflate ([\d.]+) \+ crc32 ([\d.]+) \+ record scan / filters / packing ([\d.]+); (\d+) BGZF blocks, ([\d.]+) MB inflated; copy into pinned arenas ([\d.]+) s \(([\d.]+) MB\)", err)
             gpu = [dict(device=int(m.group(1)), h2d_ms=float(m.group(2)), prep_ms=float(m.group(3)), sw_ms=float(m.group(4)), post_ms=float(m.group(5)), pairs=int(m.group(6)))
                    for m in re.finditer(r"GPU (\d+) device ms: h2d ([\d.]+), prep ([\d.]+), Smith-Waterman ([\d.]+), post ([\d.]+) \((\d+) pairs", err)]
-            run = dict(devices=dev, threads=th, stage=stage, mtx_sha1=hashlib.sha1(open(o, "rb").read()).hexdigest()[:12] if os.path.exists(o) else None,
+            lanes = [dict(device=int(m.group(1)), engine_up_s=float(m.group(2)), consumer_wait_s=float(m.group(3)), submit_s=float(m.group(4)))
+                     for m in re.finditer(r"GPU (\d+): engine up at ([\d.]+) s; consumer waited ([\d.]+) s for staged shards, spent ([\d.]+) s submitting", err)]
+            run = dict(lanes=lanes, devices=dev, threads=th, stage=stage, mtx_sha1=hashlib.sha1(open(o, "rb").read()).hexdigest()[:12] if os.path.exists(o) else None,
                        rc=p.returncode, wall_s=round(wall, 3), wall_s_all_reps=walls, reads_fetched=reads, pairs_scored=pairs, marks_s=marks, gpu=gpu,
                        mtx_bytes=os.path.getsize(o) if os.path.exists(o) else None)
             if st and reads:

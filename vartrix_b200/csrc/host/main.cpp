@@ -277,6 +277,7 @@ struct Lane {
     std::string err;
     int rc = 0;
     vtx_result dev{};                   // this lane's triplets on its device
+    double ready_s = 0, wait_s = 0, submit_s = 0;      // engine up at; consumer: waiting for staged shards / inside submit calls
     Fasta fb_fa; BamFile fb_bam; bool fb_open = false; size_t host_fallbacks = 0;    // --gpu-stage: shards the device sent back
 };
 
@@ -317,6 +318,7 @@ int main(int argc, char** argv)
                 if (vtx_create(&cfg, &ln.ctx) != VTX_OK) { ln.err = vtx_last_error(nullptr); return 1; }
                 if (vtx_set_barcodes(ln.ctx, bcs.bytes.data(), bcs.off.data(), uint32_t(bcs.keys.size())) != VTX_OK) { ln.err = vtx_last_error(ln.ctx); return 1; }
                 if (n_dev > 1 && vtx_comm_init(ln.ctx, nccl_id, int32_t(d), int32_t(n_dev)) != VTX_OK) { ln.err = vtx_last_error(ln.ctx); return 1; }
+                ln.ready_s = now_s();
                 return 0;
             });
         }
@@ -484,13 +486,17 @@ int main(int argc, char** argv)
             std::unique_ptr<StagedShard> sh;
             std::unique_ptr<DeviceShard> ds;
             {
+                const double t_w = now_s();
                 std::unique_lock<std::mutex> g(mu);
                 cv.wait(g, [&] { return failed || ready[k] || ready_dev[k]; });
                 if (failed) { ln.rc = 1; break; }
                 sh = std::move(ready[k]); ds = std::move(ready_dev[k]);
                 ln.consumed = k - ln.lo + 1;
+                ln.wait_s += now_s() - t_w;
             }
             cv.notify_all();
+            const double t_sub = now_s();
+            struct SubmitClock { Lane& l; double t0; ~SubmitClock() { l.submit_s += now_s() - t0; } } submit_clock{ ln, t_sub };
             if (ds && dump) {                   // test dump of the host's share: loci, member table, compressed bytes, record boundaries
                 auto put = [&](const void* p, size_t bytes) { uint64_t n = bytes; fwrite(&n, 8, 1, dump); if (bytes) fwrite(p, 1, bytes, dump); };
                 fwrite("VTXD", 1, 4, dump);
@@ -552,6 +558,7 @@ int main(int argc, char** argv)
     for (Lane& ln : lanes) {
         hm.add(ln.hm);
         if (ln.rc) rc = 1;
+        if (ln.ctx) LOG_INFO("GPU %d: engine up at %.3f s; consumer waited %.3f s for staged shards, spent %.3f s submitting", ln.device, ln.ready_s, ln.wait_s, ln.submit_s);
         if (gpu_stage && ln.ctx && !ln.rc) {          // the record-filter counters of the shards the device staged
             vtx_bam_metrics bm{};
             if (vtx_bam_metrics_get(ln.ctx, &bm) == VTX_OK) {

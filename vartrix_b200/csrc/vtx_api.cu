@@ -81,6 +81,7 @@ struct vtx_ctx {
     DBuf x_read_off, x_read_len, x_units, x_off4;      // slim layout expanded to the internal read arrays
     DBuf band_scratch;                                  // VTX_BAND_MODEL work buffers, one slice per resident warp
     DBuf inf_comp, inf_out, inf_desc, inf_status;       // vtx_bgzf_inflate
+    bool inflate_attr_set = false;
     StageSlot sslot[2];                                 // vtx_submit_bam
     uint64_t n_bam_submits = 0;
     cudaStream_t stage_stream = nullptr;
@@ -1117,6 +1118,14 @@ int vtx_submit2_device(vtx_ctx* ctx, const vtx_batch2* db, uint32_t max_read_len
     return process_batch(ctx, d, tr);
 }
 
+static int inflate_attr(vtx_ctx* ctx)        // the inflate kernel's tables + input windows need the opt-in shared-memory size
+{
+    if (ctx->inflate_attr_set) return VTX_OK;
+    CK(cudaFuncSetAttribute(inflate::vtx_k_bgzf_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, int(inflate::inflate_smem_bytes())));
+    ctx->inflate_attr_set = true;
+    return VTX_OK;
+}
+
 int vtx_bgzf_inflate(vtx_ctx* ctx, const vtx_bgzf_block* blocks, uint32_t n_blocks, const uint8_t* comp, uint64_t comp_len,
                      uint8_t* out, uint64_t out_len, int32_t* status, uint32_t flags)
 {
@@ -1141,7 +1150,8 @@ int vtx_bgzf_inflate(vtx_ctx* ctx, const vtx_bgzf_block* blocks, uint32_t n_bloc
     CK(cudaMemcpyAsync(ctx->inf_desc.p, blocks, size_t(n_blocks) * sizeof(vtx_bgzf_block), cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(ctx->tile_counters.p, 0, 64, st));
     const unsigned ctas = unsigned(std::min<uint64_t>((n_blocks + inflate::kInflateWarps - 1) / inflate::kInflateWarps, uint64_t(ctx->n_sm) * 6));
-    inflate::vtx_k_bgzf_inflate<<<ctas, inflate::kInflateWarps * 32, 0, st>>>(
+    if (int rc_attr = inflate_attr(ctx)) return rc_attr;
+    inflate::vtx_k_bgzf_inflate<<<ctas, inflate::kInflateWarps * 32, inflate::inflate_smem_bytes(), st>>>(
         P<inflate::BlockDesc>(ctx->inf_desc), n_blocks, P<uint8_t>(ctx->inf_comp), P<uint8_t>(ctx->inf_out), P<int32_t>(ctx->inf_status),
         P<uint32_t>(ctx->tile_counters), (flags & VTX_BGZF_CHECK_CRC) ? 1 : 0);
     CK(cudaGetLastError());
@@ -1241,7 +1251,8 @@ int vtx_submit_bam(vtx_ctx* ctx, const vtx_bam_shard* sh)
     CK(cudaMemsetAsync(sl.scalars.p, 0, 256, ss));
     if (nm) {
         const unsigned ctas = unsigned(std::min<uint64_t>((nm + inflate::kInflateWarps - 1) / inflate::kInflateWarps, uint64_t(ctx->n_sm) * 6));
-        inflate::vtx_k_bgzf_inflate<<<ctas, inflate::kInflateWarps * 32, 0, ss>>>(P<inflate::BlockDesc>(sl.desc), nm, P<uint8_t>(sl.comp), P<uint8_t>(sl.stream),
+        if (int rc_attr = inflate_attr(ctx)) return fail_out(rc_attr);
+        inflate::vtx_k_bgzf_inflate<<<ctas, inflate::kInflateWarps * 32, inflate::inflate_smem_bytes(), ss>>>(P<inflate::BlockDesc>(sl.desc), nm, P<uint8_t>(sl.comp), P<uint8_t>(sl.stream),
                                                                                  P<int32_t>(sl.status), d_sc, 1);
         CK(cudaGetLastError());
     }

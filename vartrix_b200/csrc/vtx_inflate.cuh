@@ -142,13 +142,14 @@ struct State {
     int phase;                  // 0 block header next, 1 inside a Huffman block, 2 inside a stored block, 3 done
     int final_block;
     uint32_t stored_left, stored_pos;
+    int drop;                   // bits to discard after the next refill (byte position behind a stored block)
     int status;
 };
 
 __host__ __device__ inline void state_init(State& s, const uint8_t* in, uint32_t in_len, uint32_t out_len)
 {
     s.in32 = reinterpret_cast<const uint32_t*>(in); s.in_len = in_len; s.word = 0; s.bitbuf = 0; s.bitcnt = 0;
-    s.out_len = out_len; s.op = 0; s.phase = 0; s.final_block = 0; s.stored_left = 0; s.stored_pos = 0; s.status = kOk;
+    s.out_len = out_len; s.op = 0; s.phase = 0; s.final_block = 0; s.stored_left = 0; s.stored_pos = 0; s.drop = 0; s.status = kOk;
 }
 __host__ __device__ inline void refill(State& s)
 {
@@ -157,6 +158,7 @@ __host__ __device__ inline void refill(State& s)
         const uint32_t w = s.word < max_word ? s.in32[s.word] : 0u;
         s.bitbuf |= uint64_t(w) << s.bitcnt; s.bitcnt += 32; ++s.word;
     }
+    if (s.drop) { s.bitbuf >>= s.drop; s.bitcnt -= s.drop; s.drop = 0; }       // <= 24 bits of >= 64: still > 32 valid bits
 }
 __host__ __device__ inline bool overrun(const State& s)
 {
@@ -181,12 +183,10 @@ __host__ __device__ inline bool next_block(State& s, Tables& T, uint8_t* lens /*
         const uint64_t pos_bits = uint64_t(s.word) * 32 - uint64_t(s.bitcnt);           // byte aligned here
         s.stored_pos = uint32_t(pos_bits >> 3); s.stored_left = len;
         if (uint64_t(s.stored_pos) + len > s.in_len || uint64_t(s.op) + len > s.out_len) { s.status = kBadStored; return false; }
-        // skip the stored bytes in the bit reader
+        // skip the stored bytes in the bit reader; the words behind them are only touched by the next refill (the kernel may
+        // have to move its input window first)
         const uint32_t after = s.stored_pos + len;
-        s.word = after / 4; s.bitbuf = 0; s.bitcnt = 0;
-        refill(s);
-        const int skip = int(after & 3) * 8;
-        s.bitbuf >>= skip; s.bitcnt -= skip;
+        s.word = after / 4; s.bitbuf = 0; s.bitcnt = 0; s.drop = int(after & 3) * 8;
         s.phase = 2;
         return true;
     }
@@ -243,14 +243,19 @@ __host__ __device__ inline bool next_block(State& s, Tables& T, uint8_t* lens /*
     return true;
 }
 
-// Decode up to `cap` symbols.  Returns the number decoded; s.phase == 3 when the stream has ended, s.status != 0 on error.
+// Decode up to `cap` (<= 32) symbols; a call that meets a block header decodes the header and returns.  Returns the number of
+// symbols decoded (0 is progress too when the phase or the input position moved); s.phase == 3 when the stream has ended,
+// s.status != 0 on error.
+constexpr uint32_t kMaxInputPerCall = 1024;        // bytes a call may read beyond the position it starts at (see above), with margin
 __host__ __device__ inline int decode_batch(State& s, Tables& T, uint8_t* lens, Sym* batch, int cap)
 {
     int n = 0;
     while (n < cap && s.status == kOk && s.phase != 3) {
         if (s.phase == 0) {
-            if (!next_block(s, T, lens)) break;
-            continue;
+            // one header per call, and nothing after it: a call then reads less than kMaxInputPerCall bytes of input (header
+            // <= 563 bytes, 32 symbols <= 192), and a stored block's jump ahead is followed by a return
+            next_block(s, T, lens);
+            break;
         }
         if (s.phase == 2) {                                  // stored run: at most 256 bytes per symbol keeps the apply step balanced
             if (s.stored_left == 0) { s.phase = s.final_block ? 3 : 0; continue; }
@@ -316,12 +321,18 @@ struct BlockDesc {                 // one BGZF member
     uint32_t pad;
 };
 
+constexpr int kInWords = 512;                     // input window per warp: 2 KB of the member's payload in shared memory
+static_assert(kMaxInputPerCall % 4 == 0 && kInWords * 4 >= 2 * int(kMaxInputPerCall), "a call must fit behind any start inside the first half");
+
 struct WarpShared {
     Tables T;
     uint8_t lens[512];
     Sym batch[kBatch];
+    uint32_t in_win[kInWords];     // payload words [win_first, win_first + kInWords): the bit reader's refills never leave it
     int n, status, done;
+    uint32_t reload;               // first word of the window to load next, or ~0
 };
+__host__ __device__ constexpr size_t inflate_smem_bytes() { return sizeof(WarpShared) * kInflateWarps + 256 * 4; }
 
 // CRC-32 (IEEE, reflected) of a member's output by the whole warp: every lane takes a contiguous slice, the slices are
 // combined with x^(8 len) mod P multiplications (the classic crc32_combine, done as 32 shift/xor steps per power).
@@ -370,8 +381,9 @@ __global__ void __launch_bounds__(kInflateWarps * 32) vtx_k_bgzf_inflate(const B
                                                                           const uint8_t* __restrict__ comp, uint8_t* __restrict__ out,
                                                                           int32_t* __restrict__ status, uint32_t* __restrict__ cursor, int check_crc)
 {
-    __shared__ WarpShared ws_all[kInflateWarps];
-    __shared__ uint32_t crc_table[256];
+    extern __shared__ __align__(16) uint8_t inflate_smem[];
+    WarpShared* ws_all = reinterpret_cast<WarpShared*>(inflate_smem);
+    uint32_t* crc_table = reinterpret_cast<uint32_t*>(inflate_smem + sizeof(WarpShared) * kInflateWarps);
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
         uint32_t c = i;
         for (int k = 0; k < 8; ++k) c = (c >> 1) ^ ((c & 1u) ? 0xEDB88320u : 0u);
@@ -388,16 +400,31 @@ __global__ void __launch_bounds__(kInflateWarps * 32) vtx_k_bgzf_inflate(const B
         const BlockDesc bd = blocks[b];
         uint8_t* o = out + bd.out_off;
         State st;
+        const uint32_t* in_g = reinterpret_cast<const uint32_t*>(comp + bd.in_off);
+        const uint32_t max_word = (bd.in_len + 3) / 4 + 1;           // as in refill(): words behind it read as zero
+        uint32_t win_first = 0;
         if (lane == 0) {
             state_init(st, comp + bd.in_off, bd.in_len, bd.out_len);
             if (bd.out_len > 65536u || (bd.in_off & 3)) st.status = kBadSize;
-            ws.done = 0;
+            ws.done = 0; ws.reload = 0;
         }
         uint32_t op = 0;
         for (;;) {
+            // the dependent chain of the bit reader runs on shared memory: the warp moves the window when the next call could
+            // leave it (an L2 round trip per ~1 KB of input instead of one per 4 bytes)
+            __syncwarp();
+            const uint32_t reload = ws.reload;
+            if (reload != 0xFFFFFFFFu) {
+                for (int i = lane; i < kInWords; i += 32) ws.in_win[i] = reload + i < max_word ? __ldg(in_g + reload + i) : 0u;
+                win_first = reload;
+            }
+            __syncwarp();
             if (lane == 0) {
+                st.in32 = ws.in_win - win_first;                   // in32[word] for word in [win_first, win_first + kInWords)
                 ws.n = st.status == kOk ? decode_batch(st, ws.T, ws.lens, ws.batch, kBatch) : 0;
                 ws.status = st.status; ws.done = (st.phase == 3 || st.status != kOk) ? 1 : 0;
+                // refills of the next call touch words [st.word, st.word + kMaxInputPerCall / 4 + 2)
+                ws.reload = (st.word < win_first || st.word + kMaxInputPerCall / 4 + 2 > win_first + kInWords) ? st.word : 0xFFFFFFFFu;
             }
             __syncwarp();
             const int n = ws.n;
