@@ -293,6 +293,16 @@ int main(int argc, char** argv)
     std::string err;
     const bool dumping = !o.dump_staged.empty();
 
+    // Only the requested GPUs become visible to CUDA (unless the caller already chose): on an 8-GPU host, initialising the
+    // driver with all devices visible takes 6-7 s even for --device 0, with one visible ~1 s.  `cuda_index` is what CUDA calls
+    // the device from here on; logs keep the user's numbering.
+    std::vector<int> cuda_index(o.devices.begin(), o.devices.end());
+    if (!dumping && !getenv("CUDA_VISIBLE_DEVICES")) {
+        std::string vis;
+        for (size_t d = 0; d < o.devices.size(); ++d) { vis += (d ? "," : "") + std::to_string(o.devices[d]); cuda_index[d] = int(d); }
+        setenv("CUDA_VISIBLE_DEVICES", vis.c_str(), 1);
+    }
+
     BarcodeList bcs;
     if (!load_barcodes(o.barcodes, &bcs, &err)) { LOG_ERR("%s", err.c_str()); return 1; }
     LOG_INFO("Loaded %zu barcodes", bcs.keys.size());
@@ -310,7 +320,7 @@ int main(int argc, char** argv)
             engine_ready[d] = std::async(std::launch::async, [&, d]() -> int {
                 Lane& ln = lanes[d];
                 vtx_config cfg{};
-                cfg.device = ln.device;
+                cfg.device = cuda_index[d];
                 cfg.mode = o.scoring == "consensus" ? VTX_MODE_CONSENSUS : o.scoring == "coverage" ? VTX_MODE_COVERAGE : VTX_MODE_ALT_FRAC;
                 cfg.flags = VTX_F_VALUES_ONLY;       // the writers need row, col and the matrix values only
                 cfg.use_umi = o.umi; cfg.match = 1; cfg.mismatch = -5; cfg.gap_open = -5; cfg.gap_extend = -1; cfg.min_score = 25;
@@ -355,6 +365,9 @@ int main(int argc, char** argv)
     // ---- staging: worker threads produce shards of `shard_loci` records; one lane per GPU consumes its range in order ----
     // default shard size: 2048 loci (~100 k candidates at 50x, enough to fill the GPU), smaller when the VCF is short so that
     // every staging thread still gets ~10 shards (load balance; the GPU is idle most of the time anyway)
+    // --gpu-stage: the host's share of a shard is small and the device's fixed cost per shard (three short waits, ~30 launches)
+    // is what counts: 4096 loci (~200 k reads at 50x), fewer only so that every GPU still gets a few shards to pipeline
+    if (o.shard_loci == 0 && o.gpu_stage) o.shard_loci = long(std::min<size_t>(4096, std::max<size_t>(256, recs.size() / (o.devices.size() * 6 + 1))));
     if (o.shard_loci == 0) o.shard_loci = long(std::min<size_t>(2048, std::max<size_t>(128, recs.size() / (size_t(o.threads) * 10 + 1))));
     // shard k = records [shard_lo[k], shard_lo[k + 1]).  With --gpu-stage (or --cut-at-contigs) a shard also ends where the contig
     // changes, so that every shard of a sorted VCF can be staged on the device (one contig, ascending positions).
@@ -426,7 +439,7 @@ int main(int argc, char** argv)
             };
         } else if (o.gpu_inflate) {
             vtx_config c{};
-            c.device = o.devices[size_t(worker_no.fetch_add(1)) % o.devices.size()];
+            c.device = cuda_index[size_t(worker_no.fetch_add(1)) % cuda_index.size()];
             c.mode = VTX_MODE_CONSENSUS; c.match = 1; c.mismatch = -5; c.gap_open = -5; c.gap_extend = -1; c.min_score = 25;
             if (vtx_create(&c, &ictx) != VTX_OK) { std::lock_guard<std::mutex> g(mu); failed = true; fail_msg = vtx_last_error(nullptr); cv.notify_all(); return; }
             bam.set_bulk_allocator([](void** q, size_t n) { return vtx_host_alloc(q, n) == VTX_OK; }, [](void* q) { vtx_host_free(q); });
