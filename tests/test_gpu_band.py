@@ -3,6 +3,7 @@ band model (vtxo_sw_band_model: k-mer hits, best chain, +-w band, lazy ends; no 
 pair and whole matrices -- on the shapes where band and full matrix agree and on those where they do not (short tandem
 repeats, indels longer than W).  The default mode stays the full matrix."""
 import ctypes
+import zlib
 import os
 import sys
 
@@ -79,7 +80,7 @@ def test_band_mode_scores_equal_the_oracle_band_model(oracle, name):
     import band_exposure as bx
     import vartrix_b200 as vb
     kw = dict(FAMILIES[name]); kw["genome"] = bx.rand_seq if kw["genome"] == "rand" else bx.str_seq
-    triples = bx.family(np.random.default_rng(hash(name) % 1000), **kw)
+    triples = bx.family(np.random.default_rng(zlib.crc32(name.encode()) % 1000), **kw)        # str hashes change from run to run
     # ragged and tiny reads too: shorter than k (no hits -> full matrix), empty
     triples += [(triples[0][0][:n], triples[0][1], triples[0][2]) for n in (0, 1, 5, 6, 7, 33, 100)]
     sb, bcs = _staged_from_triples(triples)

@@ -20,6 +20,7 @@ namespace vtx {
 
 constexpr int kBandThreads = 128;                 // 4 warps per CTA
 constexpr int32_t kBandNegInf = -(1 << 29);
+constexpr int kBandJ = 8;                         // window k-mers per lane kept in registers while hits are enumerated (windows <= 256 + k)
 
 struct BandArgs {
     SwArgs sw;                  // batch, pair lists, epilogue (tile fields unused)
@@ -83,17 +84,42 @@ __device__ int32_t band_align(const BandArgs& a, uint8_t* ws, const uint8_t* nib
         for (int32_t j = lane; j + k <= n; j += 32) { uint64_t c = 0; for (int32_t t = 0; t < k; ++t) c = (c << 8) | __ldg(hap + j + t); yk[j] = c; }
         __syncwarp();
         const int32_t ni = m - k + 1, nj = n - k + 1;
-        for (int32_t i = 0; i < ni; ++i) {
-            const uint64_t xi = xk[i];
-            for (int32_t j0 = 0; j0 < nj; j0 += 32) {
-                const int32_t j = j0 + lane;
-                const bool hit = j < nj && yk[j] == xi;
-                const uint32_t mask = __ballot_sync(0xffffffffu, hit);
-                if (hit) {
-                    const uint32_t slot = nh + __popc(mask & ((1u << lane) - 1u));
-                    if (slot < a.hit_cap) hits[slot] = (uint32_t(i) << 16) | uint32_t(j);
+        if (nj <= 32 * kBandJ) {
+            // the window's k-mers stay in registers (lane l holds j = l, l + 32, ...): per read position one broadcast load
+            // and kBandJ compares; the (q, lane) order of the ballots is ascending j
+            uint64_t yr[kBandJ];
+#pragma unroll
+            for (int q = 0; q < kBandJ; ++q) { const int32_t j = lane + 32 * q; yr[q] = j < nj ? yk[j] : ~0ull; }       // ~0 is no k-mer code (k <= 8 bytes of ASCII)
+            for (int32_t i = 0; i < ni; ++i) {
+                const uint64_t xi = xk[i];
+                uint32_t mine = 0;
+#pragma unroll
+                for (int q = 0; q < kBandJ; ++q) mine |= uint32_t(yr[q] == xi) << q;
+                if (!__any_sync(0xffffffffu, mine != 0)) continue;
+#pragma unroll
+                for (int q = 0; q < kBandJ; ++q) {
+                    const bool hit = (mine >> q) & 1u;
+                    const uint32_t mask = __ballot_sync(0xffffffffu, hit);
+                    if (hit) {
+                        const uint32_t slot = nh + __popc(mask & ((1u << lane) - 1u));
+                        if (slot < a.hit_cap) hits[slot] = (uint32_t(i) << 16) | uint32_t(lane + 32 * q);
+                    }
+                    nh += __popc(mask);
                 }
-                nh += __popc(mask);
+            }
+        } else {
+            for (int32_t i = 0; i < ni; ++i) {
+                const uint64_t xi = xk[i];
+                for (int32_t j0 = 0; j0 < nj; j0 += 32) {
+                    const int32_t j = j0 + lane;
+                    const bool hit = j < nj && yk[j] == xi;
+                    const uint32_t mask = __ballot_sync(0xffffffffu, hit);
+                    if (hit) {
+                        const uint32_t slot = nh + __popc(mask & ((1u << lane) - 1u));
+                        if (slot < a.hit_cap) hits[slot] = (uint32_t(i) << 16) | uint32_t(j);
+                    }
+                    nh += __popc(mask);
+                }
             }
         }
         __syncwarp();
@@ -115,10 +141,16 @@ __device__ int32_t band_align(const BandArgs& a, uint8_t* ws, const uint8_t* nib
                 if (cand > my) { my = cand; my_b = int32_t(ib); }
             }
             // warp arg-max with ties to the smallest predecessor index; a candidate equal to k never replaces "start here"
+            if (nh <= 0xFFFFu && m < 32000) {              // (score, 0xFFFF - index) fits one word: a single REDUX
+                const uint32_t key = (uint32_t(my) << 16) | (my_b == 0x7fffffff ? 0u : 0xFFFFu - uint32_t(my_b));     // "none" sorts last
+                const uint32_t top = __reduce_max_sync(0xffffffffu, key);
+                my = int32_t(top >> 16); my_b = (top & 0xFFFFu) ? int32_t(0xFFFFu - (top & 0xFFFFu)) : 0x7fffffff;
+            } else {
 #pragma unroll
-            for (int o = 16; o >= 1; o >>= 1) {
-                const int32_t os = __shfl_xor_sync(0xffffffffu, my, o), ob = __shfl_xor_sync(0xffffffffu, my_b, o);
-                if (os > my || (os == my && ob < my_b)) { my = os; my_b = ob; }
+                for (int o = 16; o >= 1; o >>= 1) {
+                    const int32_t os = __shfl_xor_sync(0xffffffffu, my, o), ob = __shfl_xor_sync(0xffffffffu, my_b, o);
+                    if (os > my || (os == my && ob < my_b)) { my = os; my_b = ob; }
+                }
             }
             if (lane == 0) { sc[ia] = my; pr[ia] = my_b == 0x7fffffff ? -1 : my_b; }
             if (my > best) { best = my; best_idx = ia; }
@@ -135,7 +167,9 @@ __device__ int32_t band_align(const BandArgs& a, uint8_t* ws, const uint8_t* nib
         int32_t cur = int32_t(best_idx), last_i = -1, last_j = -1, first_i = 0, first_j = 0;
         while (cur >= 0) {
             const int32_t hi_i = int32_t(hits[cur] >> 16), hi_j = int32_t(hits[cur] & 0xFFFFu);
-            for (int32_t t = 0; t <= k; ++t) add_box(hi_i + t, hi_j + t);
+            // the later hit one step down the diagonal already boxed this hit's cells 1..k
+            const int32_t t_end = (last_i == hi_i + 1 && last_j == hi_j + 1) ? 0 : k;
+            for (int32_t t = 0; t <= t_end; ++t) add_box(hi_i + t, hi_j + t);
             if (last_i >= 0) {              // between this hit's end and the later hit's start: straight run, then diagonal
                 int32_t ai = hi_i + k, aj = hi_j + k;
                 while (ai < last_i || aj < last_j) {
