@@ -365,9 +365,10 @@ int main(int argc, char** argv)
     // ---- staging: worker threads produce shards of `shard_loci` records; one lane per GPU consumes its range in order ----
     // default shard size: 2048 loci (~100 k candidates at 50x, enough to fill the GPU), smaller when the VCF is short so that
     // every staging thread still gets ~10 shards (load balance; the GPU is idle most of the time anyway)
-    // --gpu-stage: the host's share of a shard is small and the device's fixed cost per shard (three short waits, ~30 launches)
-    // is what counts: 4096 loci (~200 k reads at 50x), fewer only so that every GPU still gets a few shards to pipeline
-    if (o.shard_loci == 0 && o.gpu_stage) o.shard_loci = long(std::min<size_t>(4096, std::max<size_t>(256, recs.size() / (o.devices.size() * 6 + 1))));
+    // --gpu-stage: the host's share of a shard is small; what counts is the device's fixed cost per shard (three short waits,
+    // ~30 launches) and the inflate kernel, which wants thousands of BGZF members per launch to fill the GPU (one warp each):
+    // 8192 loci (~400 k reads, ~2 000 members at 50x), fewer only so that every GPU still gets a few shards to pipeline
+    if (o.shard_loci == 0 && o.gpu_stage) o.shard_loci = long(std::min<size_t>(8192, std::max<size_t>(256, recs.size() / (o.devices.size() * 6 + 1))));
     if (o.shard_loci == 0) o.shard_loci = long(std::min<size_t>(2048, std::max<size_t>(128, recs.size() / (size_t(o.threads) * 10 + 1))));
     // shard k = records [shard_lo[k], shard_lo[k + 1]).  With --gpu-stage (or --cut-at-contigs) a shard also ends where the contig
     // changes, so that every shard of a sorted VCF can be staged on the device (one contig, ascending positions).

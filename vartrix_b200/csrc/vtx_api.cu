@@ -1149,7 +1149,7 @@ int vtx_bgzf_inflate(vtx_ctx* ctx, const vtx_bgzf_block* blocks, uint32_t n_bloc
     CK(cudaMemcpyAsync(ctx->inf_comp.p, comp, comp_len, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->inf_desc.p, blocks, size_t(n_blocks) * sizeof(vtx_bgzf_block), cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(ctx->tile_counters.p, 0, 64, st));
-    const unsigned ctas = unsigned(std::min<uint64_t>((n_blocks + inflate::kInflateWarps - 1) / inflate::kInflateWarps, uint64_t(ctx->n_sm) * 2));       // two ~80 KB CTAs per SM
+    const unsigned ctas = unsigned(std::min<uint64_t>((n_blocks + inflate::kInflateWarps - 1) / inflate::kInflateWarps, uint64_t(ctx->n_sm) * 6));
     if (int rc_attr = inflate_attr(ctx)) return rc_attr;
     inflate::vtx_k_bgzf_inflate<<<ctas, inflate::kInflateWarps * 32, inflate::inflate_smem_bytes(), st>>>(
         P<inflate::BlockDesc>(ctx->inf_desc), n_blocks, P<uint8_t>(ctx->inf_comp), P<uint8_t>(ctx->inf_out), P<int32_t>(ctx->inf_status),
@@ -1250,7 +1250,7 @@ int vtx_submit_bam(vtx_ctx* ctx, const vtx_bam_shard* sh)
     uint32_t* d_sc = P<uint32_t>(sl.scalars);       // [0] walk cursor / inflate cursor, [1] err, [2] max_span, [3] max read, [4..] spare
     CK(cudaMemsetAsync(sl.scalars.p, 0, 256, ss));
     if (nm) {
-        const unsigned ctas = unsigned(std::min<uint64_t>((nm + inflate::kInflateWarps - 1) / inflate::kInflateWarps, uint64_t(ctx->n_sm) * 2));
+        const unsigned ctas = unsigned(std::min<uint64_t>((nm + inflate::kInflateWarps - 1) / inflate::kInflateWarps, uint64_t(ctx->n_sm) * 6));
         if (int rc_attr = inflate_attr(ctx)) return fail_out(rc_attr);
         inflate::vtx_k_bgzf_inflate<<<ctas, inflate::kInflateWarps * 32, inflate::inflate_smem_bytes(), ss>>>(P<inflate::BlockDesc>(sl.desc), nm, P<uint8_t>(sl.comp), P<uint8_t>(sl.stream),
                                                                                  P<int32_t>(sl.status), d_sc, 1);

@@ -309,12 +309,13 @@ __host__ __device__ inline int decode_batch(State& s, Tables& T, uint8_t* lens, 
 // ---------------------------------------------------------------------------------------------------------------
 // the warp-level kernel
 // ---------------------------------------------------------------------------------------------------------------
-// One warp per CTA: the member's whole output (<= 64 KiB) is assembled in shared memory -- match copies are shared-memory to
-// shared-memory (the first version copied through L2: every match of a batch paid a dependent L2 round trip, 2.9 ms per
-// member) -- and written to global memory once, coalesced, after the CRC has been checked.  ~80 KB per CTA: two per SM.
-constexpr int kInflateWarps = 1;
+// Output goes straight to global memory: a match copy is a dependent L2 round trip and lane 0's symbol decode a chain of
+// dependent ALU and shared-memory operations (~1 k cycles per symbol either way), so a warp takes ~2.9 ms per 64 KB member --
+// and what buys throughput is the number of members in flight: 20 warps per SM hide each other's latencies (2 960 members per
+// wave, ~65 GB/s of inflated bytes when a call brings that many).  Tried and measured worse (round 2): the member's output
+// assembled in 64 KB of shared memory by a lone warp per CTA -- 1.7 ms per member, but only 2 CTAs fit an SM: 11 GB/s.
+constexpr int kInflateWarps = 4;                  // per CTA
 constexpr int kBatch = 32;
-constexpr int kOutBuf = 65536 + 16;               // the output sits at the same offset mod 16 as its place in global memory
 
 struct BlockDesc {                 // one BGZF member
     uint64_t in_off;               // byte offset of its DEFLATE payload in `comp` (multiple of 4; 8 readable bytes behind it)
@@ -325,7 +326,7 @@ struct BlockDesc {                 // one BGZF member
     uint32_t pad;
 };
 
-constexpr int kInWords = 512;                     // input window: 2 KB of the member's payload in shared memory
+constexpr int kInWords = 512;                     // input window per warp: 2 KB of the member's payload in shared memory
 static_assert(kMaxInputPerCall % 4 == 0 && kInWords * 4 >= 2 * int(kMaxInputPerCall), "a call must fit behind any start inside the first half");
 
 struct WarpShared {
@@ -336,7 +337,7 @@ struct WarpShared {
     int n, status, done;
     uint32_t reload;               // first word of the window to load next, or ~0
 };
-__host__ __device__ constexpr size_t inflate_smem_bytes() { return ((sizeof(WarpShared) + 15) & ~size_t(15)) + 256 * 4 + kOutBuf; }
+__host__ __device__ constexpr size_t inflate_smem_bytes() { return sizeof(WarpShared) * kInflateWarps + 256 * 4; }
 
 // CRC-32 (IEEE, reflected) of a member's output by the whole warp: every lane takes a contiguous slice, the slices are
 // combined with x^(8 len) mod P multiplications (the classic crc32_combine, done as 32 shift/xor steps per power).
@@ -361,14 +362,15 @@ __device__ __forceinline__ uint32_t crc_xpow8n(uint32_t n_bytes)           // x^
     }
     return r;
 }
-__device__ uint32_t warp_crc32(const uint8_t* p /* shared */, uint32_t n, const uint32_t* table /* 256 entries, shared */)
+__device__ uint32_t warp_crc32(const uint8_t* p, uint32_t n, const uint32_t* table /* 256 entries, shared */)
 {
     const int lane = threadIdx.x & 31;
     const uint32_t per = (n + 31) / 32;
     const uint32_t b0 = min(n, per * uint32_t(lane)), b1 = min(n, b0 + per);
     uint32_t c = 0;                                     // raw register value without the 0xFFFFFFFF pre/post conditioning
-    for (uint32_t i = b0; i < b1; ++i) c = table[(c ^ p[i]) & 0xFF] ^ (c >> 8);
-    // tree combine: at each level a lane absorbs its right neighbour's slice: crc(A || B) = crc(A) * x^(8 |B|) + crc(B)
+    for (uint32_t i = b0; i < b1; ++i) c = table[(c ^ __ldcg(p + i)) & 0xFF] ^ (c >> 8);
+    // combine left to right: crc(A || B) = crc(A) * x^(8 |B|) + crc(B) for the linear part; the conditioning is added at the end
+    // tree combine: at each level a lane absorbs its right neighbour's slice
     uint32_t len = b1 - b0;
     for (int o = 1; o < 32; o <<= 1) {
         const uint32_t oc = __shfl_down_sync(0xffffffffu, c, o);
@@ -385,23 +387,23 @@ __global__ void __launch_bounds__(kInflateWarps * 32) vtx_k_bgzf_inflate(const B
                                                                           int32_t* __restrict__ status, uint32_t* __restrict__ cursor, int check_crc)
 {
     extern __shared__ __align__(16) uint8_t inflate_smem[];
-    WarpShared& ws = *reinterpret_cast<WarpShared*>(inflate_smem);
-    uint32_t* crc_table = reinterpret_cast<uint32_t*>(inflate_smem + ((sizeof(WarpShared) + 15) & ~size_t(15)));
-    uint8_t* outbuf = reinterpret_cast<uint8_t*>(crc_table + 256);                 // 16-byte aligned
+    WarpShared* ws_all = reinterpret_cast<WarpShared*>(inflate_smem);
+    uint32_t* crc_table = reinterpret_cast<uint32_t*>(inflate_smem + sizeof(WarpShared) * kInflateWarps);
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
         uint32_t c = i;
         for (int k = 0; k < 8; ++k) c = (c >> 1) ^ ((c & 1u) ? 0xEDB88320u : 0u);
         crc_table[i] = c;
     }
     __syncthreads();
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpShared& ws = ws_all[warp];
     for (;;) {
         uint32_t b = 0;
         if (lane == 0) b = atomicAdd(cursor, 1u);
         b = __shfl_sync(0xffffffffu, b, 0);
         if (b >= n_blocks) break;
         const BlockDesc bd = blocks[b];
-        uint8_t* o = outbuf + (bd.out_off & 15);                                   // shared: byte i of the member at o[i]
+        uint8_t* o = out + bd.out_off;
         State st;
         const uint32_t* in_g = reinterpret_cast<const uint32_t*>(comp + bd.in_off);
         const uint32_t max_word = (bd.in_len + 3) / 4 + 1;           // as in refill(): words behind it read as zero
@@ -431,7 +433,7 @@ __global__ void __launch_bounds__(kInflateWarps * 32) vtx_k_bgzf_inflate(const B
             }
             __syncwarp();
             const int n = ws.n;
-            // positions: exclusive scan of the symbol lengths (decode_batch keeps the running total inside out_len <= 64 KiB)
+            // positions: exclusive scan of the symbol lengths
             Sym sy{ 0, 0, 0 };
             if (lane < n) sy = ws.batch[lane];
             uint32_t incl = sy.len;
@@ -449,8 +451,8 @@ __global__ void __launch_bounds__(kInflateWarps * 32) vtx_k_bgzf_inflate(const B
                 const uint32_t kind = __shfl_sync(0xffffffffu, sy.kind, src_lane), pos = __shfl_sync(0xffffffffu, my_pos, src_lane);
                 if (kind == 1) {
                     const uint8_t* srcp = o + pos - arg;
-                    if (arg >= len) { for (uint32_t i = lane; i < len; i += 32) o[pos + i] = srcp[i]; }
-                    else { for (uint32_t i = lane; i < len; i += 32) o[pos + i] = srcp[i % arg]; }
+                    if (arg >= len) { for (uint32_t i = lane; i < len; i += 32) o[pos + i] = __ldcg(srcp + i); }
+                    else { for (uint32_t i = lane; i < len; i += 32) o[pos + i] = __ldcg(srcp + (i % arg)); }
                 } else {
                     const uint8_t* srcp = comp + bd.in_off + arg;
                     for (uint32_t i = lane; i < len; i += 32) o[pos + i] = __ldg(srcp + i);
@@ -459,21 +461,12 @@ __global__ void __launch_bounds__(kInflateWarps * 32) vtx_k_bgzf_inflate(const B
             }
             op += total;
             if (ws.done) break;
+            __syncwarp();
         }
         int stt = ws.status;
-        __syncwarp();
-        if (stt == kOk && check_crc && warp_crc32(o, bd.out_len, crc_table) != bd.crc32) stt = 7;      // CRC mismatch
-        if (stt == kOk) {
-            // flush: shared and global addresses agree mod 16, so whole 16-byte pieces move as one vector each
-            uint8_t* g = out + bd.out_off;
-            const uint32_t len = bd.out_len, sh = uint32_t(bd.out_off & 15);
-            const uint32_t head = min(len, (16u - sh) & 15u);                             // bytes before the first aligned piece
-            for (uint32_t i = lane; i < head; i += 32) g[i] = o[i];
-            const uint32_t body = (len - head) / 16;
-            const uint4* s4 = reinterpret_cast<const uint4*>(o + head);
-            uint4* g4 = reinterpret_cast<uint4*>(g + head);
-            for (uint32_t i = lane; i < body; i += 32) g4[i] = s4[i];
-            for (uint32_t i = head + body * 16 + lane; i < len; i += 32) g[i] = o[i];
+        if (stt == kOk && check_crc) {
+            __syncwarp();
+            if (warp_crc32(o, bd.out_len, crc_table) != bd.crc32) stt = 7;               // CRC mismatch
         }
         if (lane == 0) status[b] = stt;
         __syncwarp();
