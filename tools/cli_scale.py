@@ -38,13 +38,14 @@ def main():
     ap.add_argument("--stage", nargs="+", default=["host"], choices=["host", "gpu-inflate", "gpu-stage"],
                     help="who decodes the BAM: staging threads, staging threads with device inflate, or the device")
     ap.add_argument("--keep", default="")
+    ap.add_argument("--quals", default="missing", choices=["missing", "binned"])
     ap.add_argument("--reps", type=int, default=1, help="runs per configuration; the fastest is reported (the others' wall times are listed)")
     a = ap.parse_args()
     from vartrix_b200 import synth_files
     d = a.keep or tempfile.mkdtemp(prefix="vtx_scale_")
     t0 = time.time()
     if not os.path.exists(os.path.join(d, "reads.bam")):
-        ds = synth_files.write_dataset_fast(d, n_loci=a.loci, n_barcodes=a.barcodes, depth=a.depth, read_len=150, seed=2)
+        ds = synth_files.write_dataset_fast(d, n_loci=a.loci, n_barcodes=a.barcodes, depth=a.depth, read_len=150, seed=2, quals=a.quals)
     else:
         ds = {k: os.path.join(d, v) for k, v in dict(fasta="genome.fa", vcf="variants.vcf", bam="reads.bam", barcodes="barcodes.tsv").items()}
         ds["n_reads"] = a.loci * a.depth
@@ -103,7 +104,7 @@ def main():
                 run["stderr_tail"] = err[-600:] + p.stdout[-300:]
             runs.append(run)
             print(json.dumps(run)[:400], file=sys.stderr)
-    print(json.dumps(dict(what="vartrix_b200 CLI, file -> matrix, config-3-sized synthetic file set", loci=a.loci, depth=a.depth, barcodes=a.barcodes,
+    print(json.dumps(dict(what="vartrix_b200 CLI, file -> matrix, config-3-sized synthetic file set", loci=a.loci, depth=a.depth, barcodes=a.barcodes, quals=a.quals,
                           reads_in_bam=ds.get("n_reads"), bam_bytes=os.path.getsize(ds["bam"]), dataset_generation_s=round(gen_s, 1),
                           host_logical_cpus=os.cpu_count(), cgroup_cpu_quota_cores=quota(), runs=runs), indent=1))
 

@@ -34,12 +34,13 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--loci", type=int, default=20000)
     ap.add_argument("--level", type=int, default=6)
+    ap.add_argument("--quals", default="missing", choices=["missing", "binned"], help="binned: i.i.d. four-level qualities, compression ratio of a real BAM")
     a = ap.parse_args()
     import torch
     import vartrix_b200 as vb
     from vartrix_b200 import _capi, synth_files
     d = tempfile.mkdtemp(prefix="vtx_inf_")
-    ds = synth_files.write_dataset_fast(d, n_loci=a.loci, n_barcodes=5000, depth=50, level=a.level)
+    ds = synth_files.write_dataset_fast(d, n_loci=a.loci, n_barcodes=5000, depth=50, level=a.level, quals=a.quals)
     mem = members_of(ds["bam"])
     n = len(mem)
     t0 = time.perf_counter()
@@ -47,7 +48,7 @@ def main():
     t_zlib = time.perf_counter() - t0
     total_out = sum(len(r) for r in ref); total_in = sum(len(p) for p, _, _ in mem)
     out = dict(what="vtx_bgzf_inflate on the BGZF members of a synthetic BAM (write_dataset_fast)", members=n, compressed_mb=total_in / 1e6, inflated_mb=total_out / 1e6,
-               zlib_level=a.level, zlib_one_thread_mb_s=total_out / 1e6 / t_zlib, calls=[])
+               zlib_level=a.level, quals=a.quals, zlib_one_thread_mb_s=total_out / 1e6 / t_zlib, calls=[])
     with vb.Engine("coverage") as eng:
         for per_call in (64, 256, 1024, 4096, n):
             per_call = min(per_call, n)

@@ -266,10 +266,12 @@ def _reg2bin_vec(beg, end):
 
 
 def write_dataset_fast(out_dir: str, n_loci: int = 100_000, n_barcodes: int = 50_000, depth: int = 50, read_len: int = 150, seed: int = 2,
-                       umi: bool = False, spacing: int = 1200, unlisted_frac: float = 0.05, err: float = 0.005, level: int = 1, line_width: int = 60):
+                       umi: bool = False, spacing: int = 1200, unlisted_frac: float = 0.05, err: float = 0.005, level: int = 1, line_width: int = 60,
+                       quals: str = "missing"):
     """SNV loci `spacing` apart on one contig, `depth` reads of `read_len` bases per locus (start uniform over the
     positions that cover the variant, allele ref/alt 50/50, `err` substitution errors, CIGAR <read_len>M, mapq 60), cell tags
-    16-mer + "-1" with `unlisted_frac` of the reads carrying an unlisted one.  -> dict of paths like write_dataset."""
+    16-mer + "-1" with `unlisted_frac` of the reads carrying an unlisted one; `quals` = "missing" (0xFF) or "binned" (four
+    quality levels, i.i.d.: BGZF then compresses ~3.5x like a real BAM instead of ~10x).  -> dict of paths like write_dataset."""
     os.makedirs(out_dir, exist_ok=True)
     rng = np.random.default_rng(seed)
     paths = {k: os.path.join(out_dir, v) for k, v in dict(fasta="genome.fa", vcf="variants.vcf", bam="reads.bam", barcodes="barcodes.tsv").items()}
@@ -358,7 +360,11 @@ def write_dataset_fast(out_dir: str, n_loci: int = 100_000, n_barcodes: int = 50
         c = 36 + name_len
         put32(c, np.full(n, (read_len << 4) | 0)); c += 4
         rec[:, c:c + nb] = (nibv[:, 0::2] << 4) | nibv[:, 1::2]; c += nb
-        rec[:, c:c + read_len] = 0xFF; c += read_len
+        if quals == "binned":          # four-level binned qualities drawn independently: ~1 bit per base, harsher on DEFLATE than real runs
+            rec[:, c:c + read_len] = np.array([2, 11, 25, 37], np.uint8)[rng.choice(4, size=(n, read_len), p=[0.02, 0.06, 0.12, 0.80])]
+        else:                          # "missing": 0xFF as samtools writes absent qualities
+            rec[:, c:c + read_len] = 0xFF
+        c += read_len
         listed = rng.random(n) >= unlisted_frac
         cbi = np.where(listed, rng.integers(0, n_barcodes, size=n), n_barcodes + rng.integers(0, n_unl, size=n))
         rec[:, c] = ord("C"); rec[:, c + 1] = ord("B"); rec[:, c + 2] = ord("Z"); rec[:, c + 3:c + 21] = tags[cbi]; c += 22
