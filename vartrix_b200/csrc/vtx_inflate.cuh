@@ -250,53 +250,68 @@ constexpr uint32_t kMaxInputPerCall = 1024;        // bytes a call may read beyo
 __host__ __device__ inline int decode_batch(State& s, Tables& T, uint8_t* lens, Sym* batch, int cap)
 {
     int n = 0;
-    while (n < cap && s.status == kOk && s.phase != 3) {
-        if (s.phase == 0) {
-            // one header per call, and nothing after it: a call then reads less than kMaxInputPerCall bytes of input (header
-            // <= 563 bytes, 32 symbols <= 192), and a stored block's jump ahead is followed by a return
-            next_block(s, T, lens);
-            break;
-        }
-        if (s.phase == 2) {                                  // stored run: at most 256 bytes per symbol keeps the apply step balanced
-            if (s.stored_left == 0) { s.phase = s.final_block ? 3 : 0; continue; }
+    if (s.status != kOk || s.phase == 3) return 0;
+    if (s.phase == 0) {
+        // one header per call, and nothing after it: a call then reads less than kMaxInputPerCall bytes of input (header
+        // <= 563 bytes, 32 symbols <= 192), and a stored block's jump ahead is followed by a return
+        next_block(s, T, lens);
+    } else if (s.phase == 2) {                               // stored run: at most 256 bytes per symbol keeps the apply step balanced
+        while (n < cap && s.stored_left) {
             const uint32_t take = s.stored_left < 256u ? s.stored_left : 256u;
             batch[n].kind = 2; batch[n].len = take; batch[n].arg = s.stored_pos; ++n;
             s.stored_pos += take; s.stored_left -= take; s.op += take;
-            continue;
         }
-        refill(s);                                           // > 32 valid bits: one literal/length code (<= 15 + 5)
-        uint32_t e = T.lit[s.bitbuf & ((1u << kLitBits) - 1)];
-        if ((e & kTypeMask) == kTypeSub) e = T.lit[((e >> 13) & 0x1FFFF) + ((s.bitbuf >> kLitBits) & ((1u << ((e >> 8) & 31)) - 1))];
-        uint32_t l = e & 0xFF;
-        if (l == 0) { s.status = kBadStream; break; }
-        s.bitbuf >>= l; s.bitcnt -= int(l);
-        const uint32_t type = e & kTypeMask;
-        if (type == kTypeLiteral) {
-            if (s.op >= s.out_len) { s.status = kBadSize; break; }
-            batch[n].kind = 0; batch[n].len = 1; batch[n].arg = (e >> 13) & 0xFF; ++n; ++s.op;
-            continue;
+        if (s.stored_left == 0) s.phase = s.final_block ? 3 : 0;
+    } else {
+        // Huffman block: the bit reader lives in registers for the whole batch (the State may sit in local memory)
+        uint64_t bitbuf = s.bitbuf;
+        int bitcnt = s.bitcnt;
+        uint32_t word = s.word, op = s.op;
+        const uint32_t* in32 = s.in32;
+        const uint32_t max_word = (s.in_len + 3) / 4 + 1, out_len = s.out_len;     // last byte read <= in_len + 6: inside the promised padding
+        int drop = s.drop, status = kOk, phase = 1;
+#define VTX_REFILL()                                                                                              \
+        do {                                                                                                      \
+            while (bitcnt <= 32) { const uint32_t w_ = word < max_word ? in32[word] : 0u; bitbuf |= uint64_t(w_) << bitcnt; bitcnt += 32; ++word; } \
+            if (drop) { bitbuf >>= drop; bitcnt -= drop; drop = 0; }                                              \
+        } while (0)
+        while (n < cap) {
+            VTX_REFILL();                                        // > 32 valid bits: one literal/length code (<= 15 + 5)
+            uint32_t e = T.lit[uint32_t(bitbuf) & ((1u << kLitBits) - 1)];
+            if ((e & kTypeMask) == kTypeSub) e = T.lit[((e >> 13) & 0x1FFFF) + (uint32_t(bitbuf >> kLitBits) & ((1u << ((e >> 8) & 31)) - 1))];
+            uint32_t l = e & 0xFF;
+            if (l == 0) { status = kBadStream; break; }
+            bitbuf >>= l; bitcnt -= int(l);
+            const uint32_t type = e & kTypeMask;
+            if (type == kTypeLiteral) {
+                if (op >= out_len) { status = kBadSize; break; }
+                batch[n].kind = 0; batch[n].len = 1; batch[n].arg = (e >> 13) & 0xFF; ++n; ++op;
+                continue;
+            }
+            if (type == kTypeEnd) {
+                if ((e >> 13) & 0x1FFFF) { status = kBadStream; break; }           // symbols 286 / 287
+                phase = s.final_block ? 3 : 0;                                      // the next call reads the next header
+                break;
+            }
+            const uint32_t xb = (e >> 8) & 31;
+            const uint32_t length = ((e >> 13) & 0x1FFFF) + (uint32_t(bitbuf) & ((1u << xb) - 1));
+            bitbuf >>= xb; bitcnt -= int(xb);
+            VTX_REFILL();                                        // distance code (<= 15) + extra bits (<= 13)
+            uint32_t d = T.dist[uint32_t(bitbuf) & ((1u << kDistBits) - 1)];
+            if ((d & kTypeMask) == kTypeSub) d = T.dist[((d >> 13) & 0x1FFFF) + (uint32_t(bitbuf >> kDistBits) & ((1u << ((d >> 8) & 31)) - 1))];
+            l = d & 0xFF;
+            if (l == 0 || (d & kTypeMask) != kTypeBase) { status = kBadStream; break; }
+            bitbuf >>= l; bitcnt -= int(l);
+            const uint32_t db = (d >> 8) & 31;
+            const uint32_t distance = ((d >> 13) & 0x1FFFF) + (uint32_t(bitbuf) & ((1u << db) - 1));
+            bitbuf >>= db; bitcnt -= int(db);
+            if (distance > op) { status = kBadDistance; break; }
+            if (uint64_t(op) + length > out_len) { status = kBadSize; break; }
+            batch[n].kind = 1; batch[n].len = length; batch[n].arg = distance; ++n; op += length;
         }
-        if (type == kTypeEnd) {
-            if ((e >> 13) & 0x1FFFF) { s.status = kBadStream; break; }           // symbols 286 / 287
-            if (overrun(s)) { s.status = kOverrun; break; }
-            s.phase = s.final_block ? 3 : 0;
-            continue;
-        }
-        const uint32_t xb = (e >> 8) & 31;
-        const uint32_t length = ((e >> 13) & 0x1FFFF) + uint32_t(s.bitbuf & ((1u << xb) - 1));
-        s.bitbuf >>= xb; s.bitcnt -= int(xb);
-        refill(s);                                           // distance code (<= 15) + extra bits (<= 13)
-        uint32_t d = T.dist[s.bitbuf & ((1u << kDistBits) - 1)];
-        if ((d & kTypeMask) == kTypeSub) d = T.dist[((d >> 13) & 0x1FFFF) + ((s.bitbuf >> kDistBits) & ((1u << ((d >> 8) & 31)) - 1))];
-        l = d & 0xFF;
-        if (l == 0 || (d & kTypeMask) != kTypeBase) { s.status = kBadStream; break; }
-        s.bitbuf >>= l; s.bitcnt -= int(l);
-        const uint32_t db = (d >> 8) & 31;
-        const uint32_t distance = ((d >> 13) & 0x1FFFF) + uint32_t(s.bitbuf & ((1u << db) - 1));
-        s.bitbuf >>= db; s.bitcnt -= int(db);
-        if (distance > s.op) { s.status = kBadDistance; break; }
-        if (uint64_t(s.op) + length > s.out_len) { s.status = kBadSize; break; }
-        batch[n].kind = 1; batch[n].len = length; batch[n].arg = distance; ++n; s.op += length;
+#undef VTX_REFILL
+        s.bitbuf = bitbuf; s.bitcnt = bitcnt; s.word = word; s.op = op; s.drop = drop; s.status = status; s.phase = phase;
+        if (status == kOk && phase != 1 && overrun(s)) s.status = kOverrun;      // at the end of a block the bits consumed lie inside the input
     }
     if (s.phase == 3 && s.status == kOk) {
         if (overrun(s)) s.status = kOverrun;
