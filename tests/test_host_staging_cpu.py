@@ -267,7 +267,10 @@ def _read_vtxd(path):
         row = np.frombuffer(take(), np.uint32); start = np.frombuffer(take(), np.int64); end = np.frombuffer(take(), np.int64)
         members = np.frombuffer(take(), np.dtype([("in_off", "<u8"), ("in_len", "<u4"), ("out_len", "<u4"), ("out_off", "<u8"), ("crc", "<u4"), ("pad", "<u4")]))
         comp = take(); entry = np.frombuffer(take(), np.uint64)
-        out.append(dict(tid=tid, row=row, start=start, end=end, members=members, comp=comp, entry=entry))
+        hap = np.frombuffer(take(), np.uint8); ref_off = np.frombuffer(take(), np.uint32); ref_len = np.frombuffer(take(), np.uint32)
+        alt_off = np.frombuffer(take(), np.uint32); alt_len = np.frombuffer(take(), np.uint32)
+        out.append(dict(tid=tid, row=row, start=start, end=end, members=members, comp=comp, entry=entry, hap=hap, ref_off=ref_off, ref_len=ref_len,
+                        alt_off=alt_off, alt_len=alt_len))
     return out
 
 

@@ -77,6 +77,22 @@ class BgzfBlock(C.Structure):      # vtx_bgzf_block
                 ("crc32", C.c_uint32), ("reserved", C.c_uint32)]
 
 
+class BamShard(C.Structure):       # vtx_bam_shard
+    _fields_ = [
+        ("n_loci", C.c_uint32), ("locus_row", C.c_void_p), ("locus_start", C.c_void_p), ("locus_end", C.c_void_p),
+        ("hap_bytes", C.c_void_p), ("hap_bytes_len", C.c_uint64),
+        ("ref_off", C.c_void_p), ("ref_len", C.c_void_p), ("alt_off", C.c_void_p), ("alt_len", C.c_void_p),
+        ("tid", C.c_int32), ("n_members", C.c_uint32), ("members", C.c_void_p), ("comp", C.c_void_p), ("comp_len", C.c_uint64),
+        ("n_entry", C.c_uint32), ("entry_off", C.c_void_p),
+        ("mapq", C.c_uint32), ("primary_only", C.c_int32), ("no_duplicates", C.c_int32), ("bam_tag", C.c_char * 2),
+    ]
+
+
+class BamMetrics(C.Structure):     # vtx_bam_metrics
+    _fields_ = [("num_reads", C.c_uint64), ("num_low_mapq", C.c_uint64), ("num_non_primary", C.c_uint64),
+                ("num_duplicates", C.c_uint64), ("num_not_useful", C.c_uint64)]
+
+
 class Metrics(C.Structure):
     _fields_ = [("num_not_cell_bc", C.c_uint64), ("num_non_umi", C.c_uint64), ("num_scored", C.c_uint64)]
 
@@ -143,6 +159,10 @@ def load():
     L.vtx_submit2_device.argtypes = [C.c_void_p, C.POINTER(Batch2), C.c_uint32, C.c_uint32]
     L.vtx_bgzf_inflate.restype = C.c_int
     L.vtx_bgzf_inflate.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32]
+    L.vtx_submit_bam.restype = C.c_int
+    L.vtx_submit_bam.argtypes = [C.c_void_p, C.POINTER(BamShard)]
+    L.vtx_bam_metrics_get.restype = C.c_int
+    L.vtx_bam_metrics_get.argtypes = [C.c_void_p, C.POINTER(BamMetrics)]
     L.vtx_pack_cb.restype = C.c_uint64
     L.vtx_pack_cb.argtypes = [C.c_char_p, C.c_uint32]
     L.vtx_gather_start.restype = C.c_int

@@ -518,6 +518,8 @@ int main(int argc, char** argv)
                 put(&tid64, 8);
                 put(ds->locus_row.data(), ds->locus_row.size() * 4); put(ds->locus_start.data(), ds->locus_start.size() * 8); put(ds->locus_end.data(), ds->locus_end.size() * 8);
                 put(ds->members.data(), ds->members.size() * sizeof(vtx_bgzf_block)); put(ds->comp.data(), ds->comp.size()); put(ds->entry_off.data(), ds->entry_off.size() * 8);
+                put(ds->hap_bytes.data(), ds->hap_bytes.size()); put(ds->ref_off.data(), ds->ref_off.size() * 4); put(ds->ref_len.data(), ds->ref_len.size() * 4);
+                put(ds->alt_off.data(), ds->alt_off.size() * 4); put(ds->alt_len.data(), ds->alt_len.size() * 4);
                 continue;
             }
             if (ds) {

@@ -530,6 +530,34 @@ class Engine:
         res = [out[int(blocks[i].out_off): int(blocks[i].out_off) + int(blocks[i].out_len)].tobytes() for i in range(n)]
         return res, status[:n]
 
+    def submit_bam(self, sh: dict, mapq: int = 0, primary_only: bool = False, no_duplicates: bool = False, bam_tag: bytes = b"CB") -> int:
+        """vtx_submit_bam on the host's share of a device-staged shard: dict with tid, row, start, end, hap, ref_off, ref_len,
+        alt_off, alt_len, members (structured array like vtx_bgzf_block), comp (payload bytes followed by 16 bytes of padding) and
+        entry (u64) -- what `vartrix_b200 --gpu-stage --dump-staged` writes.  Returns the ABI code (0, or VTX_E_UNSUPPORTED / VTX_E_INVALID with the message in last_error())."""
+        keep = {k: np.ascontiguousarray(sh[k], dt) for k, dt in (("row", np.uint32), ("start", np.int64), ("end", np.int64), ("hap", np.uint8),
+                ("ref_off", np.uint32), ("ref_len", np.uint32), ("alt_off", np.uint32), ("alt_len", np.uint32), ("entry", np.uint64))}
+        members = np.ascontiguousarray(sh["members"])
+        comp = np.frombuffer(bytes(sh["comp"]), np.uint8)              # payloads + the 16 readable bytes behind them, as dumped
+        P = lambda a: a.ctypes.data if a.size else None
+        b = _capi.BamShard()
+        b.n_loci = len(keep["row"]); b.locus_row = P(keep["row"]); b.locus_start = P(keep["start"]); b.locus_end = P(keep["end"])
+        b.hap_bytes = P(keep["hap"]); b.hap_bytes_len = keep["hap"].size
+        b.ref_off = P(keep["ref_off"]); b.ref_len = P(keep["ref_len"]); b.alt_off = P(keep["alt_off"]); b.alt_len = P(keep["alt_len"])
+        b.tid = int(sh["tid"]); b.n_members = len(members); b.members = P(members); b.comp = comp.ctypes.data; b.comp_len = max(0, comp.size - 16)
+        b.n_entry = len(keep["entry"]); b.entry_off = P(keep["entry"])
+        b.mapq = mapq; b.primary_only = int(primary_only); b.no_duplicates = int(no_duplicates); b.bam_tag = bam_tag[:2]
+        rc = self._L.vtx_submit_bam(self._h, C.byref(b))
+        self._L.vtx_sync(self._h)                     # the arrays above may go away once this returns
+        return rc
+
+    def bam_metrics(self) -> dict:
+        m = _capi.BamMetrics()
+        self._ck(self._L.vtx_bam_metrics_get(self._h, C.byref(m)), "vtx_bam_metrics_get")
+        return {k: int(getattr(m, k)) for k, _ in _capi.BamMetrics._fields_}
+
+    def last_error(self) -> str:
+        return (self._L.vtx_last_error(self._h) or b"").decode()
+
     def fetch(self, dev_res: _capi.Result, copy: bool = True) -> Triplets:
         out = _capi.Result()
         self._ck(self._L.vtx_fetch(self._h, C.byref(dev_res), C.byref(out)), "vtx_fetch")
