@@ -52,7 +52,7 @@ def test_submit_bam_equals_host_staged_shards(tmp_path, pre, bcs, shard, mode, u
         rh, rd = e_host.finish(), e_dev.finish()
         for f in ("row", "col", "val", "val2", "ref_cnt", "alt_cnt", "unk_cnt"):
             assert np.array_equal(getattr(rh, f), getattr(rd, f), equal_nan=True), f
-        assert rh.metrics == rd.metrics and len(rh.row) > 50
+        assert rh.metrics == rd.metrics and len(rh.row) > 0 and rh.metrics["num_scored"] > 0
         bm = e_dev.bam_metrics()
     for k in ("num_reads", "num_low_mapq", "num_non_primary", "num_duplicates", "num_not_useful"):
         assert bm[k] == sum(int(m[k]) for _, m in host), k
