@@ -93,3 +93,18 @@ def test_gzipped_vcf_is_sniffed_not_named(oracle, tmp_path):
     from vartrix_b200.staged_io import read_dump
     n_rows, _, shards = read_dump(str(out))
     assert n_rows == 4 and shards[0][0].n_cand > 0
+
+
+def test_clmul_crc32_equals_zlib(shim):
+    """csrc/host/crc32_fast.hpp (carry-less multiplication, chosen at run time) against zlib.crc32: every length through the
+    16- and 64-byte folding boundaries, three alignments, and BGZF-sized buffers"""
+    import zlib
+    shim.vtx_test_crc32.restype = ctypes.c_uint32
+    shim.vtx_test_crc32.argtypes = [ctypes.c_void_p, ctypes.c_ulong]
+    rng = np.random.default_rng(3)
+    buf = rng.integers(0, 256, size=(1 << 17) + 64, dtype=np.uint8)
+    raw = buf.tobytes()
+    for off in (0, 1, 7):
+        for n in list(range(0, 300)) + [511, 512, 1023, 4096, 65279, 65280, 65535, 65536, 100003]:
+            assert shim.vtx_test_crc32(buf.ctypes.data + off, n) == (zlib.crc32(raw[off:off + n]) & 0xFFFFFFFF), (off, n)
+    assert shim.vtx_test_crc32(buf.ctypes.data, 0) == 0

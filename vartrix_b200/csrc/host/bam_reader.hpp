@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "../../../include/vartrix_b200.h"
+#include "crc32_fast.hpp"
 #include "inflate_fast.hpp"
 
 namespace vtxhost {
@@ -177,7 +178,7 @@ private:
             if (inflate(&zs_, Z_FINISH) != Z_STREAM_END || zs_.total_out != isize) return fail(coff, "inflate failed (corrupt data)");
         }
         const uint64_t t_crc = StageClock::now();
-        if (check_crc_ && uint32_t(crc32(crc32(0L, Z_NULL, 0), v->data.data(), isize)) != crc) return fail(coff, "CRC32 mismatch (corrupt data)");
+        if (check_crc_ && vtx_crc::crc32_of(v->data.data(), isize) != crc) return fail(coff, "CRC32 mismatch (corrupt data)");
         const uint64_t t_end = StageClock::now();
         clk.read_ns += t_inf - t_read; clk.inflate_ns += t_crc - t_inf; clk.crc_ns += t_end - t_crc; clk.blocks += 1; clk.inflated_bytes += isize;
         v->coff = coff; v->next = coff + total; v->len = isize; v->ptr = v->data.data();

@@ -434,7 +434,7 @@ int main(int argc, char** argv)
             sa_w.bulk_inflate = [](const vtx_bgzf_block* b, uint32_t n, const uint8_t* comp, uint64_t, uint8_t* out, uint64_t, std::string* err) {
                 for (uint32_t i = 0; i < n; ++i) {
                     if (b[i].out_len && !vtx_inflate_raw(comp + b[i].in_off, b[i].in_len, out + b[i].out_off, b[i].out_len)) { *err = "member " + std::to_string(i) + ": inflate failed"; return false; }
-                    if (uint32_t(crc32(crc32(0L, Z_NULL, 0), out + b[i].out_off, b[i].out_len)) != b[i].crc32) { *err = "member " + std::to_string(i) + ": CRC32 mismatch"; return false; }
+                    if (vtx_crc::crc32_of(out + b[i].out_off, b[i].out_len) != b[i].crc32) { *err = "member " + std::to_string(i) + ": CRC32 mismatch"; return false; }
                 }
                 return true;
             };
