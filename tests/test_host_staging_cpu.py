@@ -418,3 +418,30 @@ def _check_device_logic(tmp_path, stage_dev, vcf, bam, fa, bcs, shard, extra):
         assert len(set(cand_rec[:int(out.n_cand)].tolist())) == len(set(hb.cand_read.tolist()))
     assert n_checked > 0
     return n_checked
+
+
+@pytest.fixture(scope="module")
+def stage_fuzz(tmp_path_factory):
+    exe = str(tmp_path_factory.mktemp("stagefuzz") / "stage_dev_fuzz")
+    cuda_inc = "/usr/local/cuda/include"
+    if not os.path.isdir(cuda_inc):
+        pytest.skip("CUDA headers not found")
+    r = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=all", "-I", cuda_inc, "-o", exe,
+                        os.path.join(ROOT, "tests", "stage_dev_fuzz.cpp"), "-lz"], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("no sanitizer runtime for g++ here: " + r.stderr[-200:])
+    return exe
+
+
+@pytest.mark.parametrize("pre,bcs,shard,extra,seed", [("test", "barcodes.tsv", "1", ["--umi"], 1), ("test_dna", "dna_barcodes.tsv", "7", [], 2)])
+def test_device_staging_logic_is_memory_safe_on_damaged_input(tmp_path, stage_fuzz, pre, bcs, shard, extra, seed):
+    """tests/stage_dev_fuzz.cpp under AddressSanitizer + UBSan: the staging kernels' bodies over shards whose inflated stream has
+    random bytes overwritten (aimed at record heads half of the time), and the device DEFLATE decoder's bit-stream half over
+    members with flipped bits: nothing is read or written outside the buffers the engine allocates, every symbol stays inside
+    the member's output, and the decoder terminates."""
+    dump = str(tmp_path / "dev.staged")
+    subprocess.run([CLI, "-v", f"{REF_TEST_DIR}/{pre}.vcf", "-b", f"{REF_TEST_DIR}/{pre}.bam", "-f", f"{REF_TEST_DIR}/{pre}.fa", "-c", f"{REF_TEST_DIR}/{bcs}",
+                    "--shard-loci", shard, "--threads", "2", "--gpu-stage", "--dump-staged", dump, *extra], check=True, cwd=str(tmp_path))
+    r = subprocess.run([stage_fuzz, dump, "120", str(seed)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr[-2000:]
+    assert "refused" in r.stdout
