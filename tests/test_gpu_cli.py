@@ -111,3 +111,18 @@ def test_gpu_stage_hands_back_what_it_cannot_key(tmp_path):
     assert outs["dev"][2] == outs["host"][2] and len(outs["host"][2]) >= 5
     assert "staged on the host after the device declined them" in outs["dev"][3]
     assert outs["host"][0].count("\n") > 100
+
+
+@pytest.mark.parametrize("extra", [[], ["--gpu-stage"], ["--gpu-inflate"]])
+def test_cli_with_a_vcf_without_records(oracle, dataset, tmp_path, extra):
+    """main.rs:238-240: zero variants are a warning, the (empty) matrices are still written"""
+    vcf = tmp_path / "none.vcf"
+    vcf.write_text("##fileformat=VCFv4.2\n##contig=<ID=chr1,length=1000000>\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\n")
+    out, ref, var = (str(tmp_path / n) for n in ("out.mtx", "ref.mtx", "variants.txt"))
+    r = subprocess.run([CLI, "-v", str(vcf), "-b", dataset["bam"], "-f", dataset["fasta"], "-c", dataset["barcodes"], "-o", out, "--ref-matrix", ref,
+                        "-s", "coverage", "--out-variants", var, *extra], cwd=str(tmp_path), capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Zero variants found in input VCF" in r.stderr
+    n_cols = len(oracle.load_barcodes(dataset["barcodes"]))
+    empty = oracle.mtx_text(0, n_cols, np.zeros(0, np.uint32), np.zeros(0, np.uint32), np.zeros(0))
+    assert open(out).read() == empty and open(ref).read() == empty and open(var).read() == ""
