@@ -362,7 +362,8 @@ def test_device_staging_logic_matches_host_stager(tmp_path, stage_dev, pre, bcs,
                         f"{REF_TEST_DIR}/{bcs}", shard, extra)
 
 
-@pytest.mark.parametrize("shard,extra", [("40", []), ("13", ["--mapq", "20", "--primary-alignments", "--no-duplicates", "--padding", "80", "--umi"])])
+@pytest.mark.parametrize("shard,extra", [("40", []), ("13", ["--mapq", "20", "--primary-alignments", "--no-duplicates", "--padding", "80", "--umi"]),
+                                         ("1000", ["--shard-bytes", "30000"])])          # shards cut by the compressed bytes of BAM they span
 def test_device_staging_logic_on_synthetic_files(tmp_path, stage_dev, dataset, shard, extra):
     """... on files with multi-allelic / invalid records, reads without a cell tag, duplicates, secondary alignments"""
     n = _check_device_logic(tmp_path, stage_dev, dataset["vcf"], dataset["bam"], dataset["fasta"], dataset["barcodes"], shard, extra)

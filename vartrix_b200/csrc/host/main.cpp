@@ -47,6 +47,7 @@ struct Opts {
     std::string vcf, bam, fasta, barcodes, out_matrix = "out_matrix.mtx", ref_matrix = "ref_matrix.mtx", out_variants, out_barcodes;
     std::string scoring = "consensus", bam_tag = "CB", valid_chars = "ATGCatgc", dump_staged;
     long padding = 100, threads = 1, mapq = 0, device = 0, shard_loci = 0;      // 0: chosen from the number of loci and threads
+    long shard_bytes = 0;       // compressed BAM bytes a shard may span (0: no limit; 192 MB under --gpu-stage)
     std::vector<int> devices;          // --devices: the loci are sharded over these GPUs (contiguous ranges, main.rs:250-254)
     bool primary = false, no_dups = false, umi = false, ref_matrix_given = false, gpu_inflate = false, gpu_stage = false, cut_at_contigs = false;
 };
@@ -78,6 +79,7 @@ void usage()
          "      --shard-loci INT        VCF records per staged shard [up to 2048, fewer for short VCFs]\n"
          "      --gpu-stage             Decode the BAM on the GPU: the host only reads the compressed ranges the loci's index chunks\n"
          "                              span; inflate, record scan, fetch, record filters and tag extraction run on the device\n"
+         "      --shard-bytes INT       End a staged shard when the BAM it spans exceeds INT compressed bytes [192 MB with --gpu-stage]\n"
          "      --cut-at-contigs        End a staged shard where the contig changes (implied by --gpu-stage)\n"
          "      --gpu-inflate           Inflate the BGZF members of every shard on the GPU (one call per shard) instead of on\n"
          "                              the staging threads; for hosts with few cores per GPU\n"
@@ -135,6 +137,7 @@ bool parse(int argc, char** argv, Opts* o)
         else if (a == "--device") o->device = atol(v().c_str());
         else if (a == "--devices") { if (!parse_devices(v(), &o->devices)) { fprintf(stderr, "error: bad --devices list\n"); return false; } }
         else if (a == "--shard-loci") o->shard_loci = atol(v().c_str());
+        else if (a == "--shard-bytes") o->shard_bytes = std::max(0l, atol(v().c_str()));
         else if (a == "--dump-staged") o->dump_staged = v();
         else if (a == "--gpu-inflate") o->gpu_inflate = true;
         else if (a == "--gpu-stage") { o->gpu_stage = true; o->cut_at_contigs = true; }
@@ -372,9 +375,25 @@ int main(int argc, char** argv)
     if (o.shard_loci == 0) o.shard_loci = long(std::min<size_t>(2048, std::max<size_t>(128, recs.size() / (size_t(o.threads) * 10 + 1))));
     // shard k = records [shard_lo[k], shard_lo[k + 1]).  With --gpu-stage (or --cut-at-contigs) a shard also ends where the contig
     // changes, so that every shard of a sorted VCF can be staged on the device (one contig, ascending positions).
+    // A device-staged shard is inflated into one stream (< 4 GiB, vtx_submit_bam) that lives twice in device memory: very deep
+    // data must not put gigabytes into one shard, so a shard also ends when the BAM it spans (BAI linear index, compressed
+    // bytes) exceeds --shard-bytes [192 MB under --gpu-stage: ~0.8 GB inflated at a BAM's usual ratio].
+    if (o.shard_bytes == 0 && o.gpu_stage) o.shard_bytes = 192l << 20;
     std::vector<size_t> shard_lo;
-    for (size_t i = 0, in_shard = 0; i < recs.size(); ++i, ++in_shard) {
-        if (i == 0 || in_shard == size_t(o.shard_loci) || (o.cut_at_contigs && recs[i].chrom != recs[i - 1].chrom)) { shard_lo.push_back(i); in_shard = 0; }
+    {
+        uint64_t span_begin = 0;
+        std::string span_chrom;
+        int span_tid = -1;
+        for (size_t i = 0, in_shard = 0; i < recs.size(); ++i, ++in_shard) {
+            bool cut = i == 0 || in_shard == size_t(o.shard_loci) || (o.cut_at_contigs && recs[i].chrom != recs[i - 1].chrom);
+            uint64_t here = 0;
+            if (o.shard_bytes > 0) {
+                if (recs[i].chrom != span_chrom) { span_chrom = recs[i].chrom; span_tid = b0.tid_of(span_chrom); cut = cut || o.cut_at_contigs; }
+                here = b0.linear_offset(span_tid, recs[i].pos0);
+                if (!cut && in_shard > 0 && here > span_begin && here - span_begin > uint64_t(o.shard_bytes)) cut = true;
+            }
+            if (cut) { shard_lo.push_back(i); in_shard = 0; span_begin = here; }
+        }
     }
     const size_t n_shards = shard_lo.size();
     shard_lo.push_back(recs.size());
